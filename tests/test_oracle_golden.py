@@ -1,0 +1,112 @@
+"""CPU: the oracle restatement agrees with the reference's own outputs (tests/golden)."""
+import numpy as np
+import pytest
+
+from oracle import kriging_oracle as ko
+from conftest import load_golden, relerr
+
+RANDOM_CASES = ["ok_gaussian", "ok_exponential", "ok_matern32", "ok_matern52",
+                "ok_gaussian_trainvar", "ok_gaussian_tunednugget", "ok_composite",
+                "ok_composite_tn_tv", "trend1", "trend2", "kpls", "ok_gaussian_n200_d10"]
+
+
+def _case_kwargs(g):
+    nug = g["nugget"]
+    kw = dict(kernels=[str(k) for k in g["kernel"]], trainvar=bool(g["trainvar"]),
+              fixed_nugget=float(nug) if nug.ndim == 0 else 0.0)
+    if "plscoeff" in g:
+        kw.update(plscoeff=g["plscoeff"], n_princomp=int(g["n_princomp"]))
+    return kw
+
+
+def test_notebook_reference_reproduces_stored_values():
+    """The reference as run here matches the outputs stored in its notebooks."""
+    g = load_golden("krigdemo_nb")
+    st = g["stored"]
+    assert np.allclose(g["theta_log10"], st[:2], atol=5e-8)
+    assert abs(float(g["nll"]) - st[2]) / st[2] < 1e-9
+    assert abs(float(g["loocv_rmse"]) - st[3]) / st[3] < 1e-7
+    assert abs(float(g["rmse_grid"]) - st[4]) / st[4] < 1e-8
+    g = load_golden("sobo_nb")
+    st = g["stored"]
+    assert np.allclose(g["theta_log10"], st[:2], atol=1e-12)
+    assert abs(float(g["nll"]) - st[2]) / st[2] < 1e-12
+    assert abs(float(g["loocv_rmse"]) - st[3]) / st[3] < 1e-9
+
+
+@pytest.mark.parametrize("name", ["krigdemo_nb", "sobo_nb"])
+def test_notebook_nll_and_state(name):
+    g = load_golden(name)
+    fit = ko.nll(g["theta_log10"], g["X_norm"], g["y"], g["F"], full=True)
+    assert abs(fit["NegLnLike"] - float(g["nll"])) / abs(float(g["nll"])) < 1e-10
+    assert relerr(fit["BE"], g["BE"]) < 1e-9
+    assert relerr(fit["SigmaSqr"], g["sigma2"]) < 1e-9
+    assert relerr(fit["U"], g["U"]) < 1e-10
+    assert relerr(fit["Psi"], g["Psi"]) < 1e-13
+    xs = ko.standardize_x(g["xq"], g["lb"], g["ub"])
+    out = ko.predict(xs, g["X_norm"], g["y"], g["F"], np.zeros((1, 2), int), fit)
+    for k in ("pred", "ssqr", "s", "ei", "poi"):
+        assert relerr(out[k], g["p_" + k]) < 1e-8, k
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+def test_random_cases_nll(name):
+    g = load_golden(name)
+    kw = _case_kwargs(g)
+    for b, x in enumerate(g["xpop"]):
+        fit = ko.nll(x, g["X_norm"], g["y"], g["F"], full=True, **kw)
+        assert abs(fit["NegLnLike"] - g["nll"][b]) <= 1e-9 * abs(g["nll"][b]), (name, b)
+        assert relerr(fit["BE"], g["BE"][b]) < 1e-8
+        assert relerr(fit["SigmaSqr"], g["sigma2"][b]) < 1e-9
+    assert relerr(fit["U"], g["U_last"]) < 1e-9
+    assert relerr(fit["Psi"], g["Psi_last"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", [c for c in RANDOM_CASES if not c.startswith("trend")])
+def test_random_cases_predict(name):
+    g = load_golden(name)
+    kw = _case_kwargs(g)
+    fit = ko.nll(g["xpop"][-1], g["X_norm"], g["y"], g["F"], full=True, **kw)
+    xs = ko.standardize_x(g["xq"], g["lb"], g["ub"])
+    out = ko.predict(xs, g["X_norm"], g["y"], g["F"], g["idx"], fit, kernels=kw["kernels"],
+                     plscoeff=kw.get("plscoeff"), limit=float(g["limit"]), limittype=">=")
+    for k in ("pred", "ssqr", "s", "ei", "poi", "pof"):
+        assert relerr(out[k], g["p_" + k]) < 2e-8, (name, k, relerr(out[k], g["p_" + k]))
+
+
+def test_calckernel():
+    g = load_golden("calckernel")
+    for k in ("gaussian", "exponential", "matern32", "matern52"):
+        assert relerr(ko.corr(g["XN"], g["XM"], g["theta"], k), g["K_" + k]) < 1e-14
+    assert relerr(ko.corr(g["XN"], g["XM"], g["theta_h"], "gaussian", g["pls"]), g["K_kpls"]) < 1e-14
+
+
+def test_trend_basis():
+    g = load_golden("trend")
+    for key in [k for k in g if k.startswith("idx_")]:
+        _, o, v = key.split("_")
+        idx = ko.total_order_index(int(o), int(v))
+        assert np.array_equal(idx, g[key].astype(int)), key
+        F = ko.legendre_basis(idx, g["Xs_%s_%s" % (o, v)])
+        assert relerr(F, g["F_%s_%s" % (o, v)]) < 1e-13
+
+
+def test_akmcs_reductions():
+    g = load_golden("akmcs_fourbranch")
+    fit = ko.nll(g["theta_log10"], g["X_norm"], g["y"], g["F"], full=True)
+    xs = ko.standardize_x(g["pop"], g["lb"], g["ub"])
+    out = ko.predict(xs, g["X_norm"], g["y"], g["F"], np.zeros((1, 2), int), fit)
+    assert relerr(out["pred"], g["Gx"]) < 1e-9
+    assert relerr(out["s"], g["sigmaG"]) < 1e-8
+    st = ko.akmcs_stats(out["pred"], out["s"])
+    assert st["n_fail"] == int(g["n_fail"])
+    assert st["n_fail_minus"] == int(g["n_fail_minus"])
+    assert st["n_fail_plus"] == int(g["n_fail_plus"])
+    assert st["argminU"] == int(g["argminU"])
+    assert abs(st["minU"] - float(g["minU"])) < 1e-8 * max(1.0, float(g["minU"]))
+
+
+def test_pls_rotations_match_sklearn_fixture():
+    g = load_golden("kpls")
+    W = ko.pls1_rotations(g["X_norm"], g["y"], int(g["n_princomp"]))
+    assert relerr(W ** 2, g["plscoeff"] ** 2) < 1e-9
