@@ -1,0 +1,274 @@
+"""ctypes binding of libkrigb200.so (include/krigb200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no sm_100
+device is visible when a compute entry point is called, this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libkrigb200.so")
+
+KERNEL_IDS = {"gaussian": 0, "iso_gaussian": 0, "exponential": 1, "matern32": 2, "matern52": 3}
+OUT_IDS = {"pred": 0, "ssqr": 1, "s": 2, "ei": 3, "poi": 4, "pof": 5, "lcb": 6, "ebe": 7, "u": 8,
+           "fpc": 9}
+OUT_COUNT = 10
+NORM_DEFAULT, NORM_STD, NORM_NONE = 0, 1, 2
+TYPE_KRIGING, TYPE_KPLS = 0, 1
+ERR_NOT_PD = 4
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class AcqParams(C.Structure):
+    _fields_ = [("ybest", C.c_double), ("limit", C.c_double), ("limit_sign", C.c_int),
+                ("sigmalcb", C.c_double)]
+
+
+class SweepResult(C.Structure):
+    _fields_ = [("best_val", C.c_double), ("best_idx", C.c_longlong), ("min_u", C.c_double),
+                ("min_u_idx", C.c_longlong), ("n_fail", C.c_longlong), ("n_fail_minus", C.c_longlong),
+                ("n_fail_plus", C.c_longlong), ("n_points", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class KrigB200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("krigb200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+_lib = None
+
+# every symbol include/krigb200.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ("kb_version", C.c_int, []),
+    ("kb_last_error", C.c_char_p, []),
+    ("kb_device_count", C.c_int, []),
+    ("kb_model_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, c_double_p,
+                                  c_double_p, c_double_p, C.c_int, c_int_p, C.c_int, C.c_int, c_double_p]),
+    ("kb_model_destroy", None, [C.c_void_p]),
+    ("kb_model_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("kb_model_sync", C.c_int, [C.c_void_p]),
+    ("kb_nll_batch", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_double, c_double_p,
+                               c_int_p]),
+    ("kb_nll_batch_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                   C.c_void_p, C.c_void_p]),
+    ("kb_nll_batch_extras", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    ("kb_reserve_population", C.c_int, [C.c_void_p, C.c_int]),
+    ("kb_fit_state", C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, C.c_double, c_double_p,
+                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("kb_model_set_trend", C.c_int, [C.c_void_p, c_int_p, C.c_int, C.c_int]),
+    ("kb_model_set_norm", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    ("kb_predict", C.c_int, [C.c_void_p, C.c_longlong, c_double_p, C.POINTER(AcqParams),
+                             C.POINTER(c_double_p), C.c_int, C.POINTER(SweepResult)]),
+    ("kb_predict_dev", C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                                 C.POINTER(AcqParams), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
+                                 C.c_int, C.c_int, c_double_p, c_double_p]),
+    ("kb_measure_peak", C.c_int, [C.c_int, C.c_int, c_double_p]),
+    ("kb_launch_count", C.c_longlong, []),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+
+def load():
+    """Load the shared library (build it first with bayesianopttools_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libkrigb200.so is not built (%s). Run `python -m bayesianopttools_b200.build`; "
+            "the krig-b200 hot path has no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in _SIGNATURES:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise KrigB200Error(status, load().kb_last_error().decode("utf-8", "replace"))
+
+
+def require_gpu():
+    if load().kb_device_count() < 1:
+        raise RuntimeError("krig-b200: no CUDA device visible; this path runs on sm_100a only "
+                           "(there is no CPU fallback)")
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def default_device():
+    return int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("KRIGB200_USE_LOCAL_RANK", "1") == "1" \
+        else 0
+
+
+class DeviceModel:
+    """Owner of one ``kb_model`` handle (device copies of X_norm, y, F + workspaces)."""
+
+    def __init__(self, X_norm, y, F, kernels, model_type="kriging", plscoeff=None, device=None):
+        require_gpu()
+        lib = load()
+        self.X_norm = _f64(X_norm)
+        self.y = _f64(np.asarray(y).reshape(-1))
+        self.n, self.d = self.X_norm.shape
+        self.F = _f64(np.asarray(F).reshape(self.n, -1))
+        self.nind = self.F.shape[1]
+        self.kernels = [k.lower() for k in kernels]
+        for k in self.kernels:
+            if k not in KERNEL_IDS:
+                raise ValueError("Kernel option not available!")
+        ids = np.array([KERNEL_IDS[k] for k in self.kernels], dtype=np.int32)
+        self.model_type = TYPE_KPLS if model_type.lower() == "kpls" else TYPE_KRIGING
+        h, pls = 0, None
+        if self.model_type == TYPE_KPLS:
+            pls = _f64(plscoeff)
+            h = pls.shape[1]
+        self.h = h
+        self.device = default_device() if device is None else int(device)
+        hdl = C.c_void_p()
+        check(lib.kb_model_create(C.byref(hdl), self.device, self.n, self.d, self.nind, _dp(self.X_norm),
+                                  _dp(self.y), _dp(self.F), len(ids), ids.ctypes.data_as(c_int_p),
+                                  self.model_type, h, _dp(pls) if pls is not None else None))
+        self._h = hdl
+        self._lib = lib
+        self.fitted = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- population likelihood ---------------------------------------------
+    def nll_batch(self, xpop, trainvar, fixed_nugget, return_info=False):
+        xpop = _f64(np.atleast_2d(xpop))
+        B, nbhyp = xpop.shape
+        nll = np.empty(B)
+        info = np.zeros(B, dtype=np.int32)
+        check(self._lib.kb_nll_batch(self._h, B, nbhyp, _dp(xpop), int(bool(trainvar)),
+                                     float(fixed_nugget), _dp(nll), info.ctypes.data_as(c_int_p)))
+        return (nll, info) if return_info else nll
+
+    def nll_batch_dev(self, xpop_ptr, B, nbhyp, trainvar, fixed_nugget, nll_ptr, info_ptr=None):
+        check(self._lib.kb_nll_batch_dev(self._h, B, nbhyp, C.c_void_p(xpop_ptr), int(bool(trainvar)),
+                                         float(fixed_nugget), C.c_void_p(nll_ptr),
+                                         C.c_void_p(info_ptr) if info_ptr else None))
+
+    def nll_extras(self, B):
+        beta = np.empty((B, self.nind))
+        s2 = np.empty(B)
+        check(self._lib.kb_nll_batch_extras(self._h, B, _dp(beta), _dp(s2)))
+        return beta, s2
+
+    def reserve_population(self, B):
+        check(self._lib.kb_reserve_population(self._h, int(B)))
+
+    def set_stream(self, cuda_stream):
+        check(self._lib.kb_model_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def sync(self):
+        check(self._lib.kb_model_sync(self._h))
+
+    # -- fit ------------------------------------------------------------------
+    def fit_state(self, x, trainvar, fixed_nugget, want_U=True, want_Psi=True):
+        x = _f64(np.atleast_1d(x))
+        U = np.empty((self.n, self.n)) if want_U else None
+        Psi = np.empty((self.n, self.n)) if want_Psi else None
+        BE = np.empty(self.nind)
+        s2, nll, nug = C.c_double(), C.c_double(), C.c_double()
+        wg = np.empty(len(self.kernels))
+        check(self._lib.kb_fit_state(self._h, _dp(x), len(x), int(bool(trainvar)), float(fixed_nugget),
+                                     _dp(U) if want_U else None, _dp(Psi) if want_Psi else None, _dp(BE),
+                                     C.byref(s2), C.byref(nll), C.byref(nug), _dp(wg)))
+        self.fitted = True
+        return dict(U=U, Psi=Psi, BE=BE.reshape(-1, 1), SigmaSqr=s2.value, NegLnLike=nll.value,
+                    nugget=nug.value, wgkf=wg)
+
+    def set_trend(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        check(self._lib.kb_model_set_trend(self._h, idx.ctypes.data_as(c_int_p), idx.shape[0], idx.shape[1]))
+
+    def set_norm(self, norm_type, p0=None, p1=None):
+        if norm_type == NORM_NONE:
+            check(self._lib.kb_model_set_norm(self._h, NORM_NONE, None, None))
+        else:
+            p0, p1 = _f64(np.asarray(p0).reshape(-1)), _f64(np.asarray(p1).reshape(-1))
+            check(self._lib.kb_model_set_norm(self._h, norm_type, _dp(p0), _dp(p1)))
+
+    # -- predict --------------------------------------------------------------
+    def predict(self, x, outputs=("pred",), acq="pred", ybest=0.0, limit=0.0, limit_sign=1, sigmalcb=0.0,
+                want_result=True):
+        x = _f64(np.atleast_2d(x))
+        m = x.shape[0]
+        if x.shape[1] != self.d:
+            raise ValueError("prediction sites have %d columns, model has %d" % (x.shape[1], self.d))
+        ptrs = (c_double_p * OUT_COUNT)()
+        outs = {}
+        for name in outputs:
+            buf = np.empty(m)
+            outs[name] = buf
+            ptrs[OUT_IDS[name]] = _dp(buf)
+        ap = AcqParams(float(ybest), float(limit), int(limit_sign), float(sigmalcb))
+        res = SweepResult()
+        check(self._lib.kb_predict(self._h, m, _dp(x), C.byref(ap), ptrs, OUT_IDS[acq],
+                                   C.byref(res) if want_result else None))
+        return outs, (res.as_dict() if want_result else None)
+
+    def predict_dev(self, x_ptr, m, idx_offset=0, out_ptrs=None, acq="pred", ybest=0.0, limit=0.0,
+                    limit_sign=1, sigmalcb=0.0, result_ptr=None):
+        ptrs = (C.c_void_p * OUT_COUNT)()
+        for name, p in (out_ptrs or {}).items():
+            ptrs[OUT_IDS[name]] = p
+        ap = AcqParams(float(ybest), float(limit), int(limit_sign), float(sigmalcb))
+        check(self._lib.kb_predict_dev(self._h, int(m), C.c_void_p(x_ptr), int(idx_offset), C.byref(ap),
+                                       ptrs, OUT_IDS[acq], C.c_void_p(result_ptr) if result_ptr else None))
+
+
+def corr_matrix(XN, XM, theta, kernel="gaussian", plscoeff=None, device=None):
+    require_gpu()
+    lib = load()
+    XN, XM, theta = _f64(np.atleast_2d(XN)), _f64(np.atleast_2d(XM)), _f64(np.asarray(theta).reshape(-1))
+    if kernel.lower() not in KERNEL_IDS:
+        raise ValueError("Kernel option not available!")
+    out = np.empty((XN.shape[0], XM.shape[0]))
+    pls, h = None, 0
+    if plscoeff is not None:
+        pls = _f64(plscoeff)
+        h = pls.shape[1]
+    check(lib.kb_corr_matrix(default_device() if device is None else device, XN.shape[0], XM.shape[0],
+                             XN.shape[1], _dp(XN), _dp(XM), _dp(theta), KERNEL_IDS[kernel.lower()], h,
+                             _dp(pls) if pls is not None else None, _dp(out)))
+    return out
+
+
+def measure_peak(which, device=None):
+    require_gpu()
+    v = C.c_double()
+    check(load().kb_measure_peak(default_device() if device is None else device, int(which), C.byref(v)))
+    return v.value
+
+
+def launch_count():
+    return int(load().kb_launch_count())

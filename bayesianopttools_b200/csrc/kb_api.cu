@@ -1,0 +1,681 @@
+// krig-b200: C-ABI (include/krigb200.h) over the sm_100a kernels.
+// Host-side orchestration only: workspace ownership, task-queue construction,
+// stream-ordered launches.  No arithmetic of the hot path happens on the host.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kb_internal.h"
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+#define KB_FAIL(code, ...)                           \
+  do {                                               \
+    char buf_[512];                                  \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);       \
+    g_err = buf_;                                    \
+    return (code);                                   \
+  } while (0)
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      KB_FAIL(KB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct KbPopWs {       // one augmented-matrix workspace (population or fit geometry)
+  KbAugGeom g{};
+  int B_cap = 0;
+  double* aug = nullptr;
+  double* dinv = nullptr;
+  int* flags = nullptr;
+  int epoch = 0;
+  int4* tasks = nullptr;
+  int ntasks = 0, tasks_B = 0;
+  int* counter = nullptr;
+  int* info = nullptr;
+  KbHyper hp{};
+  double *Mbuf = nullptr, *beta = nullptr, *sigma2 = nullptr, *nll = nullptr, *lndet = nullptr;
+  double* xpop = nullptr;
+  int xpop_cap = 0;
+};
+
+struct kb_model {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int num_sms = 148;
+  int n = 0, d = 0, nind = 0, nkernel = 0, model_type = 0, h = 0, kmask = 0, n_pad = 0, nb = 0;
+  std::vector<int> kernel_ids;
+  double *XT = nullptr, *y = nullptr, *F = nullptr, *pls = nullptr;
+  int* kernel_ids_dev = nullptr;
+  KbPopWs pop, fit;
+  // predictor state
+  bool fitted = false;
+  double* AT = nullptr;
+  int ldat = 0, nrows = 0;
+  double* rt = nullptr;
+  double* dense_tmp = nullptr;   // n x n staging for U / Psi export
+  double sigma2 = 0.0;
+  int* idx_dev = nullptr;
+  int maxorder = 0;
+  int norm_type = KB_NORM_NONE;
+  double *p0 = nullptr, *p1 = nullptr;
+  // predict scratch
+  double* psi_scratch = nullptr;
+  double* ex_scratch = nullptr;
+  KbSweepResult* partials = nullptr;
+  KbSweepResult* result_dev = nullptr;
+  int pred_grid = 0;
+  // host-API staging
+  double* stage_x = nullptr;
+  double* stage_out = nullptr;
+  long long stage_pts = 0;
+  int stage_nout = 0;
+};
+
+extern int kb_predict_max_grid(int kmask, int d, int num_sms);
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static KbAugGeom make_geom(int n, int nind, bool fit_mode) {
+  KbAugGeom g{};
+  g.n = n;
+  g.n_pad = round_up(n, KB_TILE);
+  g.nb = g.n_pad / KB_TILE;
+  g.nind = nind;
+  g.q = 1 + nind;
+  g.sb = round_up(g.q, KB_TILE) / KB_TILE;
+  g.ib = fit_mode ? g.nb : 0;
+  g.NT = g.nb + g.sb + g.ib;
+  g.ld = (g.nb + g.sb) * KB_TILE;
+  g.stride = (size_t)g.NT * KB_TILE * g.ld;
+  return g;
+}
+
+// Task queue with one-column look-ahead; every dependency precedes its user.
+static void build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
+  out.clear();
+  struct T3 { int i, k, type; };
+  auto emit = [&](const std::vector<T3>& seg) {
+    for (int b = 0; b < B; ++b)
+      for (const T3& t : seg) out.push_back(make_int4(b, t.i, t.k, t.type));
+  };
+  emit({{0, 0, KB_TASK_DIAG}});
+  for (int k = 0; k < g.nb; ++k) {
+    if (k + 1 < g.NT) emit({{k + 1, k, KB_TASK_OFF}});
+    if (k + 1 < g.nb) emit({{k + 1, k + 1, KB_TASK_DIAG}});
+    std::vector<T3> seg;
+    for (int i = k + 2; i < g.NT; ++i) seg.push_back({i, k, KB_TASK_OFF});
+    emit(seg);
+  }
+  std::vector<T3> seg;
+  for (int kk = g.nb; kk < g.nb + g.sb; ++kk)
+    for (int i = kk; i < g.nb + g.sb; ++i) seg.push_back({i, kk, KB_TASK_SCHUR});
+  emit(seg);
+}
+
+static void free_ws(KbPopWs& w) {
+  cudaFree(w.aug); cudaFree(w.dinv); cudaFree(w.flags); cudaFree(w.tasks); cudaFree(w.counter);
+  cudaFree(w.info); cudaFree(w.hp.gw); cudaFree(w.hp.ith); cudaFree(w.hp.wk); cudaFree(w.hp.eps);
+  cudaFree(w.hp.sigma2); cudaFree(w.hp.nugget); cudaFree(w.Mbuf); cudaFree(w.beta); cudaFree(w.sigma2);
+  cudaFree(w.nll); cudaFree(w.lndet); cudaFree(w.xpop);
+  w = KbPopWs{};
+}
+
+static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
+  if (B <= w.B_cap) {
+    if (w.tasks_B != B) {
+      std::vector<int4> tasks;
+      build_tasks(w.g, B, tasks);
+      CK(cudaMemcpyAsync(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+      w.ntasks = (int)tasks.size();
+      w.tasks_B = B;
+    }
+    return KB_OK;
+  }
+  CK(cudaStreamSynchronize(m->stream));
+  const int epoch = w.epoch;
+  free_ws(w);
+  w.epoch = epoch;
+  w.g = make_geom(m->n, m->nind, fit_mode);
+  const KbAugGeom& g = w.g;
+  const int d = m->d, nind = m->nind;
+  CK(cudaMalloc(&w.aug, sizeof(double) * g.stride * B));
+  CK(cudaMalloc(&w.dinv, sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE));
+  CK(cudaMalloc(&w.flags, sizeof(int) * (size_t)B * g.NT * g.NT));
+  CK(cudaMemset(w.flags, 0, sizeof(int) * (size_t)B * g.NT * g.NT));
+  std::vector<int4> tasks;
+  build_tasks(g, B, tasks);
+  CK(cudaMalloc(&w.tasks, tasks.size() * sizeof(int4)));
+  CK(cudaMemcpy(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  w.ntasks = (int)tasks.size();
+  w.tasks_B = B;
+  CK(cudaMalloc(&w.counter, sizeof(int)));
+  CK(cudaMalloc(&w.info, sizeof(int) * B));
+  CK(cudaMalloc(&w.hp.gw, sizeof(double) * (size_t)B * d));
+  CK(cudaMalloc(&w.hp.ith, sizeof(double) * (size_t)B * d));
+  CK(cudaMalloc(&w.hp.wk, sizeof(double) * B * 4));
+  CK(cudaMalloc(&w.hp.eps, sizeof(double) * B));
+  CK(cudaMalloc(&w.hp.sigma2, sizeof(double) * B));
+  CK(cudaMalloc(&w.hp.nugget, sizeof(double) * B));
+  CK(cudaMalloc(&w.Mbuf, sizeof(double) * (size_t)B * nind * nind));
+  CK(cudaMalloc(&w.beta, sizeof(double) * (size_t)B * nind));
+  CK(cudaMalloc(&w.sigma2, sizeof(double) * B));
+  CK(cudaMalloc(&w.nll, sizeof(double) * B));
+  CK(cudaMalloc(&w.lndet, sizeof(double) * B));
+  w.B_cap = B;
+  return KB_OK;
+}
+
+static kb_status ensure_xpop(KbPopWs& w, int count) {
+  if (count <= w.xpop_cap) return KB_OK;
+  cudaFree(w.xpop);
+  w.xpop = nullptr;
+  CK(cudaMalloc(&w.xpop, sizeof(double) * count));
+  w.xpop_cap = count;
+  return KB_OK;
+}
+
+// decode -> build -> factorise -> reduce, all stream ordered
+static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const double* xpop_dev, int trainvar,
+                              double fixed_nugget, double* nll_dev, double* rt_out) {
+  const int nth = (m->model_type == KB_TYPE_KPLS) ? m->h : m->d;
+  const int rest = nbhyp - nth - (trainvar ? 1 : 0);
+  int has_nugget = 0, has_weights = 0;
+  if (rest == 0) { }
+  else if (rest == 1) has_nugget = 1;
+  else if (rest == m->nkernel) has_weights = 1;
+  else if (rest == m->nkernel + 1) { has_nugget = 1; has_weights = 1; }
+  else KB_FAIL(KB_ERR_INVALID, "hyper-parameter vector of length %d does not match nvar=%d trainvar=%d nkernel=%d "
+               "(likelihood_func.py:121-165)", nbhyp, nth, trainvar, m->nkernel);
+  if (!has_weights && m->nkernel > 1)
+    KB_FAIL(KB_ERR_INVALID, "composite kernel needs %d weights in the hyper-parameter vector", m->nkernel);
+  KbModelDev md{m->n, m->d, m->nind, m->n_pad, m->nb, m->kmask, m->XT, m->y, m->F};
+  CK(kb_launch_decode(m->stream, B, nbhyp, xpop_dev, m->d, nth, trainvar, has_nugget, has_weights,
+                      fixed_nugget, m->nkernel, m->kernel_ids_dev,
+                      (m->model_type == KB_TYPE_KPLS) ? m->pls : nullptr, w.hp));
+  CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug));
+  CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
+  w.epoch += 1;
+  CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.flags, w.epoch, w.tasks, w.ntasks, w.counter,
+                    w.info, m->num_sms));
+  CK(kb_launch_gls(m->stream, w.g, B, w.aug, trainvar, w.hp.sigma2, w.Mbuf, w.beta, w.sigma2, nll_dev,
+                   w.info, rt_out, w.lndet));
+  g_launches += 4;
+  return KB_OK;
+}
+
+// small export kernels live here (pure data movement)
+static __global__ void kb_export_upper_kernel(const double* __restrict__ L, int ld, int n, double* __restrict__ U) {
+  const long long total = (long long)n * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / n), c = (int)(e % n);
+    U[e] = (c >= r) ? L[(size_t)c * ld + r] : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int kb_version(void) { return 100; }
+const char* kb_last_error(void) { return g_err.c_str(); }
+long long kb_launch_count(void) { return g_launches.load(); }
+
+int kb_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, const double* Xnorm,
+                          const double* y, const double* F, int nkernel, const int* kernel_ids,
+                          int model_type, int h, const double* plscoeff) {
+  if (!out || !Xnorm || !y || !F || !kernel_ids) KB_FAIL(KB_ERR_INVALID, "null argument");
+  if (n < 1 || d < 1 || nind < 1 || nkernel < 1 || nkernel > 8) KB_FAIL(KB_ERR_INVALID, "bad sizes");
+  if (d > KB_MAX_D) KB_FAIL(KB_ERR_INVALID, "d=%d exceeds KB_MAX_D=%d", d, KB_MAX_D);
+  if (model_type == KB_TYPE_KPLS && (!plscoeff || h < 1)) KB_FAIL(KB_ERR_INVALID, "KPLS needs plscoeff and h");
+  int ndev = kb_device_count();
+  if (ndev == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: the krig-b200 path has no CPU fallback");
+  if (device < 0 || device >= ndev) KB_FAIL(KB_ERR_INVALID, "device %d out of range (%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    KB_FAIL(KB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+            prop.minor);
+  kb_model* m = new kb_model();
+  m->device = device;
+  m->num_sms = prop.multiProcessorCount;
+  m->n = n; m->d = d; m->nind = nind; m->nkernel = nkernel; m->model_type = model_type; m->h = h;
+  m->n_pad = round_up(n, KB_TILE);
+  m->nb = m->n_pad / KB_TILE;
+  m->kernel_ids.assign(kernel_ids, kernel_ids + nkernel);
+  for (int k = 0; k < nkernel; ++k) {
+    if (kernel_ids[k] < 0 || kernel_ids[k] > 3) { delete m; KB_FAIL(KB_ERR_INVALID, "Kernel option not available!"); }
+    if (model_type == KB_TYPE_KPLS && kernel_ids[k] != KB_GAUSSIAN) {
+      delete m;
+      KB_FAIL(KB_ERR_INVALID, "KPLS supports the gaussian kernel only (kernelfunc.py:43-49)");
+    }
+    m->kmask |= 1 << kernel_ids[k];
+  }
+  CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  double* Xtmp = nullptr;
+  CK(cudaMalloc(&Xtmp, sizeof(double) * (size_t)n * d));
+  CK(cudaMemcpy(Xtmp, Xnorm, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&m->XT, sizeof(double) * (size_t)d * m->n_pad));
+  CK(kb_launch_transpose_pad(m->stream, Xtmp, n, d, m->XT, m->n_pad));
+  g_launches += 1;
+  CK(cudaStreamSynchronize(m->stream));
+  cudaFree(Xtmp);
+  CK(cudaMalloc(&m->y, sizeof(double) * n));
+  CK(cudaMemcpy(m->y, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&m->F, sizeof(double) * (size_t)n * nind));
+  CK(cudaMemcpy(m->F, F, sizeof(double) * (size_t)n * nind, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&m->kernel_ids_dev, sizeof(int) * nkernel));
+  CK(cudaMemcpy(m->kernel_ids_dev, kernel_ids, sizeof(int) * nkernel, cudaMemcpyHostToDevice));
+  if (model_type == KB_TYPE_KPLS) {
+    CK(cudaMalloc(&m->pls, sizeof(double) * (size_t)d * h));
+    CK(cudaMemcpy(m->pls, plscoeff, sizeof(double) * (size_t)d * h, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&m->result_dev, sizeof(KbSweepResult)));
+  *out = m;
+  return KB_OK;
+}
+
+void kb_model_destroy(kb_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  free_ws(m->pop);
+  free_ws(m->fit);
+  cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kernel_ids_dev);
+  cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
+  cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
+  cudaFree(m->result_dev); cudaFree(m->stage_x); cudaFree(m->stage_out);
+  cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+kb_status kb_model_set_stream(kb_model* m, void* cuda_stream) {
+  if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  // caller-owned stream (e.g. torch's current stream); NULL restores the handle's own stream
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  return KB_OK;
+}
+
+kb_status kb_model_sync(kb_model* m) {
+  if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  return KB_OK;
+}
+
+kb_status kb_reserve_population(kb_model* m, int B) {
+  if (!m || B < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(m->device));
+  return ensure_ws(m, m->pop, B, false);
+}
+
+kb_status kb_nll_batch_dev(kb_model* m, int B, int nbhyp, const double* xpop_dev, int trainvar,
+                           double fixed_nugget_log10, double* nll_out_dev, int* info_out_dev) {
+  if (!m || !xpop_dev || !nll_out_dev || B < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(m->device));
+  kb_status s = ensure_ws(m, m->pop, B, false);
+  if (s != KB_OK) return s;
+  s = run_pipeline(m, m->pop, B, nbhyp, xpop_dev, trainvar, fixed_nugget_log10, nll_out_dev, nullptr);
+  if (s != KB_OK) return s;
+  if (info_out_dev)
+    CK(cudaMemcpyAsync(info_out_dev, m->pop.info, sizeof(int) * B, cudaMemcpyDeviceToDevice, m->stream));
+  return KB_OK;
+}
+
+kb_status kb_nll_batch(kb_model* m, int B, int nbhyp, const double* xpop, int trainvar,
+                       double fixed_nugget_log10, double* nll_out, int* info_out) {
+  if (!m || !xpop || !nll_out || B < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(m->device));
+  kb_status s = ensure_ws(m, m->pop, B, false);
+  if (s != KB_OK) return s;
+  s = ensure_xpop(m->pop, B * nbhyp);
+  if (s != KB_OK) return s;
+  CK(cudaMemcpyAsync(m->pop.xpop, xpop, sizeof(double) * B * nbhyp, cudaMemcpyHostToDevice, m->stream));
+  s = run_pipeline(m, m->pop, B, nbhyp, m->pop.xpop, trainvar, fixed_nugget_log10, m->pop.nll, nullptr);
+  if (s != KB_OK) return s;
+  CK(cudaMemcpyAsync(nll_out, m->pop.nll, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
+  if (info_out)
+    CK(cudaMemcpyAsync(info_out, m->pop.info, sizeof(int) * B, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return KB_OK;
+}
+
+kb_status kb_nll_batch_extras(kb_model* m, int B, double* beta_out, double* sigma2_out) {
+  if (!m || B < 1 || B > m->pop.B_cap) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  if (beta_out) CK(cudaMemcpy(beta_out, m->pop.beta, sizeof(double) * (size_t)B * m->nind, cudaMemcpyDeviceToHost));
+  if (sigma2_out) CK(cudaMemcpy(sigma2_out, m->pop.sigma2, sizeof(double) * B, cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
+kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, double fixed_nugget_log10,
+                       double* U, double* Psi, double* BE, double* sigma2, double* nll, double* nugget_out,
+                       double* wgkf_out) {
+  if (!m || !x || nbhyp < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(m->device));
+  kb_status s = ensure_ws(m, m->fit, 1, true);
+  if (s != KB_OK) return s;
+  s = ensure_xpop(m->fit, nbhyp);
+  if (s != KB_OK) return s;
+  const KbAugGeom& g = m->fit.g;
+  const int n = m->n;
+  if (!m->rt) {
+    CK(cudaMalloc(&m->rt, sizeof(double) * g.n_pad));
+    CK(cudaMemset(m->rt, 0, sizeof(double) * g.n_pad));
+  }
+  if (!m->AT) {
+    m->nrows = round_up(g.n_pad + g.q, 128);
+    m->ldat = m->nrows;
+    CK(cudaMalloc(&m->AT, sizeof(double) * (size_t)g.n_pad * m->ldat));
+  }
+  m->fitted = false;
+  CK(cudaMemcpyAsync(m->fit.xpop, x, sizeof(double) * nbhyp, cudaMemcpyHostToDevice, m->stream));
+  s = run_pipeline(m, m->fit, 1, nbhyp, m->fit.xpop, trainvar, fixed_nugget_log10, m->fit.nll, m->rt);
+  if (s != KB_OK) return s;
+  CK(kb_launch_fit_extract(m->stream, g, m->fit.aug, m->rt, m->AT, m->ldat));
+  g_launches += 1;
+  double h_nll = 0.0, h_s2 = 0.0, h_nug = 0.0, h_wk[4];
+  int h_info = 0;
+  CK(cudaMemcpyAsync(&h_nll, m->fit.nll, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(&h_s2, m->fit.sigma2, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(&h_nug, m->fit.hp.nugget, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(h_wk, m->fit.hp.wk, sizeof(double) * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(&h_info, m->fit.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  if (BE) CK(cudaMemcpyAsync(BE, m->fit.beta, sizeof(double) * m->nind, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  if (h_info != 0)
+    KB_FAIL(KB_ERR_NOT_PD, "Matrix is not positive definite (pivot %d); the reference raises LinAlgError at "
+            "likelihood_func.py:175", h_info);
+  m->sigma2 = h_s2;
+  if (sigma2) *sigma2 = h_s2;
+  if (nll) *nll = h_nll;
+  if (nugget_out) *nugget_out = h_nug;
+  if (wgkf_out) {
+    // normalised weight of each listed kernel (likelihood_func.py:139,161).  Kernels listed
+    // twice share the folded weight of their id; report an even split.
+    for (int k = 0; k < m->nkernel; ++k) {
+      int cnt = 0;
+      for (int j = 0; j < m->nkernel; ++j) cnt += (m->kernel_ids[j] == m->kernel_ids[k]);
+      wgkf_out[k] = h_wk[m->kernel_ids[k]] / cnt;
+    }
+  }
+  if (U || Psi) {
+    if (!m->dense_tmp) CK(cudaMalloc(&m->dense_tmp, sizeof(double) * (size_t)n * n));
+    if (U) {
+      kb_export_upper_kernel<<<1184, 256, 0, m->stream>>>(m->fit.aug, g.ld, n, m->dense_tmp);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(U, m->dense_tmp, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+    }
+    if (Psi) {
+      CK(kb_launch_corr_general(m->stream, n, n, m->d, m->XT, m->n_pad, m->XT, m->n_pad, m->fit.hp.gw,
+                                m->fit.hp.ith, m->fit.hp.wk, m->kmask, m->dense_tmp, n));
+      CK(cudaMemcpyAsync(Psi, m->dense_tmp, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+    }
+    g_launches += (U ? 1 : 0) + (Psi ? 1 : 0);
+  }
+  m->fitted = true;
+  return KB_OK;
+}
+
+kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d) {
+  if (!m || !idx || nind != m->nind || d != m->d) KB_FAIL(KB_ERR_INVALID, "trend index shape mismatch");
+  CK(cudaSetDevice(m->device));
+  cudaFree(m->idx_dev);
+  m->idx_dev = nullptr;
+  int maxo = 0;
+  for (int i = 0; i < nind * d; ++i) maxo = idx[i] > maxo ? idx[i] : maxo;
+  m->maxorder = maxo;
+  if (nind == 1 && maxo == 0) return KB_OK;   // ordinary Kriging: constant basis, fast path
+  CK(cudaMalloc(&m->idx_dev, sizeof(int) * (size_t)nind * d));
+  CK(cudaMemcpy(m->idx_dev, idx, sizeof(int) * (size_t)nind * d, cudaMemcpyHostToDevice));
+  return KB_OK;
+}
+
+kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const double* p1) {
+  if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
+  if (norm_type != KB_NORM_NONE && (!p0 || !p1)) KB_FAIL(KB_ERR_INVALID, "normalisation needs two vectors");
+  CK(cudaSetDevice(m->device));
+  m->norm_type = norm_type;
+  if (norm_type == KB_NORM_NONE) return KB_OK;
+  if (!m->p0) CK(cudaMalloc(&m->p0, sizeof(double) * m->d));
+  if (!m->p1) CK(cudaMalloc(&m->p1, sizeof(double) * m->d));
+  CK(cudaMemcpy(m->p0, p0, sizeof(double) * m->d, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(m->p1, p1, sizeof(double) * m->d, cudaMemcpyHostToDevice));
+  return KB_OK;
+}
+
+static kb_status ensure_predict_scratch(kb_model* m) {
+  if (m->psi_scratch) return KB_OK;
+  m->pred_grid = kb_predict_max_grid(m->kmask, m->d, m->num_sms);
+  if (m->pred_grid < 1) KB_FAIL(KB_ERR_CUDA, "predict kernel does not fit on this device (d=%d)", m->d);
+  const int qx = 1 + m->nind;
+  CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * 64));
+  CK(cudaMalloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * 64));
+  CK(cudaMalloc(&m->partials, sizeof(KbSweepResult) * m->pred_grid));
+  return KB_OK;
+}
+
+kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long long idx_offset,
+                         const kb_acq_params* ap, double* const* outs_dev, int acq, KbSweepResult* result_dev) {
+  if (!m || !x_dev || npts < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (!m->fitted) KB_FAIL(KB_ERR_STATE, "predict called before kb_fit_state");
+  if (m->nind > 1 && !m->idx_dev) KB_FAIL(KB_ERR_STATE, "nind > 1 needs kb_model_set_trend");
+  if (acq < 0 || acq >= KB_OUT_COUNT) KB_FAIL(KB_ERR_INVALID, "bad acquisition id");
+  CK(cudaSetDevice(m->device));
+  kb_status s = ensure_predict_scratch(m);
+  if (s != KB_OK) return s;
+  KbPredictArgs a{};
+  a.n = m->n; a.d = m->d; a.nind = m->nind; a.n_pad = m->n_pad; a.kmask = m->kmask;
+  a.XT = m->XT; a.gw = m->fit.hp.gw; a.ith = m->fit.hp.ith; a.wk = m->fit.hp.wk;
+  a.AT = m->AT; a.ldat = m->ldat; a.nrows = m->nrows;
+  a.beta = m->fit.beta; a.LM = m->fit.Mbuf; a.idx = m->idx_dev; a.maxorder = m->maxorder;
+  a.sigma2 = m->sigma2;
+  a.norm_type = m->norm_type; a.p0 = m->p0; a.p1 = m->p1;
+  a.m = npts; a.x = x_dev; a.idx_offset = idx_offset;
+  a.ybest = ap ? ap->ybest : 0.0;
+  a.limit = ap ? ap->limit : 0.0;
+  a.limit_sign = ap ? (ap->limit_sign >= 0 ? 1 : -1) : 1;
+  a.sigmalcb = ap ? ap->sigmalcb : 0.0;
+  a.acq = acq;
+  for (int k = 0; k < KB_OUT_COUNT; ++k) a.out[k] = outs_dev ? outs_dev[k] : nullptr;
+  a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
+  const long long nstrips = (npts + 63) / 64;
+  const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);
+  CK(kb_launch_predict(m->stream, a, grid, result_dev));
+  g_launches += result_dev ? 2 : 1;
+  return KB_OK;
+}
+
+static void merge_result(KbSweepResult& r, const KbSweepResult& q, bool first) {
+  if (first) { r = q; return; }
+  if (q.best_val < r.best_val || (q.best_val == r.best_val && q.best_idx < r.best_idx)) {
+    r.best_val = q.best_val; r.best_idx = q.best_idx;
+  }
+  if (q.min_u < r.min_u || (q.min_u == r.min_u && q.min_u_idx < r.min_u_idx)) {
+    r.min_u = q.min_u; r.min_u_idx = q.min_u_idx;
+  }
+  r.n_fail += q.n_fail; r.n_fail_minus += q.n_fail_minus; r.n_fail_plus += q.n_fail_plus;
+  r.n_points += q.n_points;
+}
+
+kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_params* ap,
+                     double* const* outs, int acq, KbSweepResult* result) {
+  if (!m || !x || npts < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(m->device));
+  int nout = 0;
+  int slot[KB_OUT_COUNT];
+  for (int k = 0; k < KB_OUT_COUNT; ++k) slot[k] = (outs && outs[k]) ? nout++ : -1;
+  const long long chunk = npts < (1LL << 20) ? npts : (1LL << 20);
+  if (chunk > m->stage_pts || nout > m->stage_nout) {
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(m->stage_x); cudaFree(m->stage_out);
+    m->stage_x = m->stage_out = nullptr;
+    const long long cp = chunk > m->stage_pts ? chunk : m->stage_pts;
+    const int no = nout > m->stage_nout ? nout : m->stage_nout;
+    CK(cudaMalloc(&m->stage_x, sizeof(double) * (size_t)cp * m->d));
+    if (no > 0) CK(cudaMalloc(&m->stage_out, sizeof(double) * (size_t)cp * no));
+    m->stage_pts = cp; m->stage_nout = no;
+  }
+  KbSweepResult total{};
+  bool first = true;
+  for (long long off = 0; off < npts; off += chunk) {
+    const long long cur = (npts - off < chunk) ? (npts - off) : chunk;
+    CK(cudaMemcpyAsync(m->stage_x, x + (size_t)off * m->d, sizeof(double) * (size_t)cur * m->d,
+                       cudaMemcpyHostToDevice, m->stream));
+    double* od[KB_OUT_COUNT];
+    for (int k = 0; k < KB_OUT_COUNT; ++k)
+      od[k] = (slot[k] >= 0) ? m->stage_out + (size_t)slot[k] * m->stage_pts : nullptr;
+    kb_status s = kb_predict_dev(m, cur, m->stage_x, off, ap, od, acq, m->result_dev);
+    if (s != KB_OK) return s;
+    for (int k = 0; k < KB_OUT_COUNT; ++k)
+      if (slot[k] >= 0)
+        CK(cudaMemcpyAsync(outs[k] + off, od[k], sizeof(double) * (size_t)cur, cudaMemcpyDeviceToHost, m->stream));
+    KbSweepResult part;
+    CK(cudaMemcpyAsync(&part, m->result_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    merge_result(total, part, first);
+    first = false;
+  }
+  if (result) *result = total;
+  return KB_OK;
+}
+
+kb_status kb_corr_matrix(int device, int n, int mm, int d, const double* XN, const double* XM,
+                         const double* theta, int kernel_id, int h, const double* plscoeff, double* out) {
+  if (!XN || !XM || !theta || !out || n < 1 || mm < 1 || d < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (kernel_id < 0 || kernel_id > 3) KB_FAIL(KB_ERR_INVALID, "Kernel option not available!");
+  if (d > KB_MAX_D) KB_FAIL(KB_ERR_INVALID, "d=%d exceeds KB_MAX_D=%d", d, KB_MAX_D);
+  if (kb_device_count() == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: no CPU fallback");
+  CK(cudaSetDevice(device));
+  const int ldn = round_up(n, KB_TILE), ldm = round_up(mm, KB_TILE);
+  std::vector<double> gw(d), ith(d), wk(4, 0.0);
+  wk[kernel_id] = 1.0;
+  for (int i = 0; i < d; ++i) {
+    if (plscoeff && h > 0) {
+      double s = 0.0;
+      for (int k = 0; k < h; ++k) s += plscoeff[i * h + k] * plscoeff[i * h + k] / (theta[k] * theta[k]);
+      gw[i] = 0.5 * s; ith[i] = 0.0;
+    } else {
+      gw[i] = 0.5 / (theta[i] * theta[i]); ith[i] = 1.0 / theta[i];
+    }
+  }
+  double *dXN = nullptr, *dXM = nullptr, *dXNT = nullptr, *dXMT = nullptr, *dpar = nullptr, *dout = nullptr;
+  cudaStream_t st = nullptr;
+  kb_status rc = KB_OK;
+  auto cleanup = [&]() {
+    cudaFree(dXN); cudaFree(dXM); cudaFree(dXNT); cudaFree(dXMT); cudaFree(dpar); cudaFree(dout);
+  };
+#define CKC(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      char buf_[512];                                                                      \
+      snprintf(buf_, sizeof(buf_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      g_err = buf_; cleanup(); return KB_ERR_CUDA;                                         \
+    }                                                                                      \
+  } while (0)
+  CKC(cudaMalloc(&dXN, sizeof(double) * (size_t)n * d));
+  CKC(cudaMalloc(&dXM, sizeof(double) * (size_t)mm * d));
+  CKC(cudaMalloc(&dXNT, sizeof(double) * (size_t)ldn * d));
+  CKC(cudaMalloc(&dXMT, sizeof(double) * (size_t)ldm * d));
+  CKC(cudaMalloc(&dpar, sizeof(double) * (2 * d + 4)));
+  CKC(cudaMalloc(&dout, sizeof(double) * (size_t)n * mm));
+  CKC(cudaMemcpy(dXN, XN, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dXM, XM, sizeof(double) * (size_t)mm * d, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dpar, gw.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dpar + d, ith.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(dpar + 2 * d, wk.data(), sizeof(double) * 4, cudaMemcpyHostToDevice));
+  CKC(kb_launch_transpose_pad(st, dXN, n, d, dXNT, ldn));
+  CKC(kb_launch_transpose_pad(st, dXM, mm, d, dXMT, ldm));
+  CKC(kb_launch_corr_general(st, n, mm, d, dXNT, ldn, dXMT, ldm, dpar, dpar + d, dpar + 2 * d,
+                             1 << kernel_id, dout, mm));
+  g_launches += 3;
+  CKC(cudaMemcpy(out, dout, sizeof(double) * (size_t)n * mm, cudaMemcpyDeviceToHost));
+#undef CKC
+  cleanup();
+  return rc;
+}
+
+kb_status kb_measure_peak(int device, int which, double* value) {
+  if (!value || which < 0 || which > 2) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (kb_device_count() == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float ms = 0.f;
+  if (which < 2) {
+    double* sink = nullptr;
+    CK(cudaMalloc(&sink, sizeof(double)));
+    const int grid = prop.multiProcessorCount * 4, iters = 20000;
+    CK(kb_launch_peak(nullptr, which, 2000, grid, sink));
+    CK(cudaDeviceSynchronize());
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaEventRecord(e0));
+      CK(kb_launch_peak(nullptr, which, iters, grid, sink));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double per_thread_block = (which == 0) ? (16.0 * 8.0 * 512.0) : (512.0 * 8.0 * 2.0);
+      const double tf = per_thread_block * iters * grid / (ms * 1e-3) / 1e12;
+      if (tf > best) best = tf;
+    }
+    g_launches += 4;
+    cudaFree(sink);
+    *value = best;
+  } else {
+    const size_t bytes = (size_t)1 << 30;
+    double *a = nullptr, *b = nullptr;
+    CK(cudaMalloc(&a, bytes));
+    CK(cudaMalloc(&b, bytes));
+    CK(cudaMemset(a, 0, bytes));
+    CK(cudaMemcpy(b, a, bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaDeviceSynchronize());
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(e0));
+      CK(cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice, nullptr));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double gbs = 2.0 * bytes / (ms * 1e-3) / 1e9;
+      if (gbs > best) best = gbs;
+    }
+    cudaFree(a); cudaFree(b);
+    *value = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+// krig-b200 K1: hyper-parameter decode + correlation-matrix build.
+//
+// Replaces calckernel/gaussian/exponential/matern32/matern52
+// (surrogate_models/supports/kernelfunc.py:4-82) and the Psi assembly +
+// nugget of likelihood()/maincalc (likelihood_func.py:93-102,171), batched over
+// the hyper-parameter population.  Training sites are kept structure-of-arrays
+// (XT[dim][point]) so one 64-point tile of one dimension is a contiguous 512-byte
+// run: each tile is staged into shared memory with 1-D TMA bulk copies
+// (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier, and every thread
+// writes its 4x4 micro-tile with 16-byte stores that coalesce to 256-byte runs.
+#include "kb_common.cuh"
+#include "kb_internal.h"
+
+// ---------------------------------------------------------------------------
+// decode: log10 hyper-parameter rows -> per-dimension weights
+// (likelihood_func.py:71-79, nuggetset :121-165, KPLS fold kernelfunc.py:43-49)
+// ---------------------------------------------------------------------------
+__global__ void kb_decode_kernel(int B, int nbhyp, const double* __restrict__ xpop, int d, int nth,
+                                 int trainvar, int has_nugget, int has_weights, double fixed_nugget,
+                                 int nkernel, const int* __restrict__ kernel_ids,
+                                 const double* __restrict__ pls, KbHyper hp) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const double* x = xpop + (size_t)b * nbhyp;
+  for (int dim = threadIdx.x; dim < d; dim += blockDim.x) {
+    double gw, ith;
+    if (pls == nullptr) {
+      const double th = pow(10.0, x[dim]);
+      ith = 1.0 / th;
+      gw = 0.5 / (th * th);
+    } else {
+      double s = 0.0;
+      for (int k = 0; k < nth; ++k) {
+        const double th = pow(10.0, x[k]);
+        const double w = pls[dim * nth + k];
+        s += (w * w) / (th * th);
+      }
+      gw = 0.5 * s;
+      ith = 0.0;
+    }
+    hp.gw[(size_t)b * d + dim] = gw;
+    hp.ith[(size_t)b * d + dim] = ith;
+  }
+  if (threadIdx.x == 0) {
+    int pos = nth;
+    double s2 = 0.0;
+    if (trainvar) s2 = pow(10.0, x[pos++]);
+    const double nug = has_nugget ? x[pos++] : fixed_nugget;
+    double wk[4] = {0.0, 0.0, 0.0, 0.0};
+    if (has_weights) {
+      double sum = 0.0;
+      for (int j = 0; j < nkernel; ++j) sum += x[pos + j];
+      for (int j = 0; j < nkernel; ++j) wk[kernel_ids[j]] += x[pos + j] / sum;
+    } else {
+      wk[kernel_ids[0]] = 1.0;
+    }
+    for (int j = 0; j < 4; ++j) hp.wk[b * 4 + j] = wk[j];
+    hp.eps[b] = pow(10.0, nug);
+    hp.nugget[b] = nug;
+    hp.sigma2[b] = s2;
+  }
+}
+
+cudaError_t kb_launch_decode(cudaStream_t st, int B, int nbhyp, const double* xpop_dev, int d, int nth,
+                             int trainvar, int has_nugget, int has_weights, double fixed_nugget,
+                             int nkernel, const int* kernel_ids_dev, const double* pls_dev, KbHyper hp) {
+  kb_decode_kernel<<<B, 128, 0, st>>>(B, nbhyp, xpop_dev, d, nth, trainvar, has_nugget, has_weights,
+                                      fixed_nugget, nkernel, kernel_ids_dev, pls_dev, hp);
+  return cudaGetLastError();
+}
+
+// X (n x d row-major) -> XT (d x n_pad), zero padded
+__global__ void kb_transpose_pad_kernel(const double* __restrict__ X, int n, int d,
+                                        double* __restrict__ XT, int n_pad) {
+  const long long total = (long long)d * n_pad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int dim = (int)(e / n_pad), k = (int)(e % n_pad);
+    XT[e] = (k < n) ? X[(size_t)k * d + dim] : 0.0;
+  }
+}
+cudaError_t kb_launch_transpose_pad(cudaStream_t st, const double* X, int n, int d, double* XT, int n_pad) {
+  const long long total = (long long)d * n_pad;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  if (grid < 1) grid = 1;
+  kb_transpose_pad_kernel<<<grid, 256, 0, st>>>(X, n, d, XT, n_pad);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// 64x64 correlation tile.  Thread (tr = tid/16, tc = tid%16) owns rows
+// tr*4 + a (a<4) and columns 2*tc + 32*a2 + e (a2<2, e<2).
+// ---------------------------------------------------------------------------
+template <int MASK>
+__device__ __forceinline__ void kb_corr_tile(const double* __restrict__ sXi, const double* __restrict__ sXj,
+                                             int d, const double* __restrict__ sgw,
+                                             const double* __restrict__ sith, const double* __restrict__ swk,
+                                             double (&out)[4][2][2]) {
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  KbPairAcc acc[4][2][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) kb_pair_init(acc[a][a2][e]);
+  for (int dim = 0; dim < d; ++dim) {
+    const double gw = sgw[dim], ith = sith[dim];
+    double xi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xi[a] = sXi[dim * KB_TILE + tr * 4 + a];
+    double2 xj[2];
+#pragma unroll
+    for (int a2 = 0; a2 < 2; ++a2)
+      xj[a2] = *reinterpret_cast<const double2*>(&sXj[dim * KB_TILE + 2 * tc + 32 * a2]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        kb_pair_dim(acc[a][a2][0], xi[a] - xj[a2].x, gw, ith, MASK);
+        kb_pair_dim(acc[a][a2][1], xi[a] - xj[a2].y, gw, ith, MASK);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) out[a][a2][e] = kb_pair_finish(acc[a][a2][e], swk, MASK);
+}
+
+// Stage XT[:, ti*64 .. +64) and XT[:, tj*64 .. +64) with TMA bulk copies.
+// sX layout: [2][d][64]; bar is a shared mbarrier (one use, parity 0).
+__device__ __forceinline__ void kb_stage_x_tiles(const double* __restrict__ XTi, int ldi, int ti,
+                                                 const double* __restrict__ XTj, int ldj, int tj, int d,
+                                                 double* sX, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    kb_mbar_init(bar, 1);
+    kb_mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    kb_mbar_expect_tx(bar, (uint32_t)(2 * d * KB_TILE * sizeof(double)));
+    for (int dim = 0; dim < d; ++dim) {
+      kb_tma_bulk_g2s(sX + dim * KB_TILE, XTi + (size_t)dim * ldi + (size_t)ti * KB_TILE,
+                      KB_TILE * sizeof(double), bar);
+      kb_tma_bulk_g2s(sX + (d + dim) * KB_TILE, XTj + (size_t)dim * ldj + (size_t)tj * KB_TILE,
+                      KB_TILE * sizeof(double), bar);
+    }
+  }
+  kb_mbar_wait(bar, 0);
+}
+
+// ---------------------------------------------------------------------------
+// Population build of the augmented matrices (one 64x64 tile per CTA).
+// ---------------------------------------------------------------------------
+template <int MASK>
+__global__ void __launch_bounds__(KB_THREADS)
+kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ aug) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sX = reinterpret_cast<double*>(smem_raw);            // [2][d][64]
+  double* sgw = sX + 2 * m.d * KB_TILE;                        // [d]
+  double* sith = sgw + m.d;                                    // [d]
+  double* swk = sith + m.d;                                    // [4]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(swk + 4);
+
+  const int b = blockIdx.y;
+  double* A = aug + (size_t)b * g.stride;
+  const int nR = g.nb * (g.nb + 1) / 2;
+  int t = blockIdx.x;
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+
+  if (t < nR) {
+    // lower-triangular tile (ti, tj), tj <= ti
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    for (int i = threadIdx.x; i < m.d; i += blockDim.x) {
+      sgw[i] = hp.gw[(size_t)b * m.d + i];
+      sith[i] = hp.ith[(size_t)b * m.d + i];
+    }
+    if (threadIdx.x < 4) swk[threadIdx.x] = hp.wk[b * 4 + threadIdx.x];
+    kb_stage_x_tiles(m.XT, m.n_pad, ti, m.XT, m.n_pad, tj, m.d, sX, bar);
+    __syncthreads();
+    double out[4][2][2];
+    kb_corr_tile<MASK>(sX, sX + m.d * KB_TILE, m.d, sgw, sith, swk, out);
+    const double eps = hp.eps[b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int row = ti * KB_TILE + tr * 4 + a;
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const int col = tj * KB_TILE + 2 * tc + 32 * a2;
+        double2 v;
+        double* pv = &v.x;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = col + e;
+          double val;
+          if (row < m.n && c < m.n) val = out[a][a2][e] + ((row == c) ? eps : 0.0);
+          else val = (row == c) ? 1.0 : 0.0;       // identity padding
+          pv[e] = val;
+        }
+        *reinterpret_cast<double2*>(&A[(size_t)row * g.ld + col]) = v;
+      }
+    }
+  } else {
+    // right-hand-side rows: y, F columns (as rows), identity rows (fit mode)
+    t -= nR;
+    const int ncolt = g.nb + g.sb;
+    const int ti = g.nb + t / ncolt, tj = t % ncolt;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = tr * 4 + a;
+      const int row = ti * KB_TILE + r;
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const int col = tj * KB_TILE + 2 * tc + 32 * a2;
+        double2 v;
+        double* pv = &v.x;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = col + e;
+          double val = 0.0;
+          if (c < m.n) {
+            if (ti < g.nb + g.sb) {
+              const int q = (ti - g.nb) * KB_TILE + r;
+              if (q == 0) val = m.y[c];
+              else if (q <= m.nind) val = m.F[(size_t)c * m.nind + (q - 1)];
+            } else {
+              const int qi = (ti - g.nb - g.sb) * KB_TILE + r;
+              if (qi == c) val = 1.0;
+            }
+          }
+          pv[e] = val;
+        }
+        *reinterpret_cast<double2*>(&A[(size_t)row * g.ld + col]) = v;
+      }
+    }
+  }
+}
+
+static size_t kb_corr_smem(int d) {
+  return (size_t)(2 * d * KB_TILE + 2 * d + 4) * sizeof(double) + 16;
+}
+
+#define KB_DISPATCH_MASK(MASKVAR, CALL)                                  \
+  switch (MASKVAR) {                                                     \
+    case 1: { constexpr int M_ = 1; CALL; } break;                       \
+    case 2: { constexpr int M_ = 2; CALL; } break;                       \
+    case 3: { constexpr int M_ = 3; CALL; } break;                       \
+    case 4: { constexpr int M_ = 4; CALL; } break;                       \
+    case 5: { constexpr int M_ = 5; CALL; } break;                       \
+    case 6: { constexpr int M_ = 6; CALL; } break;                       \
+    case 7: { constexpr int M_ = 7; CALL; } break;                       \
+    case 8: { constexpr int M_ = 8; CALL; } break;                       \
+    case 9: { constexpr int M_ = 9; CALL; } break;                       \
+    case 10: { constexpr int M_ = 10; CALL; } break;                     \
+    case 11: { constexpr int M_ = 11; CALL; } break;                     \
+    case 12: { constexpr int M_ = 12; CALL; } break;                     \
+    case 13: { constexpr int M_ = 13; CALL; } break;                     \
+    case 14: { constexpr int M_ = 14; CALL; } break;                     \
+    default: { constexpr int M_ = 15; CALL; } break;                     \
+  }
+
+template <int MASK>
+static cudaError_t kb_build_aug_launch(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B,
+                                       KbHyper hp, double* aug) {
+  const size_t smem = kb_corr_smem(m.d);
+  cudaError_t e = cudaFuncSetAttribute(kb_build_aug_kernel<MASK>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int ntiles = g.nb * (g.nb + 1) / 2 + (g.sb + g.ib) * (g.nb + g.sb);
+  dim3 grid(ntiles, B);
+  kb_build_aug_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(m, g, hp, aug);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_build_aug(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B,
+                                KbHyper hp, double* aug) {
+  cudaError_t err = cudaSuccess;
+  KB_DISPATCH_MASK(m.kmask, err = kb_build_aug_launch<M_>(st, m, g, B, hp, aug));
+  return err;
+}
+
+// ---------------------------------------------------------------------------
+// General (n x m) correlation matrix: calckernel() itself (kernelfunc.py:4-34).
+// XNT is [d][ldn], XMT is [d][ldm], both zero padded to a multiple of 64.
+// ---------------------------------------------------------------------------
+template <int MASK>
+__global__ void __launch_bounds__(KB_THREADS)
+kb_corr_general_kernel(int n, int mcols, int d, const double* __restrict__ XNT, int ldn,
+                       const double* __restrict__ XMT, int ldm, const double* __restrict__ gw,
+                       const double* __restrict__ ith, const double* __restrict__ wk,
+                       double* __restrict__ out, int ldo) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sX = reinterpret_cast<double*>(smem_raw);
+  double* sgw = sX + 2 * d * KB_TILE;
+  double* sith = sgw + d;
+  double* swk = sith + d;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(swk + 4);
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    sgw[i] = gw[i];
+    sith[i] = ith[i];
+  }
+  if (threadIdx.x < 4) swk[threadIdx.x] = wk[threadIdx.x];
+  kb_stage_x_tiles(XNT, ldn, ti, XMT, ldm, tj, d, sX, bar);
+  __syncthreads();
+  double o[4][2][2];
+  kb_corr_tile<MASK>(sX, sX + d * KB_TILE, d, sgw, sith, swk, o);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int row = ti * KB_TILE + tr * 4 + a;
+    if (row >= n) continue;
+#pragma unroll
+    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = tj * KB_TILE + 2 * tc + 32 * a2 + e;
+        if (c < mcols) out[(size_t)row * ldo + c] = o[a][a2][e];
+      }
+  }
+}
+
+template <int MASK>
+static cudaError_t kb_corr_general_launch(cudaStream_t st, int n, int m, int d, const double* XNT, int ldn,
+                                          const double* XMT, int ldm, const double* gw, const double* ith,
+                                          const double* wk, double* out, int ldo) {
+  const size_t smem = kb_corr_smem(d);
+  cudaError_t e = cudaFuncSetAttribute(kb_corr_general_kernel<MASK>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((m + KB_TILE - 1) / KB_TILE, (n + KB_TILE - 1) / KB_TILE);
+  kb_corr_general_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(n, m, d, XNT, ldn, XMT, ldm, gw, ith, wk,
+                                                               out, ldo);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_corr_general(cudaStream_t st, int n, int m, int d, const double* XNT, int ldn,
+                                   const double* XMT, int ldm, const double* gw, const double* ith,
+                                   const double* wk, int kmask, double* out, int ldo) {
+  cudaError_t err = cudaSuccess;
+  KB_DISPATCH_MASK(kmask, err = kb_corr_general_launch<M_>(st, n, m, d, XNT, ldn, XMT, ldm, gw, ith, wk,
+                                                            out, ldo));
+  return err;
+}

@@ -1,0 +1,154 @@
+// krig-b200 K3: GLS / ln-det / sigma^2 / NLL reductions per candidate, and the
+// extraction of the predictor state after a fit.
+//
+// Replaces the tail of maincalc (likelihood_func.py:180-204): with
+// Z = L^-1 [y F] already sitting in the right-hand-side rows of the factorised
+// augmented matrix and  S = -Z^T Z  in its Schur tile (kb_chol.cu),
+//   ln|R| = 2 sum ln L_ii                                 (:180)
+//   BE    = (F'R^-1F)^-1 F'R^-1 y = M^-1 b,  M,b from S   (:183-189)
+//   r~    = L^-1 (y - F BE) = z_y - Z_F BE                (:192-193)
+//   sigma^2 = r~'r~ / n,  NLL = n/2 ln sigma^2 + 1/2 ln|R|   (:201-203)
+//   or the full likelihood with sigma^2 given             (:197-199)
+// All sums are block reductions built on warp shuffles (kb_block_sum).
+#include "kb_common.cuh"
+#include "kb_internal.h"
+
+__global__ void __launch_bounds__(KB_THREADS)
+kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
+              const double* __restrict__ sigma2_in, double* __restrict__ Mbuf,
+              double* __restrict__ beta, double* __restrict__ sigma2_out, double* __restrict__ nll,
+              int* __restrict__ info, double* __restrict__ rt_out, double* __restrict__ lndet_out) {
+  __shared__ double red[32];
+  __shared__ double s_piv;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* A = aug + (size_t)b * g.stride;
+  const int n = g.n, nind = g.nind, ld = g.ld;
+  const size_t rhs0 = (size_t)g.nb * KB_TILE;
+  double* Mb = Mbuf + (size_t)b * nind * nind;
+  double* be = beta + (size_t)b * nind;
+
+  // 1. ln-det from the diagonal of L
+  double part = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) part += log(fabs(A[(size_t)i * ld + i]));
+  const double lndet = 2.0 * kb_block_sum(part, red);
+
+  // 2. normal equations from the Schur tile  S = -Z^T Z
+  for (int e = tid; e < nind * nind; e += blockDim.x) {
+    const int a = e / nind, c = e % nind;
+    if (c <= a) Mb[e] = -A[(rhs0 + 1 + a) * ld + rhs0 + 1 + c];
+  }
+  for (int a = tid; a < nind; a += blockDim.x) be[a] = -A[(rhs0 + 1 + a) * ld + rhs0];
+  __syncthreads();
+
+  // 3. Cholesky of M (nind x nind, lower, in place; nind is 1 for ordinary Kriging)
+  for (int j = 0; j < nind; ++j) {
+    __syncthreads();
+    if (tid == 0) {
+      double dj = Mb[(size_t)j * nind + j];
+      if (!(dj > 0.0)) {
+        atomicCAS(&info[b], 0, g.n_pad + j + 1);
+        dj = 1.0;
+      }
+      s_piv = sqrt(dj);
+      Mb[(size_t)j * nind + j] = s_piv;
+    }
+    __syncthreads();
+    const double inv = 1.0 / s_piv;
+    for (int r = j + 1 + tid; r < nind; r += blockDim.x) Mb[(size_t)r * nind + j] *= inv;
+    __syncthreads();
+    const int rem = nind - 1 - j;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      const int r = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= r) Mb[(size_t)r * nind + c] -= Mb[(size_t)r * nind + j] * Mb[(size_t)c * nind + j];
+    }
+  }
+  // 4. BE = M^-1 b : forward then backward substitution, column oriented
+  for (int j = 0; j < nind; ++j) {
+    __syncthreads();
+    const double xj = be[j] / Mb[(size_t)j * nind + j];
+    __syncthreads();
+    if (tid == 0) be[j] = xj;
+    for (int r = j + 1 + tid; r < nind; r += blockDim.x) be[r] -= Mb[(size_t)r * nind + j] * xj;
+  }
+  for (int j = nind - 1; j >= 0; --j) {
+    __syncthreads();
+    const double xj = be[j] / Mb[(size_t)j * nind + j];
+    __syncthreads();
+    if (tid == 0) be[j] = xj;
+    for (int r = tid; r < j; r += blockDim.x) be[r] -= Mb[(size_t)j * nind + r] * xj;
+  }
+  __syncthreads();
+
+  // 5. r~ = z_y - Z_F BE ;  rr = r~' r~
+  double rr = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    double z = A[rhs0 * ld + i];
+    for (int a = 0; a < nind; ++a) z = fma(-be[a], A[(rhs0 + 1 + a) * ld + i], z);
+    rr = fma(z, z, rr);
+    if (rt_out) rt_out[i] = z;
+  }
+  rr = kb_block_sum(rr, red);
+
+  // 6. NLL
+  if (tid == 0) {
+    double s2, val;
+    const double dn = (double)n;
+    if (trainvar) {
+      s2 = sigma2_in[b];
+      val = 0.5 * lndet + 0.5 * dn * log(2.0 * 3.14159265358979323846) + 0.5 * dn * log(s2) +
+            rr / (2.0 * s2);
+    } else {
+      s2 = rr / dn;
+      val = 0.5 * dn * log(s2) + 0.5 * lndet;
+    }
+    if (info[b] == 0 && !isfinite(val)) info[b] = -1;
+    if (info[b] != 0) val = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+    nll[b] = val;
+    sigma2_out[b] = s2;
+    if (lndet_out) lndet_out[b] = lndet;
+  }
+}
+
+cudaError_t kb_launch_gls(cudaStream_t st, const KbAugGeom& g, int B, const double* aug, int trainvar,
+                          const double* sigma2_in, double* Mbuf, double* beta, double* sigma2_out,
+                          double* nll, int* info, double* rt_out, double* lndet_out) {
+  kb_gls_kernel<<<B, KB_THREADS, 0, st>>>(g, aug, trainvar, sigma2_in, Mbuf, beta, sigma2_out, nll, info,
+                                          rt_out, lndet_out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Predictor state after a fit (B == 1, identity rows present):
+//   E = identity rows after the factorisation = L^-T  (row k, column i >= k)
+//   AT[k][i]            = E[k][i] = L^-1[i][k]                     i <  n_pad
+//   AT[k][n_pad]        = alpha_k = (R^-1 (y - F BE))_k = E[k,:] r~   (prediction.py:209-212)
+//   AT[k][n_pad+1+a]    = (R^-1 F)_{k,a} = E[k,:] z_Fa                (prediction.py:223,225)
+// One warp per row k.
+// ---------------------------------------------------------------------------
+__global__ void kb_fit_extract_kernel(KbAugGeom g, const double* __restrict__ aug,
+                                      const double* __restrict__ rt, double* __restrict__ AT, int ldat) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= g.n_pad) return;
+  const int ld = g.ld, n = g.n;
+  const size_t rhs0 = (size_t)g.nb * KB_TILE;
+  const double* E = aug + ((size_t)(g.nb + g.sb) * KB_TILE + k) * ld;
+  double* out = AT + (size_t)k * ldat;
+  for (int i = lane; i < g.n_pad; i += 32) out[i] = (k < n && i < n) ? E[i] : 0.0;
+  for (int j = 0; j < ldat - g.n_pad; ++j) {
+    double s = 0.0;
+    if (k < n && j < g.q) {
+      const double* v = (j == 0) ? rt : (aug + (rhs0 + j) * ld);
+      for (int i = (k & ~31) + lane; i < n; i += 32) s = fma(E[i], v[i], s);
+      s = kb_warp_sum(s);
+    }
+    if (lane == 0) out[g.n_pad + j] = s;
+  }
+}
+
+cudaError_t kb_launch_fit_extract(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
+                                  double* AT, int ldat) {
+  const int wpb = 8;
+  kb_fit_extract_kernel<<<(g.n_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(g, aug, rt, AT, ldat);
+  return cudaGetLastError();
+}

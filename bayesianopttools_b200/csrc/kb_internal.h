@@ -1,0 +1,114 @@
+// krig-b200 internal declarations shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/krigb200.h"
+
+#ifndef KB_TILE
+#define KB_TILE 64
+#define KB_THREADS 256
+#endif
+#define KB_MAX_D 200  // dimensions the shared-memory X tiles are sized for
+
+// Tile task kinds of the Cholesky task graph (kb_chol.cu).
+enum { KB_TASK_DIAG = 0, KB_TASK_OFF = 1, KB_TASK_SCHUR = 2 };
+
+// Geometry of one augmented matrix  [ R ; rhs rows ]  (row-major, lower tiles only).
+//   tile rows 0..nb-1        : R (n padded to nb*64 with identity)
+//   tile rows nb..nb+sb-1    : y, F columns as ROWS (they become L^-1 [y F]) and,
+//                              in tile columns nb.., the Schur block -Z Z^T
+//   tile rows nb+sb..NT-1    : identity rows (fit mode only) -> L^-T
+struct KbAugGeom {
+  int n, n_pad, nb;   // training points, padded, tile rows of R
+  int nind, q;        // trend columns, q = 1 + nind
+  int sb;             // rhs tile rows that take part in the Schur block
+  int ib;             // identity tile rows (0 in population mode, nb in fit mode)
+  int NT;             // nb + sb + ib
+  int ld;             // (nb + sb) * 64 doubles per row
+  size_t stride;      // doubles per matrix = NT*64*ld
+};
+
+// Per-candidate decoded hyper-parameters (device arrays, B rows each).
+struct KbHyper {
+  double* gw;      // [B][d]   1/(2 theta^2)  (KPLS folded)
+  double* ith;     // [B][d]   1/theta
+  double* wk;      // [B][4]   composite weight per kernel id
+  double* eps;     // [B]      10^nugget
+  double* sigma2;  // [B]      10^x[nth] when trainvar
+  double* nugget;  // [B]      log10 nugget actually used
+};
+
+struct KbModelDev {
+  int n, d, nind, n_pad, nb;
+  int kmask;             // OR of 1<<kernel_id
+  const double* XT;      // [d][n_pad]  training sites, structure-of-arrays, zero padded
+  const double* y;       // [n]
+  const double* F;       // [n][nind]
+};
+
+// --- kb_corr.cu --------------------------------------------------------------
+cudaError_t kb_launch_decode(cudaStream_t st, int B, int nbhyp, const double* xpop_dev, int d, int nth,
+                             int trainvar, int has_nugget, int has_weights, double fixed_nugget,
+                             int nkernel, const int* kernel_ids_dev, const double* pls_dev /*d*h or null*/,
+                             KbHyper hp);
+cudaError_t kb_launch_build_aug(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B,
+                                KbHyper hp, double* aug);
+cudaError_t kb_launch_corr_general(cudaStream_t st, int n, int m, int d, const double* XNT, int ldn,
+                                   const double* XMT, int ldm, const double* gw, const double* ith,
+                                   const double* wk, int kmask, double* out, int ldo);
+cudaError_t kb_launch_transpose_pad(cudaStream_t st, const double* X, int n, int d, double* XT, int n_pad);
+
+// --- kb_chol.cu --------------------------------------------------------------
+cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* aug, double* dinv,
+                           int* flags, int epoch, const int4* tasks, int ntasks, int* counter,
+                           int* info, int num_sms);
+
+// --- kb_gls.cu ---------------------------------------------------------------
+cudaError_t kb_launch_gls(cudaStream_t st, const KbAugGeom& g, int B, const double* aug, int trainvar,
+                          const double* sigma2_in, double* Mbuf, double* beta, double* sigma2_out,
+                          double* nll, int* info, double* rt_out /*[n_pad] or null (B==1)*/,
+                          double* lndet_out);
+cudaError_t kb_launch_fit_extract(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
+                                  double* AT, int ldat);
+
+// --- kb_predict.cu -----------------------------------------------------------
+struct KbPredictArgs {
+  // model
+  int n, d, nind, n_pad, kmask;
+  const double* XT;        // [d][n_pad]
+  const double* gw;        // [d]
+  const double* ith;       // [d]
+  const double* wk;        // [4]
+  const double* AT;        // [n_pad][ldat]  k-major: [L^-T | alpha | R^-1 F | 0]
+  int ldat, nrows;         // nrows = rows of the A operand (multiple of 128)
+  const double* beta;      // [nind]
+  const double* LM;        // [nind][nind] Cholesky factor of F' R^-1 F (lower)
+  const int* idx;          // [nind][d] trend multi-index (null when nind==1 and order 0)
+  int maxorder;
+  double sigma2;
+  // input normalisation: type 0: ((x-p0)/(p1-p0)-0.5)*2 ; type 1: (x-p0)/p1 ; type 2: none
+  int norm_type;
+  const double* p0;
+  const double* p1;
+  // points
+  long long m;
+  const double* x;         // [m][d] raw units (device)
+  long long idx_offset;    // global index of x[0] (multi-GPU shards)
+  // acquisition parameters
+  double ybest, limit, sigmalcb;
+  int limit_sign;          // +1 for '>' '>=' ; -1 for '<' '<='
+  int acq;                 // which output drives the arg-min reduction
+  // outputs (device, each m doubles or null)
+  double* out[KB_OUT_COUNT];
+  // scratch
+  double* psi_scratch;     // [grid][n_pad][64]
+  double* ex_scratch;      // [grid][qx][64]
+  int qx;                  // extra rows (1 + nind)
+  KbSweepResult* partials; // [grid]
+};
+cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev);
+size_t kb_predict_smem_bytes(int d);
+
+// --- kb_peak.cu --------------------------------------------------------------
+cudaError_t kb_launch_peak(cudaStream_t st, int which, int iters, int grid, double* sink);

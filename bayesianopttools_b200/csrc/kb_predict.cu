@@ -1,0 +1,384 @@
+// krig-b200 K4: fused batched predictor / acquisition sweep.
+//
+// Replaces prediction() (surrogate_models/supports/prediction.py:155-289) and the
+// AK-MCS population reductions (reliability_analysis/akmcs.py:208-238) for
+// millions of sites per call.  One persistent CTA handles strips of 64 sites:
+//   A. standardise the sites (samplingplan.py:84-88 / prediction.py:160) and build
+//      the cross-correlation strip psi (n x 64)            (prediction.py:187-201)
+//   B. one DMMA GEMM against the k-major fit state  AT = [L^-T | alpha | R^-1 F]:
+//        rows <  n_pad : v = L^-1 psi, only sum v^2 is kept  (prediction.py:222,224)
+//        row  n_pad    : psi' R^-1 (y - F BE)                (prediction.py:209-212)
+//        rows n_pad+1..: F' R^-1 psi                         (prediction.py:225)
+//      (lower-triangular L^-1: row block I only needs k < 128 (I+1))
+//   C. per site: mean, SSqr, s, EI / PoI / PoF / LCB / EBE / U  (prediction.py:227-285)
+//      and the running arg-min / failure counters (akmcs.py:208-238).
+// psi never leaves L2: the strip lives in a CTA-private scratch slab that is
+// written once and streamed back through a 4-stage cp.async ring.
+#include <float.h>
+
+#include "kb_common.cuh"
+#include "kb_internal.h"
+
+#define PK_MT 64
+#define PK_BM 128
+#define PK_KC 16
+#define PK_STAGES 4
+#define PK_LDA 132
+#define PK_LDB 68
+
+struct KbPredSmem {
+  double a[PK_STAGES][PK_KC][PK_LDA];
+  double b[PK_STAGES][PK_KC][PK_LDB];
+  double vv[4][PK_MT];
+  double red_val[8];
+  long long red_idx[8];
+  double wk[4];
+};
+
+size_t kb_predict_smem_bytes(int d) {
+  return sizeof(KbPredSmem) + (size_t)d * (PK_MT + 2) * sizeof(double);
+}
+
+__device__ __forceinline__ double kb_legendre_on(int o, double x) {
+  // orthonormal Legendre on [-1,1]: P_o(x) * sqrt(2 o + 1)   (trendfunction.py:98-101)
+  double pm = 1.0, p = x;
+  if (o == 0) return 1.0;
+  for (int k = 1; k < o; ++k) {
+    const double pn = ((2 * k + 1) * x * p - k * pm) / (k + 1);
+    pm = p;
+    p = pn;
+  }
+  return p * sqrt(2.0 * o + 1.0);
+}
+
+struct KbRunning {
+  double best_val, min_u;
+  long long best_idx, min_u_idx;
+  long long c0, c1, c2;
+};
+
+template <int MASK>
+__global__ void __launch_bounds__(KB_THREADS)
+kb_predict_kernel(KbPredictArgs P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  KbPredSmem& sm = *reinterpret_cast<KbPredSmem*>(smem_raw);
+  double* xs = reinterpret_cast<double*>(smem_raw + sizeof(KbPredSmem));   // [d][64]
+  double* sgw = xs + P.d * PK_MT;
+  double* sith = sgw + P.d;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wr = warp >> 1, wc = warp & 1;
+  const int n = P.n, d = P.d, n_pad = P.n_pad;
+  double* psi = P.psi_scratch + (size_t)blockIdx.x * n_pad * PK_MT;
+  double* ex = P.ex_scratch + (size_t)blockIdx.x * P.qx * PK_MT;
+
+  for (int i = tid; i < d; i += blockDim.x) {
+    sgw[i] = P.gw[i];
+    sith[i] = P.ith[i];
+  }
+  if (tid < 4) sm.wk[tid] = P.wk[tid];
+
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  KbRunning run;
+  run.best_val = INF; run.min_u = INF;
+  run.best_idx = 0x7fffffffffffffffLL; run.min_u_idx = 0x7fffffffffffffffLL;
+  run.c0 = run.c1 = run.c2 = 0;
+
+  const long long nstrips = (P.m + PK_MT - 1) / PK_MT;
+  for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+    const long long p0 = strip * PK_MT;
+    const int npt = (int)((P.m - p0 < PK_MT) ? (P.m - p0) : PK_MT);
+    __syncthreads();
+    // ---- A1. load + standardise the strip -------------------------------
+    for (int e = tid; e < PK_MT * d; e += blockDim.x) {
+      const int p = e / d, dim = e - p * d;
+      double v = 0.0;
+      if (p < npt) {
+        v = P.x[(size_t)(p0 + p) * d + dim];
+        if (P.norm_type == KB_NORM_DEFAULT) {
+          const double lo = P.p0[dim], hi = P.p1[dim];
+          v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
+        } else if (P.norm_type == KB_NORM_STD) {
+          v = (v - P.p0[dim]) / P.p1[dim];
+        }
+      }
+      xs[dim * PK_MT + p] = v;
+    }
+    __syncthreads();
+    // ---- A2. psi strip -> CTA-private scratch (stays in L2) ---------------
+    {
+      const int p = tid & (PK_MT - 1), kg = tid >> 6;
+      for (int k = kg; k < n_pad; k += KB_THREADS / PK_MT) {
+        double val = 0.0;
+        if (k < n) {
+          KbPairAcc acc;
+          kb_pair_init(acc);
+          for (int dim = 0; dim < d; ++dim)
+            kb_pair_dim(acc, xs[dim * PK_MT + p] - __ldg(&P.XT[(size_t)dim * n_pad + k]), sgw[dim],
+                        sith[dim], MASK);
+          val = kb_pair_finish(acc, sm.wk, MASK);
+        }
+        psi[(size_t)k * PK_MT + p] = val;
+      }
+    }
+    __syncthreads();
+
+    // ---- B. V = AT^T-blocks x psi on the FP64 tensor pipe -----------------
+    double sq[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) sq[ni][0] = sq[ni][1] = 0.0;
+
+    const int nblk = P.nrows / PK_BM;
+    for (int I = 0; I < nblk; ++I) {
+      const int kend = ((I + 1) * PK_BM > n_pad) ? n_pad : (I + 1) * PK_BM;
+      const int nch = kend / PK_KC;
+      const double* Ablk = P.AT + (size_t)I * PK_BM;
+      double acc[4][4][2];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+      auto load_chunk = [&](int c, int stage) {
+        const int k0 = c * PK_KC;
+#pragma unroll
+        for (int j = 0; j < (PK_KC * PK_BM / 2) / KB_THREADS; ++j) {
+          const int idx = tid + j * KB_THREADS;
+          const int kk = idx >> 6, seg = (idx & 63) * 2;
+          kb_cp_async16(&sm.a[stage][kk][seg], Ablk + (size_t)(k0 + kk) * P.ldat + seg);
+        }
+#pragma unroll
+        for (int j = 0; j < (PK_KC * PK_MT / 2) / KB_THREADS; ++j) {
+          const int idx = tid + j * KB_THREADS;
+          const int kk = idx >> 5, seg = (idx & 31) * 2;
+          kb_cp_async16(&sm.b[stage][kk][seg], psi + (size_t)(k0 + kk) * PK_MT + seg);
+        }
+      };
+#pragma unroll
+      for (int s = 0; s < PK_STAGES - 1; ++s) {
+        if (s < nch) load_chunk(s, s);
+        kb_cp_async_commit();
+      }
+      for (int c = 0; c < nch; ++c) {
+        kb_cp_async_wait<PK_STAGES - 2>();
+        __syncthreads();
+        {
+          const int cn = c + PK_STAGES - 1;
+          if (cn < nch) load_chunk(cn, cn % PK_STAGES);
+          kb_cp_async_commit();
+        }
+        const int stg = c % PK_STAGES;
+#pragma unroll
+        for (int ks = 0; ks < PK_KC / 4; ++ks) {
+          double af[4], bf[4];
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) af[mi] = sm.a[stg][ks * 4 + tq][wr * 32 + mi * 8 + gq];
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) bf[ni] = sm.b[stg][ks * 4 + tq][wc * 32 + ni * 8 + gq];
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+      }
+      kb_cp_async_wait<0>();
+      __syncthreads();
+      // block epilogue: squares for L^-1 rows, raw values for the extra rows
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int row = I * PK_BM + wr * 32 + mi * 8 + gq;
+        if (row < n_pad) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            sq[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], sq[ni][0]);
+            sq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], sq[ni][1]);
+          }
+        } else {
+          const int j = row - n_pad;
+          if (j < P.qx) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              const int col = wc * 32 + ni * 8 + 2 * tq;
+              ex[(size_t)j * PK_MT + col] = acc[mi][ni][0];
+              ex[(size_t)j * PK_MT + col + 1] = acc[mi][ni][1];
+            }
+          }
+        }
+      }
+    }
+    // column sums of squares: reduce over the 8 row-groups of the warp, then over wr
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = sq[ni][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (gq == 0) sm.vv[wr][wc * 32 + ni * 8 + 2 * tq + e] = v;
+      }
+    __syncthreads();
+
+    // ---- C. per-site outputs ------------------------------------------------
+    if (tid < PK_MT && tid < npt) {
+      const int p = tid;
+      const double vv = sm.vv[0][p] + sm.vv[1][p] + sm.vv[2][p] + sm.vv[3][p];
+      double fpc, t2;
+      if (P.idx == nullptr) {
+        fpc = P.beta[0];
+        const double u = (ex[PK_MT + p] - 1.0) / P.LM[0];
+        t2 = u * u;
+      } else {
+        fpc = 0.0;
+        t2 = 0.0;
+        const int nind = P.nind;
+        for (int a = 0; a < nind; ++a) {
+          double pc = 1.0;
+          for (int dim = 0; dim < d; ++dim) {
+            const int o = P.idx[a * d + dim];
+            if (o) pc *= kb_legendre_on(o, xs[dim * PK_MT + p]);
+          }
+          fpc = fma(pc, P.beta[a], fpc);
+          double u = ex[(size_t)(1 + a) * PK_MT + p] - pc;
+          for (int c = 0; c < a; ++c) u = fma(-P.LM[(size_t)a * nind + c], ex[(size_t)(1 + c) * PK_MT + p], u);
+          u /= P.LM[(size_t)a * nind + a];
+          ex[(size_t)(1 + a) * PK_MT + p] = u;   // w = LM^-1 u, in place
+          t2 = fma(u, u, t2);
+        }
+      }
+      const double f = fpc + ex[p];
+      const double ssqr = P.sigma2 * ((1.0 - vv) + t2);
+      const double s = sqrt(fabs(ssqr));
+      const double diff = P.ybest - f;
+      const double z = diff / s;
+      const double cdf = 0.5 + 0.5 * erf(0.7071067811865475 * z);
+      const double ei = -(diff * cdf + s / 2.5066282746310002 * exp(-0.5 * (diff * diff) / ssqr) + DBL_MIN);
+      const double poi = -cdf;
+      const double pof = 0.5 + 0.5 * erf(0.7071067811865475 * ((double)P.limit_sign * (f - P.limit) / s));
+      const double lcb = f - P.sigmalcb * ssqr;
+      const double U = fabs(f) / s;
+      const long long gi = p0 + p;
+      double vals[KB_OUT_COUNT];
+      vals[KB_OUT_PRED] = f; vals[KB_OUT_SSQR] = ssqr; vals[KB_OUT_S] = s; vals[KB_OUT_EI] = ei;
+      vals[KB_OUT_POI] = poi; vals[KB_OUT_POF] = pof; vals[KB_OUT_LCB] = lcb; vals[KB_OUT_EBE] = -ssqr;
+      vals[KB_OUT_U] = U; vals[KB_OUT_FPC] = fpc;
+#pragma unroll
+      for (int k = 0; k < KB_OUT_COUNT; ++k)
+        if (P.out[k]) P.out[k][gi] = vals[k];
+      double av = vals[KB_OUT_PRED];
+#pragma unroll
+      for (int k = 0; k < KB_OUT_COUNT; ++k)
+        if (P.acq == k) av = vals[k];
+      const long long ggi = gi + P.idx_offset;
+      if (av < run.best_val) { run.best_val = av; run.best_idx = ggi; }
+      if (U < run.min_u) { run.min_u = U; run.min_u_idx = ggi; }
+      run.c0 += (f <= 0.0);
+      run.c1 += (f - 1.96 * s <= 0.0);
+      run.c2 += (f + 1.96 * s <= 0.0);
+    }
+  }
+
+  // ---- CTA partial: (min, lowest index) + counters over threads 0..63 ------
+  __syncthreads();
+  if (warp < 2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, run.best_val, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, run.best_idx, o);
+      if (ov < run.best_val || (ov == run.best_val && oi < run.best_idx)) { run.best_val = ov; run.best_idx = oi; }
+      const double uv = __shfl_xor_sync(0xffffffffu, run.min_u, o);
+      const long long ui = __shfl_xor_sync(0xffffffffu, run.min_u_idx, o);
+      if (uv < run.min_u || (uv == run.min_u && ui < run.min_u_idx)) { run.min_u = uv; run.min_u_idx = ui; }
+      run.c0 += __shfl_xor_sync(0xffffffffu, run.c0, o);
+      run.c1 += __shfl_xor_sync(0xffffffffu, run.c1, o);
+      run.c2 += __shfl_xor_sync(0xffffffffu, run.c2, o);
+    }
+    if (lane == 0) {
+      sm.red_val[warp * 2] = run.best_val; sm.red_idx[warp * 4] = run.best_idx;
+      sm.red_val[warp * 2 + 1] = run.min_u; sm.red_idx[warp * 4 + 1] = run.min_u_idx;
+      sm.red_idx[warp * 4 + 2] = run.c0; sm.red_idx[warp * 4 + 3] = run.c1;
+      sm.red_val[4 + warp] = (double)run.c2;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    KbSweepResult r;
+    r.best_val = sm.red_val[0]; r.best_idx = sm.red_idx[0];
+    if (sm.red_val[2] < r.best_val || (sm.red_val[2] == r.best_val && sm.red_idx[4] < r.best_idx)) {
+      r.best_val = sm.red_val[2]; r.best_idx = sm.red_idx[4];
+    }
+    r.min_u = sm.red_val[1]; r.min_u_idx = sm.red_idx[1];
+    if (sm.red_val[3] < r.min_u || (sm.red_val[3] == r.min_u && sm.red_idx[5] < r.min_u_idx)) {
+      r.min_u = sm.red_val[3]; r.min_u_idx = sm.red_idx[5];
+    }
+    r.n_fail = sm.red_idx[2] + sm.red_idx[6];
+    r.n_fail_minus = sm.red_idx[3] + sm.red_idx[7];
+    r.n_fail_plus = (long long)(sm.red_val[4] + sm.red_val[5]);
+    r.n_points = 0;
+    P.partials[blockIdx.x] = r;
+  }
+}
+
+// Deterministic final reduction over the per-CTA partials (lowest index on ties).
+__global__ void kb_sweep_final_kernel(const KbSweepResult* __restrict__ partials, int nparts,
+                                      long long npoints, KbSweepResult* __restrict__ result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  KbSweepResult r = partials[0];
+  for (int i = 1; i < nparts; ++i) {
+    const KbSweepResult q = partials[i];
+    if (q.best_val < r.best_val || (q.best_val == r.best_val && q.best_idx < r.best_idx)) {
+      r.best_val = q.best_val; r.best_idx = q.best_idx;
+    }
+    if (q.min_u < r.min_u || (q.min_u == r.min_u && q.min_u_idx < r.min_u_idx)) {
+      r.min_u = q.min_u; r.min_u_idx = q.min_u_idx;
+    }
+    r.n_fail += q.n_fail; r.n_fail_minus += q.n_fail_minus; r.n_fail_plus += q.n_fail_plus;
+  }
+  r.n_points = npoints;
+  *result = r;
+}
+
+template <int MASK>
+static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  kb_predict_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+#define KB_DISPATCH_MASK_P(MASKVAR, CALL)                                \
+  switch (MASKVAR) {                                                     \
+    case 1: { constexpr int M_ = 1; CALL; } break;                       \
+    case 2: { constexpr int M_ = 2; CALL; } break;                       \
+    case 4: { constexpr int M_ = 4; CALL; } break;                       \
+    case 8: { constexpr int M_ = 8; CALL; } break;                       \
+    default: { constexpr int M_ = 15; CALL; } break;                     \
+  }
+
+cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {
+  const size_t smem = kb_predict_smem_bytes(a.d);
+  cudaError_t err = cudaSuccess;
+  KB_DISPATCH_MASK_P(a.kmask, err = kb_predict_launch<M_>(st, a, grid, smem));
+  if (err != cudaSuccess) return err;
+  if (result_dev) {
+    kb_sweep_final_kernel<<<1, 32, 0, st>>>(a.partials, grid, a.m, result_dev);
+    err = cudaGetLastError();
+  }
+  return err;
+}
+
+// Largest persistent grid for the predict kernel: SMs x resident CTAs per SM.
+int kb_predict_max_grid(int kmask, int d, int num_sms) {
+  const size_t smem = kb_predict_smem_bytes(d);
+  int occ = 0;
+  cudaError_t err = cudaSuccess;
+  KB_DISPATCH_MASK_P(kmask, {
+    err = cudaFuncSetAttribute(kb_predict_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess)
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_>, KB_THREADS, smem);
+  });
+  if (err != cudaSuccess) { cudaGetLastError(); return 0; }
+  return occ * num_sms;
+}

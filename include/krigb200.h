@@ -1,0 +1,141 @@
+/* krigb200.h -- C-ABI of libkrigb200.so: the B200 (sm_100a) Kriging hot path.
+ *
+ * The reference (fazaghifari/BayesianOptTools, "KADAL") is pure Python and has
+ * no FFI; its operator surface for this path is the set of Python callables
+ * cited at each entry point below.  A maintainer binds these symbols with
+ * ctypes.  Conventions:
+ *   - plain C, int status return (KB_OK == 0), no exceptions cross the boundary;
+ *     kb_last_error() gives the message of the last failure on this thread
+ *   - the caller owns every host buffer; the library owns all device memory
+ *     behind the opaque kb_model handle
+ *   - one handle is used from one host thread at a time; one CUDA stream per
+ *     handle (kb_model_set_stream); entry points named *_dev take DEVICE
+ *     pointers, enqueue on the handle's stream and do not synchronise
+ *   - all matrices are row-major FP64 (numpy default)
+ */
+#ifndef KRIGB200_H
+#define KRIGB200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb_model kb_model;
+typedef int kb_status;
+
+enum {
+  KB_OK = 0,
+  KB_ERR_INVALID = 1,   /* bad argument */
+  KB_ERR_CUDA = 2,      /* CUDA runtime error (message in kb_last_error) */
+  KB_ERR_STATE = 3,     /* e.g. predict before fit */
+  KB_ERR_NOT_PD = 4     /* correlation matrix not positive definite (fit only) */
+};
+
+/* kernel ids: surrogate_models/supports/kernelfunc.py:22-33 */
+enum { KB_GAUSSIAN = 0, KB_EXPONENTIAL = 1, KB_MATERN32 = 2, KB_MATERN52 = 3 };
+/* model types: KrigInfo["type"], likelihood_func.py:93,98 */
+enum { KB_TYPE_KRIGING = 0, KB_TYPE_KPLS = 1 };
+/* input normalisation of prediction sites: prediction.py:155-160 */
+enum { KB_NORM_DEFAULT = 0, KB_NORM_STD = 1, KB_NORM_NONE = 2 };
+
+/* predictor outputs: prediction.py:238-285; U = |pred|/s is akmcs.py:223 */
+enum {
+  KB_OUT_PRED = 0, KB_OUT_SSQR = 1, KB_OUT_S = 2, KB_OUT_EI = 3, KB_OUT_POI = 4,
+  KB_OUT_POF = 5, KB_OUT_LCB = 6, KB_OUT_EBE = 7, KB_OUT_U = 8, KB_OUT_FPC = 9,
+  KB_OUT_COUNT = 10
+};
+
+typedef struct {
+  double ybest;      /* min(y) of the training responses, prediction.py:249,272 */
+  double limit;      /* KrigInfo["limit"], prediction.py:275-285 */
+  int limit_sign;    /* +1 for '>' '>=', -1 for '<' '<=' */
+  double sigmalcb;   /* KrigInfo["sigmalcb"], prediction.py:245 */
+} kb_acq_params;
+
+/* Reduce-only results of a sweep over a point set (akmcs.py:208-238, np.argmin
+ * over the acquisition in acquifunc_opt.py:74-76).  Indices are GLOBAL point
+ * indices (idx_offset + local); ties resolve to the lowest index (np.argmin). */
+typedef struct {
+  double best_val;          /* min of the selected output */
+  long long best_idx;
+  double min_u;             /* min |pred|/s */
+  long long min_u_idx;
+  long long n_fail;         /* #{pred <= 0}              akmcs.py:209 */
+  long long n_fail_minus;   /* #{pred - 1.96 s <= 0}     akmcs.py:230,232 */
+  long long n_fail_plus;    /* #{pred + 1.96 s <= 0}     akmcs.py:231,233 */
+  long long n_points;
+} KbSweepResult;
+
+int kb_version(void);
+const char* kb_last_error(void);
+int kb_device_count(void);
+
+/* Create a model for one design.  Replaces the state set up by
+ * Kriging.__init__/standardize (kriging_model.py:54-167) and KPLS.standardize
+ * (kpls_model.py:93-108): Xnorm (n x d), y (n), F (n x nind) are the
+ * standardised design, responses and regression matrix; kernel_ids[nkernel] the
+ * composite kernel list; for KB_TYPE_KPLS plscoeff is (d x h). */
+kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, const double* Xnorm,
+                          const double* y, const double* F, int nkernel, const int* kernel_ids,
+                          int model_type, int h, const double* plscoeff);
+void kb_model_destroy(kb_model* m);
+kb_status kb_model_set_stream(kb_model* m, void* cuda_stream);
+kb_status kb_model_sync(kb_model* m);
+
+/* Population-batched negative ln-likelihood.  Replaces `likelihood(x, KrigInfo,
+ * 'default', trainvar)` (likelihood_func.py:6-118, maincalc :168-213) called once
+ * per candidate by the optimisers (kriging_model.py:420-446, uncGA.py:46-136).
+ * xpop is (B x nbhyp) log10 values laid out as nuggetset decodes them
+ * (likelihood_func.py:121-165): [theta | sigma2? | nugget? | weights?].
+ * info_out[b] = 0, or k>0 when pivot k of the Cholesky was not positive (then
+ * nll_out[b] = +inf; the reference raises LinAlgError at likelihood_func.py:175). */
+kb_status kb_nll_batch(kb_model* m, int B, int nbhyp, const double* xpop, int trainvar,
+                       double fixed_nugget_log10, double* nll_out, int* info_out);
+kb_status kb_nll_batch_dev(kb_model* m, int B, int nbhyp, const double* xpop_dev, int trainvar,
+                           double fixed_nugget_log10, double* nll_out_dev, int* info_out_dev);
+/* Optional per-candidate by-products of the last kb_nll_batch call (host copies). */
+kb_status kb_nll_batch_extras(kb_model* m, int B, double* beta_out /*B x nind*/, double* sigma2_out /*B*/);
+/* Size the population workspace once (avoids allocation inside a timed region). */
+kb_status kb_reserve_population(kb_model* m, int B);
+
+/* `likelihood(x, KrigInfo, mode='all')` (likelihood_func.py:107-116): factorise
+ * at one hyper-parameter vector and keep the predictor state on the device.
+ * Any of U (n x n upper, = L^T), Psi (n x n, WITHOUT nugget, :108), BE (nind),
+ * sigma2, nll, theta_out (d-vector of length scales actually used), may be NULL. */
+kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, double fixed_nugget_log10,
+                       double* U, double* Psi, double* BE, double* sigma2, double* nll, double* nugget_out,
+                       double* wgkf_out /*nkernel*/);
+
+/* Trend multi-index for prediction sites (trendfunction.py:7-41,70-107):
+ * idx (nind x d) ints, Legendre basis on [-1,1].  Needed when nind > 1. */
+kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d);
+
+/* Input normalisation of prediction sites: KB_NORM_DEFAULT p0=lb,p1=ub
+ * (samplingplan.py:84-88); KB_NORM_STD p0=X_mean,p1=X_std (prediction.py:160). */
+kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const double* p1);
+
+/* Batched predictor.  Replaces `prediction(x, KrigInfo, predtypes)`
+ * (prediction.py:67-298): x is (m x d) in RAW units; outs[k] (k = KB_OUT_*) is a
+ * buffer of m doubles or NULL.  result (may be NULL) receives the reductions
+ * with `acq` (a KB_OUT_* id) selecting the arg-min output. */
+kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_params* acq_params,
+                     double* const* outs, int acq, KbSweepResult* result);
+kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long long idx_offset,
+                         const kb_acq_params* acq_params, double* const* outs_dev, int acq,
+                         KbSweepResult* result_dev);
+
+/* `calckernel(XN, XM, theta, nvar, type=, plscoeff=)` (kernelfunc.py:4-34):
+ * out is (n x m).  For KPLS pass theta of length h and plscoeff (d x h). */
+kb_status kb_corr_matrix(int device, int n, int m, int d, const double* XN, const double* XM,
+                         const double* theta, int kernel_id, int h, const double* plscoeff, double* out);
+
+/* Roofline denominators measured on this device: which = 0 DMMA (mma.sync f64),
+ * 1 scalar DFMA, 2 device-to-device copy.  Returns TFLOP/s (0,1) or GB/s (2). */
+kb_status kb_measure_peak(int device, int which, double* value);
+
+/* Kernel launches issued by this library since process start (bench "gpu_launches"). */
+long long kb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRIGB200_H */

@@ -1,0 +1,217 @@
+"""GPU parity: the sm_100a path (through the C-ABI, ctypes) vs the CPU oracle and
+vs the reference's own outputs stored in tests/golden.
+
+Tolerances (BASELINE.json north_star): relative <= 1e-9 on log-likelihood, mean and
+variance -- measured scale-relative (max|a-b| / max|b|) -- and
+identical arg-min indices and failure counts.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+from oracle import kriging_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+RANDOM_CASES = ["ok_gaussian", "ok_exponential", "ok_matern32", "ok_matern52",
+                "ok_gaussian_trainvar", "ok_gaussian_tunednugget", "ok_composite",
+                "ok_composite_tn_tv", "trend1", "trend2", "kpls", "ok_gaussian_n200_d10"]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bayesianopttools_b200 import _lib
+    _lib.require_gpu()
+    return _lib
+
+
+def _case_kwargs(g):
+    nug = g["nugget"]
+    kw = dict(kernels=[str(k) for k in g["kernel"]], trainvar=bool(g["trainvar"]),
+              fixed_nugget=float(nug) if nug.ndim == 0 else 0.0)
+    if "plscoeff" in g:
+        kw.update(plscoeff=g["plscoeff"], n_princomp=int(g["n_princomp"]))
+    return kw
+
+
+def _model(lib, g, kw):
+    return lib.DeviceModel(g["X_norm"], g["y"], g["F"], kw["kernels"],
+                           model_type="kpls" if "plscoeff" in kw else "kriging",
+                           plscoeff=kw.get("plscoeff"))
+
+
+def test_calckernel_matches_reference(lib):
+    g = load_golden("calckernel")
+    for k in ("gaussian", "exponential", "matern32", "matern52"):
+        out = lib.corr_matrix(g["XN"], g["XM"], g["theta"], k)
+        assert relerr(out, g["K_" + k]) < 1e-13, k
+    out = lib.corr_matrix(g["XN"], g["XM"], g["theta_h"], "gaussian", plscoeff=g["pls"])
+    assert relerr(out, g["K_kpls"]) < 1e-13
+
+
+def test_calckernel_ragged_shapes(lib):
+    rng = np.random.default_rng(0)
+    for n, m, d in ((1, 1, 1), (3, 130, 2), (65, 64, 7), (200, 129, 33)):
+        XN, XM = rng.uniform(-1, 1, (n, d)), rng.uniform(-1, 1, (m, d))
+        th = 10.0 ** rng.uniform(-0.3, 0.3, d)
+        for k in ("gaussian", "matern52"):
+            assert relerr(lib.corr_matrix(XN, XM, th, k), ko.corr(XN, XM, th, k)) < 1e-13
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+def test_nll_population_matches_reference(lib, name):
+    g = load_golden(name)
+    kw = _case_kwargs(g)
+    mdl = _model(lib, g, kw)
+    nll, info = mdl.nll_batch(g["xpop"], kw["trainvar"], kw["fixed_nugget"], return_info=True)
+    assert np.all(info == 0)
+    assert np.max(np.abs(nll - g["nll"]) / np.abs(g["nll"])) < TOL, (nll, g["nll"])
+    beta, s2 = mdl.nll_extras(len(nll))
+    assert relerr(beta, g["BE"]) < 1e-8
+    assert relerr(s2, g["sigma2"]) < TOL
+    # a second call re-uses the workspace (flag epochs) and must reproduce bit-for-bit
+    nll2 = mdl.nll_batch(g["xpop"], kw["trainvar"], kw["fixed_nugget"])
+    assert np.array_equal(nll, nll2)
+    # sub-population (task list rebuilt for smaller B)
+    nll3 = mdl.nll_batch(g["xpop"][:2], kw["trainvar"], kw["fixed_nugget"])
+    assert np.array_equal(nll3, nll[:2])
+    mdl.close()
+
+
+@pytest.mark.parametrize("name", ["krigdemo_nb", "sobo_nb"])
+def test_notebook_golden_fit_and_predict(lib, name):
+    g = load_golden(name)
+    mdl = lib.DeviceModel(g["X_norm"], g["y"], g["F"], ["gaussian"])
+    st = mdl.fit_state(g["theta_log10"], False, -6.0)
+    assert abs(st["NegLnLike"] - float(g["nll"])) / abs(float(g["nll"])) < TOL
+    assert relerr(st["BE"], g["BE"]) < TOL
+    assert relerr(st["SigmaSqr"], g["sigma2"]) < TOL
+    assert relerr(st["U"], g["U"]) < TOL
+    assert relerr(st["Psi"], g["Psi"]) < 1e-13
+    mdl.set_norm(lib.NORM_DEFAULT, g["lb"], g["ub"])
+    outs, res = mdl.predict(g["xq"], ("pred", "ssqr", "s", "ei", "poi"), acq="ei",
+                            ybest=float(np.min(g["y"])))
+    for k in ("pred", "ssqr", "s", "ei", "poi"):
+        assert relerr(outs[k], g["p_" + k]) < 5e-9, (k, relerr(outs[k], g["p_" + k]))
+    assert res["best_idx"] == int(np.argmin(g["p_ei"]))
+    assert res["n_points"] == len(g["xq"])
+    mdl.close()
+
+
+@pytest.mark.parametrize("name", [c for c in RANDOM_CASES if not c.startswith("trend")])
+def test_predict_matches_reference(lib, name):
+    g = load_golden(name)
+    kw = _case_kwargs(g)
+    mdl = _model(lib, g, kw)
+    mdl.fit_state(g["xpop"][-1], kw["trainvar"], kw["fixed_nugget"], want_U=False, want_Psi=False)
+    mdl.set_norm(lib.NORM_DEFAULT, g["lb"], g["ub"])
+    names = ("pred", "ssqr", "s", "ei", "poi", "pof")
+    outs, res = mdl.predict(g["xq"], names, acq="pred", ybest=float(np.min(g["y"])),
+                            limit=float(g["limit"]), limit_sign=1)
+    for k in names:
+        assert relerr(outs[k], g["p_" + k]) < 2e-8, (name, k, relerr(outs[k], g["p_" + k]))
+    assert res["best_idx"] == int(np.argmin(g["p_pred"]))
+    mdl.close()
+
+
+@pytest.mark.parametrize("name", ["trend1", "trend2"])
+def test_predict_with_trend_matches_oracle(lib, name):
+    """TrendOrder > 0: the reference's predict crashes; parity is vs the oracle."""
+    g = load_golden(name)
+    kw = _case_kwargs(g)
+    mdl = _model(lib, g, kw)
+    x = g["xpop"][0]
+    st = mdl.fit_state(x, False, kw["fixed_nugget"])
+    fit = ko.nll(x, g["X_norm"], g["y"], g["F"], full=True, **kw)
+    assert abs(st["NegLnLike"] - fit["NegLnLike"]) / abs(fit["NegLnLike"]) < TOL
+    assert relerr(st["U"], fit["U"]) < TOL
+    mdl.set_trend(g["idx"])
+    mdl.set_norm(lib.NORM_DEFAULT, g["lb"], g["ub"])
+    rng = np.random.default_rng(1)
+    xq = rng.uniform(-5, 5, (77, g["X"].shape[1]))
+    outs, _ = mdl.predict(xq, ("pred", "ssqr", "fpc"))
+    ref = ko.predict(ko.standardize_x(xq, g["lb"], g["ub"]), g["X_norm"], g["y"], g["F"], g["idx"], fit)
+    for k in ("pred", "ssqr", "fpc"):
+        assert relerr(outs[k], ref[k]) < 5e-9, (k, relerr(outs[k], ref[k]))
+    mdl.close()
+
+
+def test_akmcs_reductions_match_reference(lib):
+    g = load_golden("akmcs_fourbranch")
+    mdl = lib.DeviceModel(g["X_norm"], g["y"], g["F"], ["gaussian"])
+    mdl.fit_state(g["theta_log10"], False, -6.0, want_U=False, want_Psi=False)
+    mdl.set_norm(lib.NORM_DEFAULT, g["lb"], g["ub"])
+    outs, res = mdl.predict(g["pop"], ("pred", "s", "u"), acq="u")
+    assert relerr(outs["pred"], g["Gx"]) < TOL
+    assert relerr(outs["s"], g["sigmaG"]) < 1e-8
+    assert res["n_fail"] == int(g["n_fail"])
+    assert res["n_fail_minus"] == int(g["n_fail_minus"])
+    assert res["n_fail_plus"] == int(g["n_fail_plus"])
+    assert res["min_u_idx"] == int(g["argminU"])
+    assert res["best_idx"] == int(g["argminU"])
+    mdl.close()
+
+
+def test_nll_not_positive_definite_is_flagged_not_fatal(lib):
+    """Duplicate sites + tiny nugget: the reference raises LinAlgError (likelihood_func.py:175);
+    the batched path flags the candidate and keeps the rest of the population intact."""
+    rng = np.random.default_rng(2)
+    X = rng.uniform(-1, 1, (40, 2))
+    X[7] = X[3]
+    y = np.sum(X ** 2, axis=1)
+    F = np.ones((40, 1))
+    mdl = lib.DeviceModel(X, y, F, ["gaussian"])
+    xpop = np.array([[0.0, 0.0, -30.0], [0.0, 0.1, -6.0], [3.0, 3.0, -30.0]])
+    nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
+    assert info[0] != 0 and np.isinf(nll[0])
+    assert info[1] == 0 and np.isfinite(nll[1])
+    ref = ko.nll(xpop[1], X, y, F)
+    assert abs(nll[1] - ref) / abs(ref) < TOL
+    mdl.close()
+
+
+def test_nll_c2_size_properties(lib):
+    """BASELINE config 2 shape (n=1000, d=10, B=64): a seeded subset vs the oracle plus
+    size-independent properties (determinism, permutation equivariance over the population)."""
+    rng = np.random.default_rng(1)
+    n, d, B = 1000, 10, 64
+    X = rng.uniform(-1, 1, (n, d))
+    y = 0.5 * np.sum((5 * X) ** 4 - 16 * (5 * X) ** 2 + 5 * (5 * X), axis=1)
+    F = np.ones((n, 1))
+    xpop = np.random.default_rng(2).uniform(-0.3, 0.7, (B, d))
+    mdl = lib.DeviceModel(X, y, F, ["gaussian"])
+    nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
+    assert np.all(info == 0)
+    for b in (0, 17, 63):
+        ref = ko.nll(xpop[b], X, y, F)
+        assert abs(nll[b] - ref) / abs(ref) < TOL, (b, nll[b], ref)
+    perm = np.random.default_rng(3).permutation(B)
+    nll_p = mdl.nll_batch(xpop[perm], False, -6.0)
+    assert np.array_equal(nll_p, nll[perm])
+    mdl.close()
+
+
+def test_predict_c2_size_vs_oracle(lib):
+    rng = np.random.default_rng(4)
+    n, d = 1000, 10
+    X = rng.uniform(-1, 1, (n, d))
+    y = 0.5 * np.sum((5 * X) ** 4 - 16 * (5 * X) ** 2 + 5 * (5 * X), axis=1)
+    F = np.ones((n, 1))
+    x = np.full(d, 0.3)
+    mdl = lib.DeviceModel(X, y, F, ["gaussian"])
+    st = mdl.fit_state(x, False, -6.0, want_U=False, want_Psi=False)
+    fit = ko.nll(x, X, y, F, full=True)
+    assert abs(st["NegLnLike"] - fit["NegLnLike"]) / abs(fit["NegLnLike"]) < TOL
+    mdl.set_norm(lib.NORM_NONE)
+    m = 20000 + 37                      # ragged last strip, several persistent rounds
+    xq = rng.uniform(-1, 1, (m, d))
+    outs, res = mdl.predict(xq, ("pred", "ssqr", "ei"), acq="ei", ybest=float(y.min()))
+    sub = np.concatenate([np.arange(0, 300), np.arange(m - 300, m)])
+    ref = ko.predict(xq[sub], X, y, F, np.zeros((1, d), int), fit)
+    for k in ("pred", "ssqr", "ei"):
+        assert relerr(outs[k][sub], ref[k]) < 5e-9, (k, relerr(outs[k][sub], ref[k]))
+    assert res["best_idx"] == int(np.argmin(outs["ei"]))
+    assert res["n_fail"] == int(np.sum(outs["pred"] <= 0))
+    mdl.close()
