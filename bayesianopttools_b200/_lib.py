@@ -69,6 +69,7 @@ _SIGNATURES = [
                              C.POINTER(c_double_p), C.c_int, C.POINTER(SweepResult)]),
     ("kb_predict_dev", C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                  C.POINTER(AcqParams), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("kb_loocv", C.c_int, [C.c_void_p, c_double_p]),
     ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  C.c_int, C.c_int, c_double_p, c_double_p]),
     ("kb_measure_peak", C.c_int, [C.c_int, C.c_int, c_double_p]),
@@ -186,7 +187,7 @@ class DeviceModel:
         check(self._lib.kb_reserve_population(self._h, int(B)))
 
     def set_stream(self, cuda_stream):
-        check(self._lib.kb_model_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        check(self._lib.kb_model_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def sync(self):
         check(self._lib.kb_model_sync(self._h))
@@ -216,6 +217,11 @@ class DeviceModel:
         else:
             p0, p1 = _f64(np.asarray(p0).reshape(-1)), _f64(np.asarray(p1).reshape(-1))
             check(self._lib.kb_model_set_norm(self._h, norm_type, _dp(p0), _dp(p1)))
+
+    def loocv(self):
+        pred = np.empty(self.n)
+        check(self._lib.kb_loocv(self._h, _dp(pred)))
+        return pred
 
     # -- predict --------------------------------------------------------------
     def predict(self, x, outputs=("pred",), acq="pred", ybest=0.0, limit=0.0, limit_sign=1, sigmalcb=0.0,

@@ -314,8 +314,8 @@ kb_status kb_model_set_stream(kb_model* m, void* cuda_stream) {
   if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
   CK(cudaSetDevice(m->device));
   CK(cudaStreamSynchronize(m->stream));
-  // caller-owned stream (e.g. torch's current stream); NULL restores the handle's own stream
-  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  // caller-owned stream (e.g. torch's current stream); NULL is the legacy default stream
+  m->stream = (cudaStream_t)cuda_stream;
   return KB_OK;
 }
 
@@ -563,6 +563,18 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
     first = false;
   }
   if (result) *result = total;
+  return KB_OK;
+}
+
+kb_status kb_loocv(kb_model* m, double* pred_out) {
+  if (!m || !pred_out) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (!m->fitted) KB_FAIL(KB_ERR_STATE, "loocv called before kb_fit_state");
+  CK(cudaSetDevice(m->device));
+  if (!m->dense_tmp) CK(cudaMalloc(&m->dense_tmp, sizeof(double) * (size_t)m->n * m->n));
+  CK(kb_launch_loocv(m->stream, m->n, m->n_pad, m->nind, m->AT, m->ldat, m->fit.Mbuf, m->y, m->dense_tmp));
+  g_launches += 1;
+  CK(cudaMemcpyAsync(pred_out, m->dense_tmp, sizeof(double) * m->n, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
   return KB_OK;
 }
 

@@ -152,3 +152,46 @@ cudaError_t kb_launch_fit_extract(cudaStream_t st, const KbAugGeom& g, const dou
   kb_fit_extract_kernel<<<(g.n_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(g, aug, rt, AT, ldat);
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// Leave-one-out predictions at fixed theta from ONE factorisation (replaces the n refits of
+// krigloocv2.py:15-30).  With Q = R^-1 - R^-1 F (F'R^-1F)^-1 F'R^-1 (Dubrule 1983):
+//   y_i - yhat_{-i} = (Q y)_i / Q_ii,   (Q y)_i = alpha_i,
+//   Q_ii = (R^-1)_ii - |LM^-1 (R^-1 F)_i|^2,   (R^-1)_ii = sum_k L^-1[k][i]^2 = |AT[i, :]|^2.
+// One warp per training point.
+// ---------------------------------------------------------------------------
+__global__ void kb_loocv_kernel(int n, int n_pad, int nind, const double* __restrict__ AT, int ldat,
+                                const double* __restrict__ LM, const double* __restrict__ y,
+                                double* __restrict__ pred) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const double* row = AT + (size_t)i * ldat;
+  double s = 0.0;
+  for (int k = (i & ~31) + lane; k < n; k += 32) s = fma(row[k], row[k], s);
+  s = kb_warp_sum(s);
+  if (lane == 0) {
+    double t2 = 0.0;
+    // forward solve LM w = G_i, accumulating |w|^2 (w kept in a small local window via recompute)
+    // nind is small (1 for ordinary Kriging); O(nind^2) per point.
+    extern __shared__ double wbuf[];
+    double* w = wbuf + (size_t)(threadIdx.x >> 5) * nind;
+    for (int a = 0; a < nind; ++a) {
+      double u = row[n_pad + 1 + a];
+      for (int c = 0; c < a; ++c) u = fma(-LM[(size_t)a * nind + c], w[c], u);
+      u /= LM[(size_t)a * nind + a];
+      w[a] = u;
+      t2 = fma(u, u, t2);
+    }
+    const double qii = s - t2;
+    pred[i] = y[i] - row[n_pad] / qii;
+  }
+}
+
+cudaError_t kb_launch_loocv(cudaStream_t st, int n, int n_pad, int nind, const double* AT, int ldat,
+                            const double* LM, const double* y, double* pred) {
+  const int wpb = 4;
+  const size_t smem = sizeof(double) * wpb * nind;
+  kb_loocv_kernel<<<(n + wpb - 1) / wpb, wpb * 32, smem, st>>>(n, n_pad, nind, AT, ldat, LM, y, pred);
+  return cudaGetLastError();
+}

@@ -72,6 +72,9 @@ cudaError_t kb_launch_gls(cudaStream_t st, const KbAugGeom& g, int B, const doub
 cudaError_t kb_launch_fit_extract(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
                                   double* AT, int ldat);
 
+cudaError_t kb_launch_loocv(cudaStream_t st, int n, int n_pad, int nind, const double* AT, int ldat,
+                            const double* LM, const double* y, double* pred);
+
 // --- kb_predict.cu -----------------------------------------------------------
 struct KbPredictArgs {
   // model

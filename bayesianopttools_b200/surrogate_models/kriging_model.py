@@ -1,0 +1,315 @@
+"""Kriging model class over the GPU hot path (reference: surrogate_models/kriging_model.py).
+
+Same constructor, attributes, KrigInfo contract and methods as the reference's ``Kriging``;
+the arithmetic (likelihood, Cholesky, prediction) runs in libkrigb200.so.  The hyper-parameter
+optimisers stay on the host but evaluate POPULATIONS: the finite-difference stencil of
+L-BFGS-B / SLSQP (nbhyp+1 candidates), a CMA-ES generation or a GA population is one batched
+call instead of one `likelihood()` per candidate (kriging_model.py:420-446).
+"""
+import numpy as np
+from scipy.optimize import fmin_cobyla, minimize
+
+from bayesianopttools_b200.misc.sampling.samplingplan import sampling, standardize
+from bayesianopttools_b200.optim_tools.cmaes import fmin_batched
+from bayesianopttools_b200.optim_tools.ga.uncGA import uncGA
+from .supports.errperf import errperf
+from .supports.likelihood_func import likelihood, likelihood_batch
+from .supports.prediction import prediction
+from .supports.trendfunction import compute_regression_mat, polytruncation
+
+PENALTY = 1e4      # the reference's penalty value for failed evaluations (likelihood_func.py:207)
+
+
+class Kriging:
+    """See the reference docstring (kriging_model.py:16-52) for the KrigInfo keys."""
+
+    def __init__(self, KrigInfo, ub=5, lb=-5, standardization=False, standtype="default", normy=True,
+                 trainvar=True, inherit=False):
+        KrigInfo["nvar"] = np.size(KrigInfo["X"], 1)
+        KrigInfo["nsamp"] = np.size(KrigInfo["X"], 0)
+        self.nbhyp = KrigInfo["nvar"] + 1 if trainvar is True else KrigInfo["nvar"]
+        self.trainvar = trainvar
+        self.normy = normy
+        self.standardization = standardization
+        self.standtype = standtype
+        self.Y = KrigInfo["y"]
+        self.X = KrigInfo["X"]
+        self.lb = lb
+        self.ub = ub
+        if not inherit:
+            self.type = "kriging"
+            KrigInfo["type"] = self.type
+            KrigInfo, scaling = kriginfocheck(KrigInfo, lb, ub, self.nbhyp)
+            self.KrigInfo = KrigInfo
+            self.scaling = scaling
+            self.sigmacmaes = (ub - lb) / 5
+            if self.standardization is True:
+                self.standardize()
+
+    # ------------------------------------------------------------------
+    def standardize(self):
+        """kriging_model.py:102-167 (host): X_norm, optional y_norm, trend index and F."""
+        K = self.KrigInfo
+        K["idx"] = polytruncation(K["TrendOrder"], K["nvar"], 1)
+        self.Y = K["y"]
+        if self.standardization is True:
+            if self.standtype.lower() == "default":
+                K["normtype"] = "default"
+                bound = np.vstack((-np.ones((1, K["nvar"])), np.ones((1, K["nvar"]))))
+                if self.normy is True:
+                    # intended behaviour of kriging_model.py:121-129 (the reference passes `normy=` to a
+                    # callee whose keyword is `norm_y` and crashes)
+                    rng = np.vstack((np.hstack((K["lb"], np.min(self.Y, axis=0))),
+                                     np.hstack((K["ub"], np.max(self.Y, axis=0)))))
+                    K["X_norm"], K["y_norm"] = standardize(K["X"], K["y"], type="default", norm_y=True, range=rng)
+                    K["norm_y"] = True
+                else:
+                    K["X_norm"] = standardize(K["X"], K["y"], type="default",
+                                              range=np.vstack((K["lb"], K["ub"])))
+                    K.pop("y_norm", None)
+                    K["norm_y"] = False
+            else:
+                K["normtype"] = "std"
+                if self.normy is True:
+                    (K["X_norm"], K["y_norm"], K["X_mean"], K["y_mean"], K["X_std"], K["y_std"]) = \
+                        standardize(K["X"], K["y"], type="std", norm_y=True)
+                    K["norm_y"] = True
+                else:
+                    K["X_norm"], K["X_mean"], K["X_std"] = standardize(K["X"], K["y"], type="std")
+                    K.pop("y_norm", None)
+                    K["norm_y"] = False
+                bound = np.vstack((np.min(K["X_norm"], axis=0), np.max(K["X_norm"], axis=0)))
+            K["standardization"] = True
+            K["F"] = compute_regression_mat(K["idx"], K["X_norm"], bound, np.ones(K["nvar"]))
+        else:
+            K["standardization"] = False
+            K["norm_y"] = False
+            bound = np.vstack((np.min(K["X"], axis=0), np.max(K["X"], axis=0)))
+            K["F"] = compute_regression_mat(K["idx"], K["X"], bound, np.ones(K["nvar"]))
+
+    # ------------------------------------------------------------------
+    def _batch_nll(self, xpop):
+        f = likelihood_batch(xpop, self.KrigInfo, trainvar=self.trainvar)
+        return f
+
+    def _fun_and_grad(self, x, lbv, ubv, eps=1e-3):
+        """Objective and forward-difference gradient from ONE batched evaluation; the stencil
+        follows scipy's '2-point' rule with bounds (step flipped where x+eps leaves the box)."""
+        n = len(x)
+        h = np.full(n, eps)
+        flip = (x + h > ubv) & (x - h >= lbv)
+        h[flip] = -eps
+        pts = np.vstack([x[None, :], x[None, :] + np.diag(h)])
+        f = self._batch_nll(pts)
+        f = np.where(np.isfinite(f), f, PENALTY)
+        dx = (pts[1:, :] - x[None, :])[np.arange(n), np.arange(n)]
+        return float(f[0]), (f[1:] - f[0]) / dx
+
+    def train(self, parallel=False, disp=True, pre_theta=None):
+        """kriging_model.py:169-260."""
+        K = self.KrigInfo
+        if disp:
+            print("Begin train hyperparam.")
+        if K["kernel"] == ["iso_gaussian"]:
+            self.nbhyp = 1
+        elif len(K["kernel"]) != 1 and "iso_gaussian" in K["kernel"]:
+            raise NotImplementedError("Isotropic Gaussian kernel is not available for composite kernel")
+        elif len(K["ubhyp"]) != self.nbhyp:
+            self.nbhyp = len(K["ubhyp"])
+        nhyp = len(K["ubhyp"]) if self.nbhyp != 1 or K["kernel"] != ["iso_gaussian"] else 1
+
+        if K["nrestart"] < 1:
+            xhyp = np.zeros((1, nhyp))
+        else:
+            _, xhyp = sampling("sobol", nhyp, K["nrestart"], result="real",
+                               upbound=K["ubhyp"][:nhyp], lobound=K["lbhyp"][:nhyp])
+        if pre_theta is not None:
+            pre_theta = np.asarray(pre_theta, dtype=float)
+            xhyp = np.vstack((pre_theta, np.random.rand(K["nrestart"] - 1, nhyp) + pre_theta))
+
+        if self.nbhyp == 1:
+            best_x, neglnlikecand = self._train_1d()
+            if disp:
+                print(f"Best hyperparameter is {best_x}")
+                print(f"With NegLnLikelihood of {neglnlikecand}")
+        else:
+            if disp:
+                print(f"Training {K['nrestart']} hyperparameter(s)")
+            bestxcand, neglnlikecand = self.parallelopt(xhyp, parallel, None, disp)
+            I = int(np.argmin(neglnlikecand))
+            best_x = bestxcand[I, :]
+            if disp:
+                print("Single Objective, train hyperparam, end.")
+                print(f"Best hyperparameter is {best_x}")
+                print(f"With NegLnLikelihood of {neglnlikecand[I]}")
+        self.KrigInfo = likelihood(best_x, K, mode="all", trainvar=self.trainvar)
+
+    def _train_1d(self):
+        """nbhyp == 1 (kriging_model.py:213-227): batched bracketing + golden section, or batched GA."""
+        K = self.KrigInfo
+        if K["optimizer"] == "ga":
+            bx, bf, _ = uncGA(self._batch_nll, lb=self.lb, ub=self.ub, npop=100, maxg=100)
+            return np.atleast_1d(bx), bf
+        grid = np.linspace(self.lb, self.ub, 65)
+        f = self._batch_nll(grid[:, None])
+        f = np.where(np.isfinite(f), f, np.inf)
+        i = int(np.argmin(f))
+        a, b = grid[max(i - 1, 0)], grid[min(i + 1, len(grid) - 1)]
+        gr = (np.sqrt(5) - 1) / 2
+        for _ in range(60):
+            c, d = b - gr * (b - a), a + gr * (b - a)
+            fc, fd = self._batch_nll(np.array([[c], [d]]))
+            if not np.isfinite(fc):
+                fc = np.inf
+            if not np.isfinite(fd):
+                fd = np.inf
+            if fc < fd:
+                b = d
+            else:
+                a = c
+            if abs(b - a) < 1e-9:
+                break
+        x = np.array([(a + b) / 2])
+        return x, float(self._batch_nll(x[None, :])[0])
+
+    def parallelopt(self, xhyp, parallel=False, optimbound=None, disp=True):
+        """kriging_model.py:326-389.  Restarts run in sequence; the parallelism is inside each
+        objective call (population on the GPU), so `parallel` is accepted and ignored."""
+        K = self.KrigInfo
+        nres = xhyp.shape[0]
+        bestxcand = np.zeros((nres, xhyp.shape[1]))
+        neglnlikecand = np.zeros(nres)
+        for ii in range(nres):
+            if disp:
+                print(f"Training hyperparameter candidate no.{ii + 1}")
+            bestxcand[ii, :], neglnlikecand[ii] = self.tune_hyperparameters(xhyp[ii, :])
+        return bestxcand, neglnlikecand
+
+    def tune_hyperparameters(self, x0):
+        """kriging_model.py:392-455 with batched objective evaluations."""
+        K = self.KrigInfo
+        lbv, ubv = np.asarray(K["lbhyp"], dtype=float), np.asarray(K["ubhyp"], dtype=float)
+        opt = K["optimizer"].lower()
+
+        def scalar(x, *a):
+            f = self._batch_nll(np.asarray(x, dtype=float)[None, :])[0]
+            return float(f) if np.isfinite(f) else PENALTY
+
+        if opt == "cmaes":
+            bx, bf, _ = fmin_batched(lambda P: self._batch_nll(P), x0, self.sigmacmaes, bounds=[lbv, ubv],
+                                     scaling=self.scaling, popsize=K.get("cmaes_popsize"),
+                                     seed=K.get("seed"), maxiter=K.get("cmaes_maxiter"))
+            return bx, bf
+        if opt == "lbfgsb":
+            res = minimize(lambda x: self._fun_and_grad(x, lbv, ubv, 1e-3), x0, method="L-BFGS-B", jac=True,
+                           bounds=np.column_stack((lbv, ubv)))
+            return res.x, res.fun
+        if opt == "slsqp":
+            res = minimize(lambda x: self._fun_and_grad(x, lbv, ubv, 1.4901161193847656e-08), x0,
+                           method="SLSQP", jac=True, bounds=np.column_stack((lbv, ubv)))
+            return res.x, res.fun
+        if opt == "cobyla":
+            cons = []
+            for i in range(len(ubv)):
+                cons.append(lambda x, i=i: x[i] - lbv[i])
+                cons.append(lambda x, i=i: ubv[i] - x[i])
+            res = fmin_cobyla(scalar, x0, cons, rhobeg=0.5, rhoend=1e-4)
+            return res, scalar(res)
+        if opt == "ga":
+            bx, bf, _ = uncGA(self._batch_nll, lb=lbv, ub=ubv, npop=K.get("ga_npop", 100),
+                              maxg=K.get("ga_maxg", 100), seed=K.get("seed"))
+            return bx, bf
+        raise KeyError(f"{K['optimizer']} in KrigInfo['Optimizer'] is not recognised.")
+
+    # ------------------------------------------------------------------
+    def loocvcalc(self, metrictype="mape", drm=None):
+        """kriging_model.py:262-296 / krigloocv2.py:7-33: leave-one-out predictions at fixed theta.
+
+        The reference refits n models of n-1 points; the identical numbers follow from ONE
+        factorisation (Dubrule 1983): with Q = R^-1 - R^-1 F (F'R^-1F)^-1 F'R^-1,
+        y_i - yhat_-i = (Q y)_i / Q_ii.  diag(R^-1), R^-1 F and Q y come from the device fit state."""
+        from .supports.loocv import loocv_device
+        K = self.KrigInfo
+        pred = loocv_device(K)
+        K["LOOCVerror"], K["LOOCVpred"] = errperf(K["y"], pred, metrictype), pred
+        return K["LOOCVerror"], K["LOOCVpred"]
+
+    def predict(self, x, predtypes=["pred"], drmmodel=None):
+        """kriging_model.py:298-324."""
+        return prediction(np.asarray(x, dtype=float), self.KrigInfo, predtypes=predtypes, drm=drmmodel)
+
+    def predict_sweep(self, x, acq="EI", want=()):
+        """Reduce-only sweep over many sites: arg-min of one acquisition plus the AK-MCS
+        counters, without materialising per-site outputs.  Returns (result dict, outputs dict)."""
+        from .supports.prediction import _configure, _ensure_fitted
+        from .supports.device_state import get_model
+        K = self.KrigInfo
+        holder = get_model(K)
+        _ensure_fitted(K, holder)
+        _configure(K, holder.model)
+        kw = dict(ybest=float(np.min(holder.model.y)))
+        if "limit" in K:
+            kw.update(limit=float(K["limit"]), limit_sign=1 if K.get("limittype", ">=") in (">", ">=") else -1)
+        if "sigmalcb" in K:
+            kw["sigmalcb"] = float(K["sigmalcb"])
+        outs, res = holder.model.predict(np.asarray(x, dtype=float), tuple(w.lower() for w in want),
+                                         acq=acq.lower(), **kw)
+        return res, outs
+
+
+def kriginfocheck(KrigInfo, lb, ub, nbhyp):
+    """kriging_model.py:458-571: defaults and the hyper-parameter box."""
+    eps = np.finfo(float).eps
+    if "nrestart" not in KrigInfo:
+        KrigInfo["nrestart"] = 1
+    elif KrigInfo["nrestart"] < 1:
+        raise ValueError('Minimum value of KrigInfo["nrestart"] is 1')
+    if "optimizer" not in KrigInfo:
+        KrigInfo["optimizer"] = "lbfgsb"
+        print("The optimizer is not specified, set to lbfgsb")
+    elif KrigInfo["optimizer"].lower() not in ["lbfgsb", "cmaes", "cobyla", "slsqp", "ga"]:
+        raise ValueError(KrigInfo["optimizer"], " is not a valid optimizer.")
+    if "TrendOrder" not in KrigInfo:
+        KrigInfo["TrendOrder"] = 0
+    elif KrigInfo["TrendOrder"] < 0:
+        raise ValueError("The order of the polynomial trend should be a positive value.")
+    nnugget = 1
+    if "nugget" not in KrigInfo:
+        KrigInfo["nugget"] = -6
+        KrigInfo["nuggetparam"] = "fixed"
+        print("Nugget is not defined, set nugget to 1e-06")
+    elif type(KrigInfo["nugget"]) is not list:
+        KrigInfo["nuggetparam"] = "fixed"
+    elif len(KrigInfo["nugget"]) == 2:
+        KrigInfo["nuggetparam"] = "tuned"
+        nnugget = 2
+        if KrigInfo["nugget"][0] > KrigInfo["nugget"][1]:
+            raise TypeError("The lower bound of the nugget should be lower than the upper bound.")
+    if "kernel" not in KrigInfo:
+        KrigInfo["kernel"] = ["gaussian"]
+        print("Kernel is not defined, set kernel to gaussian")
+    elif type(KrigInfo["kernel"]) is not list:
+        KrigInfo["kernel"] = [KrigInfo["kernel"]]
+    nkernel = len(KrigInfo["kernel"])
+    KrigInfo["nkernel"] = nkernel
+    if KrigInfo["type"] == "kriging":
+        KrigInfo["n_princomp"] = False
+    if "limit" in KrigInfo and "limittype" not in KrigInfo:
+        KrigInfo["limittype"] = ">="
+        print("KrigInfo['limittype'] is set to greater than equal'>='.")
+    lbhyp = lb * np.ones(nbhyp)
+    ubhyp = ub * np.ones(nbhyp)
+    if nnugget > 1:
+        lbhyp = np.hstack((lbhyp, KrigInfo["nugget"][0]))
+        ubhyp = np.hstack((ubhyp, KrigInfo["nugget"][1]))
+    if nkernel > 1:
+        lbhyp = np.hstack((lbhyp, np.zeros(nkernel) + eps))
+        ubhyp = np.hstack((ubhyp, np.ones(nkernel)))
+    scaling = np.ones(len(lbhyp))
+    if nnugget > 1:
+        scaling[-1 - (nkernel if nkernel > 1 else 0)] = (KrigInfo["nugget"][1] - KrigInfo["nugget"][0]) / (ub - lb)
+    if nkernel > 1:
+        scaling[-nkernel:] = 1 / (ub - lb)
+    KrigInfo["lbhyp"] = lbhyp
+    KrigInfo["ubhyp"] = ubhyp
+    return KrigInfo, scaling

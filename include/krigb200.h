@@ -123,6 +123,11 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
                          const kb_acq_params* acq_params, double* const* outs_dev, int acq,
                          KbSweepResult* result_dev);
 
+/* Leave-one-out predictions at the fitted hyper-parameters, pred_out[n].  Replaces the n
+ * refits + n single-site predictions of loocv2 (krigloocv2.py:7-33) with the closed form
+ * from one factorisation; same numbers up to rounding. */
+kb_status kb_loocv(kb_model* m, double* pred_out);
+
 /* `calckernel(XN, XM, theta, nvar, type=, plscoeff=)` (kernelfunc.py:4-34):
  * out is (n x m).  For KPLS pass theta of length h and plscoeff (d x h). */
 kb_status kb_corr_matrix(int device, int n, int m, int d, const double* XN, const double* XM,

@@ -1,0 +1,144 @@
+"""GPU: the reference-facing Python surface (Kriging / KPLS / likelihood / prediction / SOBO /
+AKMCS) reproduces the reference's stored outputs end to end."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _info(g, **extra):
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    K = initkriginfo("single")
+    K.update(X=g["X"].copy(), y=g["y"].copy(), lb=g["lb"].copy(), ub=g["ub"].copy(), nrestart=5,
+             kernel=["gaussian"], nugget=-6, TrendOrder=0, optimizer="lbfgsb", problem="styblinski")
+    K.update(extra)
+    return K
+
+
+@pytest.mark.parametrize("name", ["krigdemo_nb", "sobo_nb"])
+def test_train_reproduces_notebook(name, capsys):
+    """Kriging_Demo.ipynb:341-345 / Single_Objective_...ipynb:307-310: same Sobol starts, same
+    L-BFGS-B (eps=1e-3 forward differences, evaluated as one batched stencil) -> same optimum."""
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    g = load_golden(name)
+    obj = Kriging(_info(g), standardization=True, standtype="default", normy=False, trainvar=False)
+    assert np.array_equal(obj.KrigInfo["X_norm"], g["X_norm"])
+    obj.train(disp=False)
+    K = obj.KrigInfo
+    assert abs(K["NegLnLike"] - float(g["nll"])) / abs(float(g["nll"])) < 1e-8
+    assert np.allclose(K["Theta"], g["theta_log10"], atol=2e-5)
+    assert K["U"].shape == g["U"].shape and K["BE"].shape == (1, 1) and K["SigmaSqr"].shape == (1, 1)
+    err, pred = obj.loocvcalc(metrictype="rmse")
+    assert pred.shape == (len(g["y"]), 1)
+    assert abs(err - float(g["loocv_rmse"])) / float(g["loocv_rmse"]) < 1e-5
+    xx = np.linspace(-5, 5, 100)
+    gx, gy = np.meshgrid(xx, xx)
+    grid = np.column_stack([gx.reshape(-1), gy.reshape(-1)])
+    ygrid = obj.predict(grid, ["pred"])
+    assert ygrid.shape == (10000, 1)
+    assert relerr(ygrid.ravel()[g["grid_idx"]], g["grid_pred_sub"]) < 1e-5
+    yact = 0.5 * np.sum(grid ** 4 - 16 * grid ** 2 + 5 * grid, axis=1)
+    rmse = np.sqrt(np.mean((yact - ygrid.ravel()) ** 2))
+    assert abs(rmse - float(g["rmse_grid"])) / float(g["rmse_grid"]) < 1e-5
+
+
+def test_likelihood_and_prediction_shims_follow_reference_conventions():
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.likelihood_func import likelihood, likelihood_batch
+    from bayesianopttools_b200.surrogate_models.supports.kernelfunc import calckernel
+    g = load_golden("ok_composite_tn_tv")
+    K = _info(g, kernel=["gaussian", "matern52"], nugget=[-8, -3])
+    obj = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=True)
+    assert len(obj.KrigInfo["ubhyp"]) == g["xpop"].shape[1]
+    for b in (0, 3):
+        v = likelihood(g["xpop"][b], obj.KrigInfo, mode="default", trainvar=True)
+        assert isinstance(v, float) and abs(v - g["nll"][b]) / abs(g["nll"][b]) < 1e-9
+    vb = likelihood_batch(g["xpop"], obj.KrigInfo, trainvar=True)
+    assert np.max(np.abs(vb - g["nll"]) / np.abs(g["nll"])) < 1e-9
+    Kout = likelihood(g["xpop"][-1], obj.KrigInfo, mode="all", trainvar=True)
+    assert Kout is obj.KrigInfo
+    assert relerr(Kout["U"], g["U_last"]) < 1e-9 and relerr(Kout["Psi"], g["Psi_last"]) < 1e-13
+    assert np.isscalar(Kout["SigmaSqr"]) or np.ndim(Kout["SigmaSqr"]) == 0
+    with pytest.raises(TypeError):
+        likelihood(g["xpop"][0], obj.KrigInfo, mode="bogus")
+    # predict conventions (prediction.py:292-298)
+    obj.KrigInfo["limit"], obj.KrigInfo["limittype"] = float(g["limit"]), ">="
+    outs = obj.predict(g["xq"], ["pred", "SSqr", "s", "EI", "poi", "pof"])
+    assert isinstance(outs, list) and outs[0].shape == (133, 1) and outs[1].shape == (1, 133)
+    for o, k in zip(outs, ("pred", "ssqr", "s", "ei", "poi", "pof")):
+        assert relerr(o, g["p_" + k]) < 2e-8, k
+    one = obj.predict(g["xq"][5], "EI")
+    assert isinstance(one, float) and abs(one - g["p_ei"][5]) <= 2e-8 * np.max(np.abs(g["p_ei"]))
+    with pytest.raises(ValueError):
+        obj.predict(g["xq"][:2], ["nope"])
+    with pytest.raises(ValueError):
+        calckernel(g["X_norm"], g["X_norm"], np.ones(3), 3, type="cubic")
+    k = calckernel(g["X_norm"][:5], g["X_norm"][:7], np.ones(3), 3, type="matern32")
+    assert k.shape == (5, 7)
+
+
+def test_likelihood_raises_linalgerror_when_not_pd():
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.likelihood_func import likelihood
+    g = load_golden("ok_gaussian")
+    X = g["X"].copy()
+    X[1] = X[0]
+    K = _info(g, X=X, nugget=-30)
+    obj = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    with pytest.raises(np.linalg.LinAlgError):
+        likelihood(np.zeros(3), obj.KrigInfo, mode="default", trainvar=False)
+    with pytest.raises(np.linalg.LinAlgError):
+        likelihood(np.zeros(3), obj.KrigInfo, mode="all", trainvar=False)
+
+
+def test_kpls_train_cmaes_and_predict():
+    from bayesianopttools_b200.surrogate_models.kpls_model import KPLS
+    from oracle import kriging_oracle as ko
+    g = load_golden("kpls")
+    K = _info(g, n_princomp=3, optimizer="cmaes", nrestart=1, cmaes_popsize=16, cmaes_maxiter=40, seed=3)
+    obj = KPLS(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    assert relerr(obj.KrigInfo["plscoeff"] ** 2, g["plscoeff"] ** 2) < 1e-9
+    obj.train(disp=False)
+    Kt = obj.KrigInfo
+    ref = ko.nll(Kt["Theta"], g["X_norm"], g["y"], g["F"], plscoeff=Kt["plscoeff"], n_princomp=3, full=True)
+    assert abs(Kt["NegLnLike"] - ref["NegLnLike"]) / abs(ref["NegLnLike"]) < 1e-9
+    assert Kt["NegLnLike"] <= np.min(g["nll"]) + 1e-6          # at least as good as the random population
+    pr = obj.predict(g["xq"], ["pred", "s"])
+    out = ko.predict(ko.standardize_x(g["xq"], g["lb"], g["ub"]), g["X_norm"], g["y"], g["F"], g["idx"], ref,
+                     plscoeff=Kt["plscoeff"])
+    assert relerr(pr[0], out["pred"]) < 1e-8 and relerr(pr[1], out["s"]) < 1e-7
+
+
+def test_akmcs_iteration0_matches_reference():
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.reliability_analysis.akmcs import AKMCS
+    g = load_golden("akmcs_fourbranch")
+    obj = Kriging(_info(g, problem="fourbranches"), standardization=True, standtype="default", normy=False,
+                  trainvar=False)
+    obj.train(disp=False)
+    assert abs(obj.KrigInfo["NegLnLike"] - float(g["nll"])) / abs(float(g["nll"])) < 1e-7
+    ak = AKMCS(obj, dict(init_samp=g["pop"], maxupdate=2, problem="fourbranches"))
+    ak.run(autoupdate=False, disp=False)
+    assert ak.Gx.shape == (4000, 1) and ak.sigmaG.shape == (1, 4000)
+    assert relerr(ak.Gx, g["Gx"]) < 1e-6
+    assert ak.Pf == float(g["Pf"])
+    assert np.array_equal(ak.xnew, g["xnew"])
+    assert abs(ak.stop_criteria - float(g["stop"])) < 1e-12
+    ak.run(autoupdate=True, disp=False)                          # two enrichment steps run end to end
+    assert obj.KrigInfo["X"].shape[0] == len(g["X"]) + 2 and ak.updateX.shape == (3, 2)
+
+
+def test_sobo_sweep_improves_best():
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.optim_tools.SOBO import SOBO
+    g = load_golden("sobo_nb")
+    obj = Kriging(_info(g, nrestart=3), standardization=True, standtype="default", normy=False, trainvar=False)
+    obj.train(disp=False)
+    y0 = float(np.min(obj.KrigInfo["y"]))
+    sobo = SOBO(dict(nup=3, nrestart=2, acquifunc="EI", acquifuncopt="sweep", ncandidates=200000, nsamp=10,
+                     rng=np.random.default_rng(0)), obj)
+    sobo.run(disp=False)
+    assert obj.KrigInfo["X"].shape[0] == 13
+    assert float(np.min(obj.KrigInfo["y"])) <= y0

@@ -1,0 +1,104 @@
+"""CPU: host-side logic of the drop-in layer (no GPU compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, relerr
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from bayesianopttools_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "krigb200.h")).read()
+    declared = set(re.findall(r"\b(kb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.kb_version() >= 100
+    assert isinstance(lib.kb_device_count(), int)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bayesianopttools_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_no_gpu_fails_loudly():
+    from bayesianopttools_b200 import _lib
+    if _lib.load().kb_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        _lib.DeviceModel(np.zeros((4, 2)), np.zeros(4), np.ones((4, 1)), ["gaussian"])
+    with pytest.raises(RuntimeError):
+        _lib.corr_matrix(np.zeros((2, 2)), np.zeros((2, 2)), np.ones(2))
+
+
+def test_samplers_match_reference():
+    from bayesianopttools_b200.misc.sampling.samplingplan import sampling
+    g = load_golden("sampling")
+    for nv, ns in ((2, 5), (10, 7), (3, 16)):
+        assert np.array_equal(sampling("sobol", nv, ns)[0], g["sobol_%d_%d" % (nv, ns)])
+        assert np.allclose(sampling("halton", nv, ns)[0], g["halton_%d_%d" % (nv, ns)], atol=1e-15)
+    g = load_golden("krigdemo_nb")
+    _, xh = sampling("sobol", 2, 5, result="real", upbound=np.array([5., 5.]), lobound=np.array([-5., -5.]))
+    assert np.array_equal(xh, g["xhyp"])
+
+
+def test_trend_and_standardize_match_reference():
+    from bayesianopttools_b200.misc.sampling.samplingplan import standardize
+    from bayesianopttools_b200.surrogate_models.supports.trendfunction import (compute_regression_mat,
+                                                                                 polytruncation)
+    g = load_golden("trend")
+    for key in [k for k in g if k.startswith("idx_")]:
+        _, o, v = key.split("_")
+        idx = polytruncation(int(o), int(v), 1)
+        assert np.array_equal(idx, g[key])
+        nv = int(v)
+        bound = np.vstack((-np.ones((1, nv)), np.ones((1, nv))))
+        assert relerr(compute_regression_mat(idx, g["Xs_%s_%s" % (o, v)], bound, np.ones(nv)),
+                      g["F_%s_%s" % (o, v)]) < 1e-13
+    g = load_golden("ok_gaussian")
+    Xn = standardize(g["X"], g["y"], type="default", range=np.vstack((g["lb"], g["ub"])))
+    assert np.array_equal(Xn, g["X_norm"])
+
+
+def test_kriginfocheck_hyperparameter_box():
+    from bayesianopttools_b200.surrogate_models.kriging_model import kriginfocheck
+    K = dict(type="kriging", nugget=[-8, -3], kernel=["gaussian", "matern32"], nrestart=3, optimizer="cmaes")
+    K, scaling = kriginfocheck(K, -5, 5, 4)
+    assert len(K["lbhyp"]) == 4 + 1 + 2 and K["nkernel"] == 2
+    assert K["lbhyp"][4] == -8 and K["ubhyp"][4] == -3 and np.all(K["ubhyp"][5:] == 1)
+    assert np.isclose(scaling[4], 0.5) and np.allclose(scaling[5:], 0.1)
+    with pytest.raises(ValueError):
+        kriginfocheck(dict(type="kriging", nugget=-6, optimizer="adam"), -5, 5, 2)
+
+
+def test_cmaes_and_ga_minimise_with_batched_objective():
+    from bayesianopttools_b200.optim_tools.cmaes import fmin_batched
+    from bayesianopttools_b200.optim_tools.ga.uncGA import uncGA
+    calls = []
+
+    def sphere(P):
+        calls.append(len(P))
+        return np.sum((P - 0.7) ** 2, axis=1)
+
+    bx, bf, es = fmin_batched(sphere, np.zeros(5), 2.0, bounds=[-5 * np.ones(5), 5 * np.ones(5)], popsize=16,
+                              seed=1)
+    assert bf < 1e-12 and np.allclose(bx, 0.7, atol=1e-5) and set(calls) == {16}
+    bx, bf, _ = uncGA(sphere, lb=-5 * np.ones(3), ub=5 * np.ones(3), npop=60, maxg=80, seed=2)
+    assert bf < 1e-2
+
+
+def test_pls_rotations_match_reference_fixture():
+    from bayesianopttools_b200.surrogate_models.kpls_model import pls1_rotations
+    g = load_golden("kpls")
+    W = pls1_rotations(g["X_norm"], g["y"], int(g["n_princomp"]))
+    assert relerr(W ** 2, g["plscoeff"] ** 2) < 1e-9
