@@ -73,6 +73,8 @@ _SIGNATURES = [
     ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  C.c_int, C.c_int, c_double_p, c_double_p]),
     ("kb_measure_peak", C.c_int, [C.c_int, C.c_int, c_double_p]),
+    ("kb_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
+    ("kb_get_stage_ms", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     ("kb_launch_count", C.c_longlong, []),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -185,6 +187,15 @@ class DeviceModel:
 
     def reserve_population(self, B):
         check(self._lib.kb_reserve_population(self._h, int(B)))
+
+    def set_profiling(self, on=True):
+        check(self._lib.kb_set_profiling(self._h, int(bool(on))))
+
+    def stage_ms(self, back=0):
+        """(decode, build, chol, gls, predict) device milliseconds, `back` calls ago (-1: none)."""
+        buf = (C.c_float * 5)()
+        check(self._lib.kb_get_stage_ms(self._h, int(back), buf))
+        return tuple(float(v) for v in buf)
 
     def set_stream(self, cuda_stream):
         check(self._lib.kb_model_set_stream(self._h, C.c_void_p(int(cuda_stream))))

@@ -28,6 +28,7 @@ static std::atomic<long long> g_launches{0};
       KB_FAIL(KB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
 
+#define KB_PROF_RING 32
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct KbPopWs {       // one augmented-matrix workspace (population or fit geometry)
@@ -79,6 +80,11 @@ struct kb_model {
   double* stage_out = nullptr;
   long long stage_pts = 0;
   int stage_nout = 0;
+  // optional per-stage timing (bench roofline): decode|build|chol|gls boundaries, predict
+  int profile = 0;
+  cudaEvent_t ev[KB_PROF_RING][5] = {};
+  cudaEvent_t evp[KB_PROF_RING][2] = {};
+  long long pop_calls = 0, pred_calls = 0;
 };
 
 extern int kb_predict_max_grid(int kmask, int d, int num_sms);
@@ -201,16 +207,23 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
   if (!has_weights && m->nkernel > 1)
     KB_FAIL(KB_ERR_INVALID, "composite kernel needs %d weights in the hyper-parameter vector", m->nkernel);
   KbModelDev md{m->n, m->d, m->nind, m->n_pad, m->nb, m->kmask, m->XT, m->y, m->F};
+  const bool prof = m->profile && (&w == &m->pop);
+  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][0], m->stream));
   CK(kb_launch_decode(m->stream, B, nbhyp, xpop_dev, m->d, nth, trainvar, has_nugget, has_weights,
                       fixed_nugget, m->nkernel, m->kernel_ids_dev,
                       (m->model_type == KB_TYPE_KPLS) ? m->pls : nullptr, w.hp));
+  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][1], m->stream));
   CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug));
   CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
+  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
   w.epoch += 1;
   CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.flags, w.epoch, w.tasks, w.ntasks, w.counter,
                     w.info, m->num_sms));
+  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][3], m->stream));
   CK(kb_launch_gls(m->stream, w.g, B, w.aug, trainvar, w.hp.sigma2, w.Mbuf, w.beta, w.sigma2, nll_dev,
                    w.info, rt_out, w.lndet));
+  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][4], m->stream));
+  if (prof) m->pop_calls += 1;
   g_launches += 4;
   return KB_OK;
 }
@@ -323,6 +336,38 @@ kb_status kb_model_sync(kb_model* m) {
   if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
   CK(cudaSetDevice(m->device));
   CK(cudaStreamSynchronize(m->stream));
+  return KB_OK;
+}
+
+kb_status kb_set_profiling(kb_model* m, int on) {
+  if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
+  CK(cudaSetDevice(m->device));
+  if (on && !m->ev[0][0]) {
+    for (int r = 0; r < KB_PROF_RING; ++r) {
+      for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&m->ev[r][i]));
+      for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&m->evp[r][i]));
+    }
+  }
+  m->profile = on ? 1 : 0;
+  m->pop_calls = m->pred_calls = 0;
+  return KB_OK;
+}
+
+kb_status kb_get_stage_ms(kb_model* m, int back, float* ms5) {
+  if (!m || !ms5 || !m->ev[0][0]) KB_FAIL(KB_ERR_INVALID, "profiling is not enabled");
+  if (back < 0 || back >= KB_PROF_RING) KB_FAIL(KB_ERR_INVALID, "history depth is %d", KB_PROF_RING);
+  CK(cudaSetDevice(m->device));
+  for (int i = 0; i < 5; ++i) ms5[i] = -1.f;
+  if (m->pop_calls > back) {
+    cudaEvent_t* e = m->ev[(m->pop_calls - 1 - back) % KB_PROF_RING];
+    CK(cudaEventSynchronize(e[4]));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms5[i], e[i], e[i + 1]));
+  }
+  if (m->pred_calls > back) {
+    cudaEvent_t* e = m->evp[(m->pred_calls - 1 - back) % KB_PROF_RING];
+    CK(cudaEventSynchronize(e[1]));
+    CK(cudaEventElapsedTime(&ms5[4], e[0], e[1]));
+  }
   return KB_OK;
 }
 
@@ -507,7 +552,9 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
   const long long nstrips = (npts + 63) / 64;
   const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);
+  if (m->profile) CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][0], m->stream));
   CK(kb_launch_predict(m->stream, a, grid, result_dev));
+  if (m->profile) { CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][1], m->stream)); m->pred_calls += 1; }
   g_launches += result_dev ? 2 : 1;
   return KB_OK;
 }

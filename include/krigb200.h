@@ -137,6 +137,13 @@ kb_status kb_corr_matrix(int device, int n, int m, int d, const double* XN, cons
  * 1 scalar DFMA, 2 device-to-device copy.  Returns TFLOP/s (0,1) or GB/s (2). */
 kb_status kb_measure_peak(int device, int which, double* value);
 
+/* Per-stage device timing, measured with CUDA events on the handle's stream:
+ * ms5 = {decode, correlation build, Cholesky, GLS reductions, predict}; `back` = 0 is the most
+ * recent population call / predict launch, up to 31 calls back (-1 where no such call).
+ * Enable with kb_set_profiling(m, 1): it adds event records only, no synchronisation. */
+kb_status kb_set_profiling(kb_model* m, int on);
+kb_status kb_get_stage_ms(kb_model* m, int back, float* ms5);
+
 /* Kernel launches issued by this library since process start (bench "gpu_launches"). */
 long long kb_launch_count(void);
 
