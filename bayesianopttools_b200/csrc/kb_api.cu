@@ -158,8 +158,8 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   const int d = m->d, nind = m->nind;
   CK(cudaMalloc(&w.aug, sizeof(double) * g.stride * B));
   CK(cudaMalloc(&w.dinv, sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE));
-  CK(cudaMalloc(&w.flags, sizeof(int) * (size_t)B * g.NT * g.NT));
-  CK(cudaMemset(w.flags, 0, sizeof(int) * (size_t)B * g.NT * g.NT));
+  CK(cudaMalloc(&w.flags, sizeof(int) * (size_t)B * g.NT));
+  CK(cudaMemset(w.flags, 0, sizeof(int) * (size_t)B * g.NT));
   std::vector<int4> tasks;
   build_tasks(g, B, tasks);
   CK(cudaMalloc(&w.tasks, tasks.size() * sizeof(int4)));
@@ -217,6 +217,10 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
   CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
   w.epoch += 1;
+  if (w.epoch >= (1 << 20)) {          // row-progress words are (epoch << 10) + columns
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)w.B_cap * w.g.NT, m->stream));
+    w.epoch = 1;
+  }
   CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.flags, w.epoch, w.tasks, w.ntasks, w.counter,
                     w.info, m->num_sms));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][3], m->stream));

@@ -36,9 +36,138 @@ struct KbCholSmem {
   double a[KB_STAGES][KB_TILE][KB_LDK];
   double b[KB_STAGES][KB_TILE][KB_LDK];
   int task;
+  int ready;
 };
 static_assert(sizeof(double) * KB_STAGES * KB_TILE * KB_LDK >= sizeof(double) * KB_TILE * KB_LDC,
               "epilogue tiles alias the pipeline buffers");
+
+
+#define KB_LDT 12       // row stride of the per-warp 16x8 scratch tile (12 == 12 mod 16: conflict free)
+static_assert(sizeof(double) * (KB_TILE * KB_LDC + 8 * 16 * KB_LDT) <=
+                  sizeof(double) * KB_STAGES * KB_TILE * KB_LDK, "diag scratch must fit behind Ds");
+
+// 64x64 SPD tile in Cs (lower part used) -> Cs = L (lower), Ds = L^-1 (lower, zeros above).
+// Right-looking with 16-wide panels.  The 16x16 diagonal blocks are factored AND inverted by
+// warp 0 entirely in registers (lane r owns row r; columns travel by shuffle) - the only serial
+// chain left is 64 x (rsqrt -> scale -> shuffle).  Panels, trailing updates and the off-diagonal
+// blocks of the inverse are 8x8x4 DMMA products on padded shared tiles (conflict free).
+__device__ __forceinline__ void kb_diag_factor_inverse(double (*Cs)[KB_LDC], double (*Ds)[KB_LDC],
+                                                       double* Ts_base, int* info, int pivot_base) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const unsigned FULL = 0xffffffffu;
+  for (int e = tid; e < KB_TILE * KB_TILE; e += KB_THREADS) Ds[e >> 6][e & 63] = 0.0;
+  __syncthreads();
+  for (int jb = 0; jb < 4; ++jb) {
+    const int c0 = jb * 16;
+    if (warp == 0) {
+      const int r = lane & 15;
+      double a[16], x[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { a[c] = Cs[c0 + r][c0 + c]; x[c] = 0.0; }
+      double invd = 1.0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double piv = __shfl_sync(FULL, a[j], j);
+        if (!(piv > 0.0)) {          // not positive definite (or NaN): flag, keep the batch alive
+          if (lane == 0) atomicCAS(info, 0, pivot_base + c0 + j + 1);
+          piv = 1.0;
+        }
+        const double inv = rsqrt(piv);
+        const double l = (r == j) ? piv * inv : a[j] * inv;
+        if (r == j) invd = inv;
+        a[j] = l;
+#pragma unroll
+        for (int c = j + 1; c < 16; ++c) {
+          const double lc = __shfl_sync(FULL, l, c);
+          if (r >= c) a[c] = fma(-l, lc, a[c]);
+        }
+      }
+      // inverse of the 16x16 factor, row by row (row k is final when the sweep reaches k)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int c = 0; c <= k; ++c) {
+          const double t = (c == k) ? invd : -x[c] * invd;
+          const double xk = __shfl_sync(FULL, t, k);
+          if (r == k) x[c] = t;
+          else if (r > k) x[c] = fma(a[k], xk, x[c]);
+        }
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          Cs[c0 + r][c0 + c] = a[c];
+          Ds[c0 + r][c0 + c] = (c <= r) ? x[c] : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    if (jb == 3) break;
+    // panel: rows below the block, P = A * inv(L_D)^T ; one warp per 8 rows, both 8-column halves
+    const int nrb = (KB_TILE - 16 - c0) / 8;
+    if (warp < nrb) {
+      const int r0 = c0 + 16 + 8 * warp;
+      double af[4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) af[ks] = Cs[r0 + gq][c0 + ks * 4 + tq];
+      double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) kb_dmma(p[ni][0], p[ni][1], af[ks], Ds[c0 + ni * 8 + gq][c0 + ks * 4 + tq]);
+      __syncwarp();
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+        *reinterpret_cast<double2*>(&Cs[r0 + gq][c0 + ni * 8 + 2 * tq]) = make_double2(p[ni][0], p[ni][1]);
+    }
+    __syncthreads();
+    // trailing update of the lower 8x8 tiles: C -= P P^T
+    const int mt = nrb, ntile = mt * (mt + 1) / 2;
+    for (int t = warp; t < ntile; t += 8) {
+      int ri = 0;
+      while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
+      const int ci = t - ri * (ri + 1) / 2;
+      const int r0 = c0 + 16 + 8 * ri, cc0 = c0 + 16 + 8 * ci;
+      double2 cv = *reinterpret_cast<double2*>(&Cs[r0 + gq][cc0 + 2 * tq]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        kb_dmma(cv.x, cv.y, -Cs[r0 + gq][c0 + ks * 4 + tq], Cs[cc0 + gq][c0 + ks * 4 + tq]);
+      *reinterpret_cast<double2*>(&Cs[r0 + gq][cc0 + 2 * tq]) = cv;
+    }
+    __syncthreads();
+  }
+  // off-diagonal 16x16 blocks of the inverse, by block distance:
+  //   X_ij = -inv(L_ii) * sum_{k=j}^{i-1} L_ik X_kj
+  double* Ts = Ts_base + warp * 16 * KB_LDT;
+  for (int delta = 1; delta <= 3; ++delta) {
+    const int nblk = 4 - delta;
+    if (warp < 2 * nblk) {
+      const int j = warp >> 1, h = warp & 1, i = j + delta;
+      double t0[2] = {0.0, 0.0}, t1[2] = {0.0, 0.0};
+      for (int kb = j; kb < i; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double bv = Ds[kb * 16 + ks * 4 + tq][j * 16 + h * 8 + gq];
+          kb_dmma(t0[0], t0[1], Cs[i * 16 + gq][kb * 16 + ks * 4 + tq], bv);
+          kb_dmma(t1[0], t1[1], Cs[i * 16 + 8 + gq][kb * 16 + ks * 4 + tq], bv);
+        }
+      *reinterpret_cast<double2*>(&Ts[gq * KB_LDT + 2 * tq]) = make_double2(t0[0], t0[1]);
+      *reinterpret_cast<double2*>(&Ts[(8 + gq) * KB_LDT + 2 * tq]) = make_double2(t1[0], t1[1]);
+      __syncwarp();
+      double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const double bv = Ts[(ks * 4 + tq) * KB_LDT + gq];
+        kb_dmma(x0[0], x0[1], Ds[i * 16 + gq][i * 16 + ks * 4 + tq], bv);
+        kb_dmma(x1[0], x1[1], Ds[i * 16 + 8 + gq][i * 16 + ks * 4 + tq], bv);
+      }
+      *reinterpret_cast<double2*>(&Ds[i * 16 + gq][j * 16 + h * 8 + 2 * tq]) = make_double2(-x0[0], -x0[1]);
+      *reinterpret_cast<double2*>(&Ds[i * 16 + 8 + gq][j * 16 + h * 8 + 2 * tq]) = make_double2(-x1[0], -x1[1]);
+    }
+    __syncthreads();
+  }
+}
 
 __global__ void __launch_bounds__(KB_THREADS, 2)
 kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv, int* __restrict__ flags,
@@ -48,6 +177,7 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
   KbCholSmem& sm = *reinterpret_cast<KbCholSmem*>(smem_raw);
   double (*Cs)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.a[0][0][0]);
   double (*Ds)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.b[0][0][0]);
+  double* Ts_base = &sm.b[0][0][0] + KB_TILE * KB_LDC;     // 8 warps x 16 x KB_LDT scratch after Ds
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
@@ -63,15 +193,27 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
     const int4 T = tasks[tk];
     const int b = T.x, ti = T.y, tkc = T.z, type = T.w;
     double* A = aug + (size_t)b * g.stride;
-    int* fl = flags + (size_t)b * NT * NT;
+    int* fl = flags + (size_t)b * NT;
     const int kt = (tkc < g.nb) ? tkc : g.nb;
 
-    // ---- wait for the input tiles (all earlier in the queue) -------------
-    for (int p = tid; p < 2 * kt; p += KB_THREADS) {
-      const int* f = (p < kt) ? &fl[ti * NT + p] : &fl[tkc * NT + (p - kt)];
-      while (kb_flag_acquire(f) != epoch) __nanosleep(64);
+    // ---- input tiles: row-progress counters, polled only when the K loop catches up ----
+    // prog[r] = (epoch << 10) + number of leading tile columns of row r that are final.
+    const int ebase = epoch << 10;
+    int ready_cols = 0;
+    if (kt > 0) {
+      if (tid == 0) {
+        int ra, rb;
+        while (true) {
+          ra = kb_flag_acquire(&fl[ti]) - ebase;
+          rb = kb_flag_acquire(&fl[tkc]) - ebase;
+          if (ra >= 1 && rb >= 1) break;
+          __nanosleep(64);
+        }
+        sm.ready = ra < rb ? ra : rb;
+      }
+      __syncthreads();
+      ready_cols = sm.ready;
     }
-    __syncthreads();
 
     // ---- C_acc = sum_p L[i,p] L[k,p]^T on the FP64 tensor pipe ------------
     double acc[2][4][2];
@@ -102,10 +244,23 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
       kb_cp_async_commit();
     }
     for (int c = 0; c < nchunks; ++c) {
+      const int cn = c + KB_STAGES - 1;
+      const int pn = cn / (KB_TILE / KB_KC);          // tile column the next prefetch reads
+      const bool poll = (cn < nchunks) && (pn >= ready_cols);
+      if (poll && tid == 0) {
+        int ra, rb;
+        while (true) {
+          ra = kb_flag_acquire(&fl[ti]) - ebase;
+          rb = kb_flag_acquire(&fl[tkc]) - ebase;
+          if (ra > pn && rb > pn) break;
+          __nanosleep(64);
+        }
+        sm.ready = ra < rb ? ra : rb;
+      }
       kb_cp_async_wait<KB_STAGES - 2>();
       __syncthreads();
+      if (poll) ready_cols = sm.ready;
       {
-        const int cn = c + KB_STAGES - 1;
         if (cn < nchunks) load_chunk(cn, cn % KB_STAGES);
         kb_cp_async_commit();
       }
@@ -161,7 +316,7 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
       if (type == KB_TASK_OFF) {
         // L[i,k] = C * inv(L[k,k])^T : wait for the diagonal task, then one 64^3 DMMA multiply
         if (tid == 0)
-          while (kb_flag_acquire(&fl[tkc * NT + tkc]) != epoch) __nanosleep(64);
+          while (kb_flag_acquire(&fl[tkc]) - ebase < tkc + 1) __nanosleep(64);
         __syncthreads();
         const double* Dg = dinv + ((size_t)b * g.nb + tkc) * (KB_TILE * KB_TILE);
 #pragma unroll
@@ -198,45 +353,8 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
                 make_double2(acc[mi][ni][0], acc[mi][ni][1]);
           }
       } else {
-        // ---- diagonal tile: unblocked POTRF in shared memory ---------------
-        for (int j = 0; j < KB_TILE; ++j) {
-          __syncthreads();
-          double dj = Cs[j][j];
-          if (!(dj > 0.0)) {   // not positive definite (or NaN): flag, keep the batch alive
-            if (tid == 0) atomicCAS(&info[b], 0, tkc * KB_TILE + j + 1);
-            dj = 1.0;
-          }
-          const double sj = sqrt(dj), inv = 1.0 / sj;
-          __syncthreads();
-          if (tid < KB_TILE) {
-            if (tid > j) Cs[tid][j] *= inv;
-            else if (tid == j) Cs[j][j] = sj;
-          }
-          __syncthreads();
-          const int nel = (KB_TILE - 1 - j) * KB_TILE;
-          for (int e = tid; e < nel; e += KB_THREADS) {
-            const int r = j + 1 + (e >> 6), c = e & 63;
-            if (c > j && c <= r) Cs[r][c] -= Cs[r][j] * Cs[c][j];
-          }
-        }
-        __syncthreads();
-        // ---- inverse of the 64x64 lower factor (row-by-row elimination) ----
-        for (int e = tid; e < KB_TILE * KB_TILE; e += KB_THREADS) {
-          const int r = e >> 6, c = e & 63;
-          Ds[r][c] = (r == c) ? 1.0 : 0.0;
-        }
-        for (int j = 0; j < KB_TILE; ++j) {
-          __syncthreads();
-          const double inv = 1.0 / Cs[j][j];
-          if (tid <= j) Ds[j][tid] *= inv;
-          __syncthreads();
-          const int nel = (KB_TILE - 1 - j) * KB_TILE;
-          for (int e = tid; e < nel; e += KB_THREADS) {
-            const int r = j + 1 + (e >> 6), c = e & 63;
-            if (c <= j) Ds[r][c] -= Cs[r][j] * Ds[j][c];
-          }
-        }
-        __syncthreads();
+        // ---- diagonal tile: blocked (16) POTRF + inverse, DMMA for every block update ----
+        kb_diag_factor_inverse(Cs, Ds, Ts_base, &info[b], tkc * KB_TILE);
         double* Dg = dinv + ((size_t)b * g.nb + tkc) * (KB_TILE * KB_TILE);
         for (int e = tid; e < KB_TILE * KB_TILE; e += KB_THREADS) {
           const int r = e >> 6, c = e & 63;
@@ -247,9 +365,9 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
     }
     // ---- publish the tile ---------------------------------------------------
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && type != KB_TASK_SCHUR) {
       __threadfence();
-      kb_flag_release(&fl[ti * NT + tkc], epoch);
+      kb_flag_release(&fl[ti], ebase + tkc + 1);
     }
   }
 }
