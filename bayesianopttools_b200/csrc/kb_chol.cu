@@ -24,6 +24,10 @@
 //  * Operand tiles stream L2 -> shared memory through a 3-stage cp.async ring;
 //    shared tiles are padded (row stride == 4 mod 16 doubles) so every DMMA
 //    fragment load is bank-conflict free.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "kb_common.cuh"
 #include "kb_internal.h"
 
@@ -42,9 +46,27 @@ static_assert(sizeof(double) * KB_STAGES * KB_TILE * KB_LDK >= sizeof(double) * 
               "epilogue tiles alias the pipeline buffers");
 
 
+__device__ __forceinline__ unsigned long long kb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 #define KB_LDT 12       // row stride of the per-warp 16x8 scratch tile (12 == 12 mod 16: conflict free)
 static_assert(sizeof(double) * (KB_TILE * KB_LDC + 8 * 16 * KB_LDT) <=
                   sizeof(double) * KB_STAGES * KB_TILE * KB_LDK, "diag scratch must fit behind Ds");
+
+// 1/sqrt(p) to full FP64 accuracy with a 4-deep dependent chain: hardware approximation
+// (relative error ~2^-23) + one third-order step  y (1 + e/2 + 3e^2/8),  e = 1 - p y^2.
+__device__ __forceinline__ double kb_rsqrt(double p) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  const double py = p * y;
+  const double e = fma(-py, y, 1.0);
+  const double ye = y * e;
+  const double q = fma(e, 0.375, 0.5);
+  return fma(ye, q, y);
+}
 
 // 64x64 SPD tile in Cs (lower part used) -> Cs = L (lower), Ds = L^-1 (lower, zeros above).
 // Right-looking with 16-wide panels.  The 16x16 diagonal blocks are factored AND inverted by
@@ -60,47 +82,39 @@ __device__ __forceinline__ void kb_diag_factor_inverse(double (*Cs)[KB_LDC], dou
   __syncthreads();
   for (int jb = 0; jb < 4; ++jb) {
     const int c0 = jb * 16;
-    if (warp == 0) {
-      const int r = lane & 15;
-      double a[16], x[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) { a[c] = Cs[c0 + r][c0 + c]; x[c] = 0.0; }
-      double invd = 1.0;
-#pragma unroll
+    {
+      // 16x16 diagonal block: factor AND invert with one element of each per thread
+      // (thread (r,c) keeps A[r][c] and W[r][c] in registers).  Per column j the pivot column
+      // and the finished inverse row travel through a double-buffered 32-double shared
+      // exchange: ONE block barrier per column, and every thread redoes the 4-op rsqrt so the
+      // serial chain is  barrier -> rsqrt -> scale -> fma.  (A single-warp register/shuffle
+      // version was issue-bound at ~4 clk per instruction.)
+      const int r = tid >> 4, c = tid & 15;
+      double a = Cs[c0 + r][c0 + c];
+      double w = (r == c) ? 1.0 : 0.0;
+      double* xch = Ts_base;                       // [2][32]: column of A | row of W
+#pragma unroll 1
       for (int j = 0; j < 16; ++j) {
-        double piv = __shfl_sync(FULL, a[j], j);
+        double* buf = xch + (j & 1) * 32;
+        if (c == j) buf[r] = a;
+        if (r == j) buf[16 + c] = w;
+        __syncthreads();
+        double piv = buf[j];
         if (!(piv > 0.0)) {          // not positive definite (or NaN): flag, keep the batch alive
-          if (lane == 0) atomicCAS(info, 0, pivot_base + c0 + j + 1);
+          if (tid == 0) atomicCAS(info, 0, pivot_base + c0 + j + 1);
           piv = 1.0;
         }
-        const double inv = rsqrt(piv);
-        const double l = (r == j) ? piv * inv : a[j] * inv;
-        if (r == j) invd = inv;
-        a[j] = l;
-#pragma unroll
-        for (int c = j + 1; c < 16; ++c) {
-          const double lc = __shfl_sync(FULL, l, c);
-          if (r >= c) a[c] = fma(-l, lc, a[c]);
-        }
+        const double inv = kb_rsqrt(piv);
+        const double lr = (r == j) ? piv * inv : buf[r] * inv;     // L[r][j]
+        const double lc = buf[c] * inv;                            // L[c][j]
+        const double xj = buf[16 + c] * inv;                       // X[j][c]
+        if (c == j) a = lr;
+        else if (c > j) a = fma(-lr, lc, a);
+        if (r == j) w = xj;
+        else if (r > j) w = fma(-lr, xj, w);
       }
-      // inverse of the 16x16 factor, row by row (row k is final when the sweep reaches k)
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-#pragma unroll
-        for (int c = 0; c <= k; ++c) {
-          const double t = (c == k) ? invd : -x[c] * invd;
-          const double xk = __shfl_sync(FULL, t, k);
-          if (r == k) x[c] = t;
-          else if (r > k) x[c] = fma(a[k], xk, x[c]);
-        }
-      }
-      if (lane < 16) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          Cs[c0 + r][c0 + c] = a[c];
-          Ds[c0 + r][c0 + c] = (c <= r) ? x[c] : 0.0;
-        }
-      }
+      if (c <= r) Cs[c0 + r][c0 + c] = a;
+      Ds[c0 + r][c0 + c] = (c <= r) ? w : 0.0;
     }
     __syncthreads();
     if (jb == 3) break;
@@ -172,7 +186,7 @@ __device__ __forceinline__ void kb_diag_factor_inverse(double (*Cs)[KB_LDC], dou
 __global__ void __launch_bounds__(KB_THREADS, 2)
 kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv, int* __restrict__ flags,
                int epoch, const int4* __restrict__ tasks, int ntasks, int* __restrict__ counter,
-               int* __restrict__ info) {
+               int* __restrict__ info, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KbCholSmem& sm = *reinterpret_cast<KbCholSmem*>(smem_raw);
   double (*Cs)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.a[0][0][0]);
@@ -192,6 +206,8 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
     if (tk >= ntasks) break;
     const int4 T = tasks[tk];
     const int b = T.x, ti = T.y, tkc = T.z, type = T.w;
+    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
+    if (trace && tid == 0) tr0 = kb_globaltimer();
     double* A = aug + (size_t)b * g.stride;
     int* fl = flags + (size_t)b * NT;
     const int kt = (tkc < g.nb) ? tkc : g.nb;
@@ -215,6 +231,7 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
       ready_cols = sm.ready;
     }
 
+    if (trace && tid == 0) tr1 = kb_globaltimer();
     // ---- C_acc = sum_p L[i,p] L[k,p]^T on the FP64 tensor pipe ------------
     double acc[2][4][2];
 #pragma unroll
@@ -283,6 +300,7 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
     kb_cp_async_wait<0>();
     __syncthreads();
 
+    if (trace && tid == 0) tr2 = kb_globaltimer();
     // ---- C = A[i,k] - C_acc ------------------------------------------------
     double* Atile = A + (size_t)ti * KB_TILE * ld + (size_t)tkc * KB_TILE;
 #pragma unroll
@@ -318,6 +336,7 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
         if (tid == 0)
           while (kb_flag_acquire(&fl[tkc]) - ebase < tkc + 1) __nanosleep(64);
         __syncthreads();
+        if (trace && tid == 0) tr3 = kb_globaltimer();
         const double* Dg = dinv + ((size_t)b * g.nb + tkc) * (KB_TILE * KB_TILE);
 #pragma unroll
         for (int j = 0; j < (KB_TILE * KB_TILE / 2) / KB_THREADS; ++j) {
@@ -369,6 +388,14 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
       __threadfence();
       kb_flag_release(&fl[ti], ebase + tkc + 1);
     }
+    if (trace && tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* t = trace + (size_t)tk * 8;
+      t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = tr3; t[4] = kb_globaltimer();
+      t[5] = ((unsigned long long)b << 40) | ((unsigned long long)ti << 24) | ((unsigned long long)tkc << 8) | type;
+      t[6] = smid; t[7] = blockIdx.x;
+    }
   }
 }
 
@@ -385,6 +412,23 @@ cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* a
   int grid = num_sms * 2;
   if (grid > ntasks) grid = ntasks;
   if (grid < 1) grid = 1;
-  kb_chol_kernel<<<grid, KB_THREADS, smem, st>>>(g, aug, dinv, flags, epoch, tasks, ntasks, counter, info);
-  return cudaGetLastError();
+  // Debug aid: KB_CHOL_TRACE=<file> dumps per-task timestamps (ns) of this launch.
+  static const char* trace_path = getenv("KB_CHOL_TRACE");
+  unsigned long long* trace = nullptr;
+  if (trace_path) {
+    e = cudaMalloc(&trace, sizeof(unsigned long long) * 8 * (size_t)ntasks);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 8 * (size_t)ntasks, st);
+  }
+  kb_chol_kernel<<<grid, KB_THREADS, smem, st>>>(g, aug, dinv, flags, epoch, tasks, ntasks, counter, info, trace);
+  e = cudaGetLastError();
+  if (trace_path && e == cudaSuccess) {
+    std::vector<unsigned long long> h((size_t)ntasks * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(trace_path, "wb");
+    if (f) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+    cudaFree(trace);
+  }
+  return e;
 }
