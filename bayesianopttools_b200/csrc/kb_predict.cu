@@ -58,7 +58,7 @@ struct KbRunning {
 };
 
 template <int MASK>
-__global__ void __launch_bounds__(KB_THREADS)
+__global__ void __launch_bounds__(KB_THREADS, 2)
 kb_predict_kernel(KbPredictArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KbPredSmem& sm = *reinterpret_cast<KbPredSmem*>(smem_raw);
