@@ -36,11 +36,9 @@ struct KbPopWs {       // one augmented-matrix workspace (population or fit geom
   int B_cap = 0;
   double* aug = nullptr;
   double* dinv = nullptr;
-  int* flags = nullptr;
-  int epoch = 0;
+  int* sync_words = nullptr;
   int4* tasks = nullptr;
   int ntasks = 0, tasks_B = 0;
-  int* counter = nullptr;
   int* info = nullptr;
   KbHyper hp{};
   double *Mbuf = nullptr, *beta = nullptr, *sigma2 = nullptr, *nll = nullptr, *lndet = nullptr;
@@ -107,30 +105,8 @@ static KbAugGeom make_geom(int n, int nind, bool fit_mode) {
   return g;
 }
 
-// Task queue with one-column look-ahead; every dependency precedes its user.
-static void build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
-  out.clear();
-  struct T3 { int i, k, type; };
-  auto emit = [&](const std::vector<T3>& seg) {
-    for (int b = 0; b < B; ++b)
-      for (const T3& t : seg) out.push_back(make_int4(b, t.i, t.k, t.type));
-  };
-  emit({{0, 0, KB_TASK_DIAG}});
-  for (int k = 0; k < g.nb; ++k) {
-    if (k + 1 < g.NT) emit({{k + 1, k, KB_TASK_OFF}});
-    if (k + 1 < g.nb) emit({{k + 1, k + 1, KB_TASK_DIAG}});
-    std::vector<T3> seg;
-    for (int i = k + 2; i < g.NT; ++i) seg.push_back({i, k, KB_TASK_OFF});
-    emit(seg);
-  }
-  std::vector<T3> seg;
-  for (int kk = g.nb; kk < g.nb + g.sb; ++kk)
-    for (int i = kk; i < g.nb + g.sb; ++i) seg.push_back({i, kk, KB_TASK_SCHUR});
-  emit(seg);
-}
-
 static void free_ws(KbPopWs& w) {
-  cudaFree(w.aug); cudaFree(w.dinv); cudaFree(w.flags); cudaFree(w.tasks); cudaFree(w.counter);
+  cudaFree(w.aug); cudaFree(w.dinv); cudaFree(w.sync_words); cudaFree(w.tasks);
   cudaFree(w.info); cudaFree(w.hp.gw); cudaFree(w.hp.ith); cudaFree(w.hp.wk); cudaFree(w.hp.eps);
   cudaFree(w.hp.sigma2); cudaFree(w.hp.nugget); cudaFree(w.Mbuf); cudaFree(w.beta); cudaFree(w.sigma2);
   cudaFree(w.nll); cudaFree(w.lndet); cudaFree(w.xpop);
@@ -141,7 +117,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   if (B <= w.B_cap) {
     if (w.tasks_B != B) {
       std::vector<int4> tasks;
-      build_tasks(w.g, B, tasks);
+      kb_chol_build_tasks(w.g, B, tasks);
       CK(cudaMemcpyAsync(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, m->stream));
       CK(cudaStreamSynchronize(m->stream));
       w.ntasks = (int)tasks.size();
@@ -150,23 +126,19 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
     return KB_OK;
   }
   CK(cudaStreamSynchronize(m->stream));
-  const int epoch = w.epoch;
   free_ws(w);
-  w.epoch = epoch;
   w.g = make_geom(m->n, m->nind, fit_mode);
   const KbAugGeom& g = w.g;
   const int d = m->d, nind = m->nind;
   CK(cudaMalloc(&w.aug, sizeof(double) * g.stride * B));
   CK(cudaMalloc(&w.dinv, sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE));
-  CK(cudaMalloc(&w.flags, sizeof(int) * (size_t)B * g.NT));
-  CK(cudaMemset(w.flags, 0, sizeof(int) * (size_t)B * g.NT));
+  CK(cudaMalloc(&w.sync_words, sizeof(int) * kb_chol_sync_words(g, B)));
   std::vector<int4> tasks;
-  build_tasks(g, B, tasks);
+  kb_chol_build_tasks(g, B, tasks);
   CK(cudaMalloc(&w.tasks, tasks.size() * sizeof(int4)));
   CK(cudaMemcpy(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
   w.ntasks = (int)tasks.size();
   w.tasks_B = B;
-  CK(cudaMalloc(&w.counter, sizeof(int)));
   CK(cudaMalloc(&w.info, sizeof(int) * B));
   CK(cudaMalloc(&w.hp.gw, sizeof(double) * (size_t)B * d));
   CK(cudaMalloc(&w.hp.ith, sizeof(double) * (size_t)B * d));
@@ -216,13 +188,7 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
   CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug));
   CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
-  w.epoch += 1;
-  if (w.epoch >= (1 << 20)) {          // row-progress words are (epoch << 10) + columns
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)w.B_cap * w.g.NT, m->stream));
-    w.epoch = 1;
-  }
-  CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.flags, w.epoch, w.tasks, w.ntasks, w.counter,
-                    w.info, m->num_sms));
+  CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.sync_words, w.tasks, w.ntasks, w.info, m->num_sms));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][3], m->stream));
   CK(kb_launch_gls(m->stream, w.g, B, w.aug, trainvar, w.hp.sigma2, w.Mbuf, w.beta, w.sigma2, nll_dev,
                    w.info, rt_out, w.lndet));

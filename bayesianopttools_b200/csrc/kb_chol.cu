@@ -10,41 +10,50 @@
 //    the factorisation also produces L^-1 y, L^-1 F (and L^-T in fit mode), and
 //    the trailing Schur tile is -(L^-1[y F])^T (L^-1[y F]) = the GLS normal
 //    equations.  No separate, latency-bound forward substitution exists.
-//  * Left-looking TILE task graph: task (i,k) computes
-//        C = A[i,k] - sum_{p<k} L[i,p] L[k,p]^T        (DMMA m8n8k4, K = 64k)
-//    with the accumulator held in registers for the whole K loop (each tile is
-//    read once and written once), then POTRF+inverse (diagonal) or a DMMA
-//    multiply by the inverted diagonal block (off-diagonal).
-//  * One persistent launch for the whole population: CTAs pull tasks from a
-//    global queue ordered (with one-column look-ahead) so that every dependency
-//    is EARLIER in the queue; tile completion is published with release/acquire
-//    flags.  A CTA that claimed a task is running, so the oldest unfinished task
-//    always has all inputs -> no deadlock, no grid-wide barrier, and all SMs
-//    stay busy across candidates regardless of population size.
-//  * Operand tiles stream L2 -> shared memory through a 3-stage cp.async ring;
-//    shared tiles are padded (row stride == 4 mod 16 doubles) so every DMMA
-//    fragment load is bank-conflict free.
+//  * Left-looking 64x64 TILE tasks  C = A[i,k] - sum_{p<k} L[i,p] L[k,p]^T  (DMMA m8n8k4, the
+//    accumulator stays in registers for the whole K loop) followed by one DMMA multiply with the
+//    inverted diagonal block.  One persistent launch for the whole population; CTAs split in
+//    two roles so that the serial chain never queues behind (or shares an FP64 pipe with) bulk work:
+//      - CHAIN workers (the CTAs of a few SMs) walk the critical path of their candidates,
+//        step k:  L[k,k-1] = C1 Dinv_{k-1}^T ;  C2 -= L[k,k-1] L[k,k-1]^T ;  factor + invert
+//        C2 -> L[k,k], Dinv_k.  C1/C2 arrive pre-updated with all terms p < k-1 from a bulk
+//        PRE task, so a step is three tile loads, two 64^3 DMMA products and the in-shared
+//        factorisation (kb_diag.cuh) - no global round trip inside the chain.
+//      - BULK workers pull tile tasks from a global queue ordered so that every dependency
+//        is EARLIER in the queue; completion is published through per-row progress words
+//        (st.release.gpu / ld.acquire.gpu), polled only when the K loop catches up with them.
+//        The oldest unfinished task always has all inputs (chain steps run as soon as their PRE
+//        task is done) -> no deadlock and no grid-wide barrier.
+//  * Operand tiles stream L2 -> shared memory through a 3-stage cp.async ring; shared tiles
+//    are padded (row stride == 4 mod 16 doubles) so every DMMA fragment load is conflict free.
+//  * Wasted tensor work is skipped: only the lower 8x8 blocks of diagonal tiles are
+//    accumulated, the multiply by the (triangular) inverse stops at the diagonal, and when the
+//    right-hand sides occupy <= 16 rows (ordinary Kriging: y and 1) they run as THIN tasks
+//    (16 x 64 outputs, one 8-column block per warp).
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
 #include "kb_common.cuh"
 #include "kb_internal.h"
+#include "kb_diag.cuh"
 
 #define KB_KC 32        // K chunk (doubles) per pipeline stage
 #define KB_STAGES 3
 #define KB_LDK 36       // padded row stride of a 64 x KC chunk
-#define KB_LDC 68       // padded row stride of a 64 x 64 tile
 
+// One ring of 384 chunk rows: three stages of (64 A rows + 64 B rows) for the 64-row tasks, or two
+// stages of (128 A rows + 64 B rows) for the 128-row tasks.  Epilogue tiles and the chain worker's
+// three tiles alias it.
+#define KB_RING_ROWS 384
 struct KbCholSmem {
-  double a[KB_STAGES][KB_TILE][KB_LDK];
-  double b[KB_STAGES][KB_TILE][KB_LDK];
+  double ring[KB_RING_ROWS][KB_LDK];
   int task;
   int ready;
+  int misc[6];
 };
-static_assert(sizeof(double) * KB_STAGES * KB_TILE * KB_LDK >= sizeof(double) * KB_TILE * KB_LDC,
-              "epilogue tiles alias the pipeline buffers");
-
+static_assert(sizeof(double) * KB_RING_ROWS * KB_LDK >= sizeof(double) * (3 * KB_TILE * KB_LDC + KB_DIAG_SCRATCH),
+              "three padded tiles and the exchange scratch must fit in the pipeline ring");
 
 __device__ __forceinline__ unsigned long long kb_globaltimer() {
   unsigned long long t;
@@ -52,238 +61,308 @@ __device__ __forceinline__ unsigned long long kb_globaltimer() {
   return t;
 }
 
-#define KB_LDT 12       // row stride of the per-warp 16x8 scratch tile (12 == 12 mod 16: conflict free)
-static_assert(sizeof(double) * (KB_TILE * KB_LDC + 8 * 16 * KB_LDT) <=
-                  sizeof(double) * KB_STAGES * KB_TILE * KB_LDK, "diag scratch must fit behind Ds");
-
-// 1/sqrt(p) to full FP64 accuracy with a 4-deep dependent chain: hardware approximation
-// (relative error ~2^-23) + one third-order step  y (1 + e/2 + 3e^2/8),  e = 1 - p y^2.
-__device__ __forceinline__ double kb_rsqrt(double p) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-  const double py = p * y;
-  const double e = fma(-py, y, 1.0);
-  const double ye = y * e;
-  const double q = fma(e, 0.375, 0.5);
-  return fma(ye, q, y);
+// 64 x 64 tile (row stride ld in global) -> padded shared tile, 16-byte cp.async per thread.
+__device__ __forceinline__ void kb_load_tile_async(double (*dst)[KB_LDC], const double* src, int ld) {
+#pragma unroll
+  for (int j = 0; j < (KB_TILE * KB_TILE / 2) / KB_THREADS; ++j) {
+    const int idx = threadIdx.x + j * KB_THREADS;
+    const int row = idx >> 5, seg = (idx & 31) * 2;
+    kb_cp_async16(&dst[row][seg], src + (size_t)row * ld + seg);
+  }
 }
 
-// 64x64 SPD tile in Cs (lower part used) -> Cs = L (lower), Ds = L^-1 (lower, zeros above).
-// Right-looking with 16-wide panels.  The 16x16 diagonal blocks are factored AND inverted by
-// warp 0 entirely in registers (lane r owns row r; columns travel by shuffle) - the only serial
-// chain left is 64 x (rsqrt -> scale -> shuffle).  Panels, trailing updates and the off-diagonal
-// blocks of the inverse are 8x8x4 DMMA products on padded shared tiles (conflict free).
-__device__ __forceinline__ void kb_diag_factor_inverse(double (*Cs)[KB_LDC], double (*Ds)[KB_LDC],
-                                                       double* Ts_base, int* info, int pivot_base) {
+// out = C * Dinv^T for a 64-row tile, Dinv lower triangular: column block cb only needs
+// k < 8 (cb + 1).  Warp (wr, wc) owns rows wr*16.. and the interleaved column blocks
+// cb = 2 ni + wc so both column halves carry the same work.
+template <int MI>
+__device__ __forceinline__ void kb_tri_multiply(const double (*Cs)[KB_LDC], const double (*Ds)[KB_LDC],
+                                                double (&acc)[4][4][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < KB_TILE / 4; ++ks) {
+    double af[MI];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) af[mi] = Cs[wr * (8 * MI) + mi * 8 + gq][ks * 4 + tq];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      if (ks < 2 * (2 * ni + wc + 1)) {
+        const double bf = Ds[(2 * ni + wc) * 8 + gq][ks * 4 + tq];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
+      }
+    }
+  }
+}
+
+struct KbCholArgs {
+  KbAugGeom g;
+  double* aug;
+  double* dinv;
+  int* prog;          // [B][NT]  number of final leading tile columns of each tile row
+  int* pre;           // [B][nb]  1 once the PRE task of tile row r has written C1, C2
+  int* pre_a;         // [B][nb]  1 once the early part (tile columns < r-2) of that PRE task is in
+  int* ctl;           // [0] bulk queue head, [1] chain-SM tickets, [2] finished chains,
+                      // [8 + smid] CTA arrivals per SM, [8 + 512 + smid] chain-SM id + 1 or -1
+  const int4* tasks;
+  int ntasks;
+  int B;
+  int chain_sms;      // SMs reserved for chain workers
+  int chain_wps;      // chain workers per reserved SM (1 or 2)
+  int* info;
+  unsigned long long* trace;
+};
+
+// ---------------------------------------------------------------------------
+// Chain worker: critical path of its home candidates, round robin, never blocks on a step
+// that is not ready.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& sm, int b, int k,
+                                              unsigned long long* stamps) {
+  double* raw = &sm.ring[0][0];
+  double (*C2)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw);
+  double (*C1)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw + KB_TILE * KB_LDC);
+  double (*Dk)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw + 2 * KB_TILE * KB_LDC);
+  double* xch = raw + 3 * KB_TILE * KB_LDC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gq = lane >> 2, tq = lane & 3;
-  const unsigned FULL = 0xffffffffu;
-  for (int e = tid; e < KB_TILE * KB_TILE; e += KB_THREADS) Ds[e >> 6][e & 63] = 0.0;
+  const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
+  const int ld = P.g.ld;
+  double* A = P.aug + (size_t)b * P.g.stride;
+  int* fl = P.prog + (size_t)b * P.g.NT;
+  double* Tkk = A + (size_t)k * KB_TILE * ld + (size_t)k * KB_TILE;
+
+  kb_load_tile_async(C2, Tkk, ld);
+  if (k > 0) {
+    kb_load_tile_async(C1, Tkk - KB_TILE, ld);
+    kb_load_tile_async(Dk, P.dinv + ((size_t)b * P.g.nb + (k - 1)) * (KB_TILE * KB_TILE), KB_TILE);
+  }
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
   __syncthreads();
-  for (int jb = 0; jb < 4; ++jb) {
-    const int c0 = jb * 16;
-    {
-      // 16x16 diagonal block: factor AND invert with one element of each per thread
-      // (thread (r,c) keeps A[r][c] and W[r][c] in registers).  Per column j the pivot column
-      // and the finished inverse row travel through a double-buffered 32-double shared
-      // exchange: ONE block barrier per column, and every thread redoes the 4-op rsqrt so the
-      // serial chain is  barrier -> rsqrt -> scale -> fma.  (A single-warp register/shuffle
-      // version was issue-bound at ~4 clk per instruction.)
-      const int r = tid >> 4, c = tid & 15;
-      double a = Cs[c0 + r][c0 + c];
-      double w = (r == c) ? 1.0 : 0.0;
-      double* xch = Ts_base;                       // [2][32]: column of A | row of W
-#pragma unroll 1
-      for (int j = 0; j < 16; ++j) {
-        double* buf = xch + (j & 1) * 32;
-        if (c == j) buf[r] = a;
-        if (r == j) buf[16 + c] = w;
-        __syncthreads();
-        double piv = buf[j];
-        if (!(piv > 0.0)) {          // not positive definite (or NaN): flag, keep the batch alive
-          if (tid == 0) atomicCAS(info, 0, pivot_base + c0 + j + 1);
-          piv = 1.0;
-        }
-        const double inv = kb_rsqrt(piv);
-        const double lr = (r == j) ? piv * inv : buf[r] * inv;     // L[r][j]
-        const double lc = buf[c] * inv;                            // L[c][j]
-        const double xj = buf[16 + c] * inv;                       // X[j][c]
-        if (c == j) a = lr;
-        else if (c > j) a = fma(-lr, lc, a);
-        if (r == j) w = xj;
-        else if (r > j) w = fma(-lr, xj, w);
+  if (stamps && tid == 0) stamps[1] = kb_globaltimer();
+  if (k > 0) {
+    // L[k,k-1] = C1 Dinv_{k-1}^T  -> shared (in place) and global, published at once
+    double acc[4][4][2];
+    kb_tri_multiply<2>(C1, Dk, acc);
+    __syncthreads();
+    double* Tsub = Tkk - KB_TILE;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wr * 16 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+        const double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        *reinterpret_cast<double2*>(&C1[r][c]) = v;
+        *reinterpret_cast<double2*>(&Tsub[(size_t)r * ld + c]) = v;
       }
-      if (c <= r) Cs[c0 + r][c0 + c] = a;
-      Ds[c0 + r][c0 + c] = (c <= r) ? w : 0.0;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      kb_flag_release(&fl[k], k);
+      if (stamps) stamps[2] = kb_globaltimer();
     }
-    __syncthreads();
-    if (jb == 3) break;
-    // panel: rows below the block, P = A * inv(L_D)^T ; one warp per 8 rows, both 8-column halves
-    const int nrb = (KB_TILE - 16 - c0) / 8;
-    if (warp < nrb) {
-      const int r0 = c0 + 16 + 8 * warp;
-      double af[4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) af[ks] = Cs[r0 + gq][c0 + ks * 4 + tq];
-      double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-      for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) kb_dmma(p[ni][0], p[ni][1], af[ks], Ds[c0 + ni * 8 + gq][c0 + ks * 4 + tq]);
-      __syncwarp();
-#pragma unroll
-      for (int ni = 0; ni < 2; ++ni)
-        *reinterpret_cast<double2*>(&Cs[r0 + gq][c0 + ni * 8 + 2 * tq]) = make_double2(p[ni][0], p[ni][1]);
-    }
-    __syncthreads();
-    // trailing update of the lower 8x8 tiles: C -= P P^T
-    const int mt = nrb, ntile = mt * (mt + 1) / 2;
-    for (int t = warp; t < ntile; t += 8) {
-      int ri = 0;
-      while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
-      const int ci = t - ri * (ri + 1) / 2;
-      const int r0 = c0 + 16 + 8 * ri, cc0 = c0 + 16 + 8 * ci;
-      double2 cv = *reinterpret_cast<double2*>(&Cs[r0 + gq][cc0 + 2 * tq]);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        kb_dmma(cv.x, cv.y, -Cs[r0 + gq][c0 + ks * 4 + tq], Cs[cc0 + gq][c0 + ks * 4 + tq]);
-      *reinterpret_cast<double2*>(&Cs[r0 + gq][cc0 + 2 * tq]) = cv;
-    }
-    __syncthreads();
-  }
-  // off-diagonal 16x16 blocks of the inverse, by block distance:
-  //   X_ij = -inv(L_ii) * sum_{k=j}^{i-1} L_ik X_kj
-  double* Ts = Ts_base + warp * 16 * KB_LDT;
-  for (int delta = 1; delta <= 3; ++delta) {
-    const int nblk = 4 - delta;
-    if (warp < 2 * nblk) {
-      const int j = warp >> 1, h = warp & 1, i = j + delta;
-      double t0[2] = {0.0, 0.0}, t1[2] = {0.0, 0.0};
-      for (int kb = j; kb < i; ++kb)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const double bv = Ds[kb * 16 + ks * 4 + tq][j * 16 + h * 8 + gq];
-          kb_dmma(t0[0], t0[1], Cs[i * 16 + gq][kb * 16 + ks * 4 + tq], bv);
-          kb_dmma(t1[0], t1[1], Cs[i * 16 + 8 + gq][kb * 16 + ks * 4 + tq], bv);
-        }
-      *reinterpret_cast<double2*>(&Ts[gq * KB_LDT + 2 * tq]) = make_double2(t0[0], t0[1]);
-      *reinterpret_cast<double2*>(&Ts[(8 + gq) * KB_LDT + 2 * tq]) = make_double2(t1[0], t1[1]);
-      __syncwarp();
-      double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const double bv = Ts[(ks * 4 + tq) * KB_LDT + gq];
-        kb_dmma(x0[0], x0[1], Ds[i * 16 + gq][i * 16 + ks * 4 + tq], bv);
-        kb_dmma(x1[0], x1[1], Ds[i * 16 + 8 + gq][i * 16 + ks * 4 + tq], bv);
-      }
-      *reinterpret_cast<double2*>(&Ds[i * 16 + gq][j * 16 + h * 8 + 2 * tq]) = make_double2(-x0[0], -x0[1]);
-      *reinterpret_cast<double2*>(&Ds[i * 16 + 8 + gq][j * 16 + h * 8 + 2 * tq]) = make_double2(-x1[0], -x1[1]);
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(KB_THREADS, 2)
-kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv, int* __restrict__ flags,
-               int epoch, const int4* __restrict__ tasks, int ntasks, int* __restrict__ counter,
-               int* __restrict__ info, unsigned long long* __restrict__ trace) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  KbCholSmem& sm = *reinterpret_cast<KbCholSmem*>(smem_raw);
-  double (*Cs)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.a[0][0][0]);
-  double (*Ds)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.b[0][0][0]);
-  double* Ts_base = &sm.b[0][0][0] + KB_TILE * KB_LDC;     // 8 warps x 16 x KB_LDT scratch after Ds
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gq = lane >> 2, tq = lane & 3;
-  const int wr = warp >> 1, wc = warp & 1;
-  const int NT = g.NT, ld = g.ld;
-
-  while (true) {
-    __syncthreads();
-    if (tid == 0) sm.task = atomicAdd(counter, 1);
-    __syncthreads();
-    const int tk = sm.task;
-    if (tk >= ntasks) break;
-    const int4 T = tasks[tk];
-    const int b = T.x, ti = T.y, tkc = T.z, type = T.w;
-    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
-    if (trace && tid == 0) tr0 = kb_globaltimer();
-    double* A = aug + (size_t)b * g.stride;
-    int* fl = flags + (size_t)b * NT;
-    const int kt = (tkc < g.nb) ? tkc : g.nb;
-
-    // ---- input tiles: row-progress counters, polled only when the K loop catches up ----
-    // prog[r] = (epoch << 10) + number of leading tile columns of row r that are final.
-    const int ebase = epoch << 10;
-    int ready_cols = 0;
-    if (kt > 0) {
-      if (tid == 0) {
-        int ra, rb;
-        while (true) {
-          ra = kb_flag_acquire(&fl[ti]) - ebase;
-          rb = kb_flag_acquire(&fl[tkc]) - ebase;
-          if (ra >= 1 && rb >= 1) break;
-          __nanosleep(64);
-        }
-        sm.ready = ra < rb ? ra : rb;
-      }
-      __syncthreads();
-      ready_cols = sm.ready;
-    }
-
-    if (trace && tid == 0) tr1 = kb_globaltimer();
-    // ---- C_acc = sum_p L[i,p] L[k,p]^T on the FP64 tensor pipe ------------
-    double acc[2][4][2];
+    // C2 -= L L^T on the lower 8x8 blocks (each thread owns its accumulator positions)
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    unsigned need = 0;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        if (wc * 4 + ni <= wr * 2 + mi) need |= 1u << (mi * 4 + ni);
+    if (need) {
+#pragma unroll 4
+      for (int ks = 0; ks < KB_TILE / 4; ++ks) {
+        double af[2], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) af[mi] = C1[wr * 16 + mi * 8 + gq][ks * 4 + tq];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = C1[wc * 32 + ni * 8 + gq][ks * 4 + tq];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni)
+            if (need & (1u << (mi * 4 + ni))) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          if (need & (1u << (mi * 4 + ni))) {
+            const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
+            double2 v = *reinterpret_cast<double2*>(&C2[r][c]);
+            v.x -= acc[mi][ni][0];
+            v.y -= acc[mi][ni][1];
+            *reinterpret_cast<double2*>(&C2[r][c]) = v;
+          }
+    }
+    __syncthreads();
+  }
+  if (stamps && tid == 0) stamps[3] = kb_globaltimer();
+  kb_diag_factor_inverse(C2, Dk, xch, &P.info[b], k * KB_TILE);
+  if (stamps && tid == 0) stamps[6] = kb_globaltimer();
+  double* Dg = P.dinv + ((size_t)b * P.g.nb + k) * (KB_TILE * KB_TILE);
+  for (int e = tid; e < KB_TILE * KB_TILE / 2; e += KB_THREADS) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    double2 l = *reinterpret_cast<double2*>(&C2[r][c]);
+    if (c > r) l.x = 0.0;
+    if (c + 1 > r) l.y = 0.0;
+    *reinterpret_cast<double2*>(&Tkk[(size_t)r * ld + c]) = l;
+    *reinterpret_cast<double2*>(&Dg[r * KB_TILE + c]) = *reinterpret_cast<double2*>(&Dk[r][c]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    kb_flag_release(&fl[k], k + 1);
+  }
+}
 
-    const bool same = (ti == tkc);
-    const double* Arow = A + (size_t)ti * KB_TILE * ld;
-    const double* Brow = A + (size_t)tkc * KB_TILE * ld;
-    const int nchunks = kt * (KB_TILE / KB_KC);
+__device__ __forceinline__ void kb_chain_worker(const KbCholArgs& P, KbCholSmem& sm, int wid, int nworkers) {
+  const int tid = threadIdx.x;
+  const int nb = P.g.nb;
+  // home candidates b = wid + j * nworkers; next step per candidate in shared memory (<= 6 kept)
+  int nhome = 0;
+  for (int b = wid; b < P.B; b += nworkers) ++nhome;
+  int done = 0;
+  int knext[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) knext[j] = 0;
+  while (done < nhome) {
+    bool progressed = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = wid + j * nworkers;
+      if (b >= P.B || knext[j] >= nb) continue;
+      const int k = knext[j];
+      __syncthreads();
+      if (tid == 0) sm.ready = (k <= 1) ? 1 : kb_flag_acquire(&P.pre[(size_t)b * nb + k]);
+      __syncthreads();
+      if (sm.ready == 0) continue;
+      unsigned long long tr0 = 0;
+      if (P.trace && tid == 0) tr0 = kb_globaltimer();
+      unsigned long long* trec = P.trace ? P.trace + ((size_t)P.ntasks + (size_t)b * nb + k) * 8 : nullptr;
+      kb_chain_step(P, sm, b, k, trec);
+      if (P.trace && tid == 0) {
+        // chain record: start | tiles loaded | sub-diagonal tile published | factor start | end | meta | factor end
+        trec[0] = tr0; trec[4] = kb_globaltimer();
+        trec[5] = ((unsigned long long)b << 40) | ((unsigned long long)k << 24) | ((unsigned long long)k << 8) | 0;
+        trec[7] = blockIdx.x;
+      }
+      knext[j] = k + 1;
+      if (k + 1 == nb) ++done;
+      progressed = true;
+    }
+    if (!progressed) __nanosleep(200);
+  }
+  // more than 8 home candidates per worker never happens: the host sizes chain_sms for it
+  if (tid == 0) atomicAdd(&P.ctl[2], nhome);
+}
 
-    auto load_chunk = [&](int c, int stage) {
-      const int col0 = c * KB_KC;
+// ---------------------------------------------------------------------------
+// Bulk K loop.  MODE 0: 64-row tile task (A 64 rows, B 64 rows, 16 x 32 per warp)
+//               MODE 1: PRE task: A = tile row r, B = tile row r-1 (acc[0..1]); second
+//                       accumulator acc[2..3] with B = A (lower 8x8 blocks only)
+//               MODE 2: thin task: A = 16 rows, B 64 rows, warp w owns column block w
+//               MODE 4: 128-row task (two tile rows i, i+1 against one B row): 32 x 32 per warp,
+//                       16 DMMA per 8 fragment loads, two pipeline stages
+// ---------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restrict__ Arow,
+                                         const double* __restrict__ Brow, bool same, int ld, int k0, int k1,
+                                         const int* fa, const int* fa2, const int* fb, int ready_cols,
+                                         unsigned need2, double (&acc)[4][4][2]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
+  constexpr int CPT = KB_TILE / KB_KC;      // chunks per tile column
+  constexpr int NS = (MODE == 4) ? 2 : 3;   // pipeline stages
+  constexpr int AROWS = (MODE == 4) ? 128 : 64;
+  constexpr int SROWS = AROWS + 64;         // ring rows per stage
+  const int c_begin = k0 * CPT, c_end = k1 * CPT;
+
+  auto load_chunk = [&](int c, int stage) {
+    const int col0 = c * KB_KC;
+    double (*as)[KB_LDK] = &sm.ring[stage * SROWS];
+    double (*bs)[KB_LDK] = &sm.ring[stage * SROWS + AROWS];
+    if (MODE == 2) {
+      const int row = tid >> 4, seg = (tid & 15) * 2;
+      kb_cp_async16(&as[row][seg], Arow + (size_t)row * ld + col0 + seg);
+    } else {
+#pragma unroll
+      for (int j = 0; j < (AROWS * KB_KC / 2) / KB_THREADS; ++j) {
+        const int idx = tid + j * KB_THREADS;
+        const int row = idx >> 4, seg = (idx & 15) * 2;
+        kb_cp_async16(&as[row][seg], Arow + (size_t)row * ld + col0 + seg);
+      }
+    }
+    if (!same) {
 #pragma unroll
       for (int j = 0; j < (KB_TILE * KB_KC / 2) / KB_THREADS; ++j) {
         const int idx = tid + j * KB_THREADS;
         const int row = idx >> 4, seg = (idx & 15) * 2;
-        kb_cp_async16(&sm.a[stage][row][seg], Arow + (size_t)row * ld + col0 + seg);
-        if (!same) kb_cp_async16(&sm.b[stage][row][seg], Brow + (size_t)row * ld + col0 + seg);
+        kb_cp_async16(&bs[row][seg], Brow + (size_t)row * ld + col0 + seg);
       }
-    };
+    }
+  };
 
 #pragma unroll
-    for (int s = 0; s < KB_STAGES - 1; ++s) {
-      if (s < nchunks) load_chunk(s, s);
+  for (int s = 0; s < NS - 1; ++s) {
+    if (c_begin + s < c_end) load_chunk(c_begin + s, s);
+    kb_cp_async_commit();
+  }
+  for (int c = c_begin; c < c_end; ++c) {
+    const int cn = c + NS - 1;
+    const int pn = cn / CPT;                  // tile column the next prefetch reads
+    const bool poll = (cn < c_end) && (pn >= ready_cols);
+    if (poll && tid == 0) {
+      int ra, rb, rc;
+      while (true) {
+        ra = kb_flag_acquire(fa);
+        rb = kb_flag_acquire(fb);
+        rc = kb_flag_acquire(fa2);
+        if (ra > pn && rb > pn && rc > pn) break;
+        __nanosleep(64);
+      }
+      ra = ra < rb ? ra : rb;
+      sm.ready = ra < rc ? ra : rc;
+    }
+    kb_cp_async_wait<NS - 2>();
+    __syncthreads();
+    if (poll) ready_cols = sm.ready;
+    {
+      if (cn < c_end) load_chunk(cn, (cn - c_begin) % NS);
       kb_cp_async_commit();
     }
-    for (int c = 0; c < nchunks; ++c) {
-      const int cn = c + KB_STAGES - 1;
-      const int pn = cn / (KB_TILE / KB_KC);          // tile column the next prefetch reads
-      const bool poll = (cn < nchunks) && (pn >= ready_cols);
-      if (poll && tid == 0) {
-        int ra, rb;
-        while (true) {
-          ra = kb_flag_acquire(&fl[ti]) - ebase;
-          rb = kb_flag_acquire(&fl[tkc]) - ebase;
-          if (ra > pn && rb > pn) break;
-          __nanosleep(64);
-        }
-        sm.ready = ra < rb ? ra : rb;
+    const int stg = (c - c_begin) % NS;
+    const double (*as)[KB_LDK] = &sm.ring[stg * SROWS];
+    const double (*bs)[KB_LDK] = same ? as : &sm.ring[stg * SROWS + AROWS];
+    if (MODE == 2) {
+#pragma unroll
+      for (int ks = 0; ks < KB_KC / 4; ++ks) {
+        const double a0 = as[gq][ks * 4 + tq], a1 = as[8 + gq][ks * 4 + tq];
+        const double bf = bs[warp * 8 + gq][ks * 4 + tq];
+        kb_dmma(acc[0][0][0], acc[0][0][1], a0, bf);
+        kb_dmma(acc[1][0][0], acc[1][0][1], a1, bf);
       }
-      kb_cp_async_wait<KB_STAGES - 2>();
-      __syncthreads();
-      if (poll) ready_cols = sm.ready;
-      {
-        if (cn < nchunks) load_chunk(cn, cn % KB_STAGES);
-        kb_cp_async_commit();
+    } else if (MODE == 4) {
+#pragma unroll
+      for (int ks = 0; ks < KB_KC / 4; ++ks) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) af[mi] = as[wr * 32 + mi * 8 + gq][ks * 4 + tq];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = bs[wc * 32 + ni * 8 + gq][ks * 4 + tq];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
       }
-      const int stg = c % KB_STAGES;
-      const double (*as)[KB_LDK] = sm.a[stg];
-      const double (*bs)[KB_LDK] = same ? sm.a[stg] : sm.b[stg];
+    } else {
 #pragma unroll
       for (int ks = 0; ks < KB_KC / 4; ++ks) {
         double af[2], bf[4];
@@ -295,103 +374,261 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-      }
-    }
-    kb_cp_async_wait<0>();
-    __syncthreads();
-
-    if (trace && tid == 0) tr2 = kb_globaltimer();
-    // ---- C = A[i,k] - C_acc ------------------------------------------------
-    double* Atile = A + (size_t)ti * KB_TILE * ld + (size_t)tkc * KB_TILE;
+        if (MODE == 1 && need2) {
+          double b2[4];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(&Atile[(size_t)r * ld + c]));
-        acc[mi][ni][0] = v.x - acc[mi][ni][0];
-        acc[mi][ni][1] = v.y - acc[mi][ni][1];
-      }
-
-    if (type == KB_TASK_SCHUR) {
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
-          *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) =
-              make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        }
-    } else {
-      // C -> shared (A-operand layout for the multiply / in-place POTRF)
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
-          *reinterpret_cast<double2*>(&Cs[r][c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        }
-      if (type == KB_TASK_OFF) {
-        // L[i,k] = C * inv(L[k,k])^T : wait for the diagonal task, then one 64^3 DMMA multiply
-        if (tid == 0)
-          while (kb_flag_acquire(&fl[tkc]) - ebase < tkc + 1) __nanosleep(64);
-        __syncthreads();
-        if (trace && tid == 0) tr3 = kb_globaltimer();
-        const double* Dg = dinv + ((size_t)b * g.nb + tkc) * (KB_TILE * KB_TILE);
-#pragma unroll
-        for (int j = 0; j < (KB_TILE * KB_TILE / 2) / KB_THREADS; ++j) {
-          const int idx = tid + j * KB_THREADS;
-          const int row = idx >> 5, seg = (idx & 31) * 2;
-          kb_cp_async16(&Ds[row][seg], Dg + row * KB_TILE + seg);
-        }
-        kb_cp_async_commit();
-        kb_cp_async_wait<0>();
-        __syncthreads();
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-#pragma unroll 4
-        for (int ks = 0; ks < KB_TILE / 4; ++ks) {
-          double af[2], bf[4];
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi) af[mi] = Cs[wr * 16 + mi * 8 + gq][ks * 4 + tq];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) bf[ni] = Ds[wc * 32 + ni * 8 + gq][ks * 4 + tq];
+          for (int ni = 0; ni < 4; ++ni) b2[ni] = as[wc * 32 + ni * 8 + gq][ks * 4 + tq];
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            for (int ni = 0; ni < 4; ++ni)
+              if (need2 & (1u << (mi * 4 + ni))) kb_dmma(acc[2 + mi][ni][0], acc[2 + mi][ni][1], af[mi], b2[ni]);
         }
+      }
+    }
+  }
+  kb_cp_async_wait<0>();
+  __syncthreads();
+}
+
+__device__ __forceinline__ int kb_wait_rows(KbCholSmem& sm, const int* fa, const int* fa2, const int* fb, int need) {
+  if (threadIdx.x == 0) {
+    int ra, rb, rc;
+    while (true) {
+      ra = kb_flag_acquire(fa);
+      rb = kb_flag_acquire(fb);
+      rc = kb_flag_acquire(fa2);
+      if (ra >= need && rb >= need && rc >= need) break;
+      __nanosleep(64);
+    }
+    ra = ra < rb ? ra : rb;
+    sm.ready = ra < rc ? ra : rc;
+  }
+  __syncthreads();
+  return sm.ready;
+}
+
+// wait for the chain's Dinv_k, stage it behind the C tile(s)
+__device__ __forceinline__ void kb_fetch_dinv(const KbCholArgs& P, double (*Ds)[KB_LDC], const int* flk, int b, int tkc) {
+  if (threadIdx.x == 0)
+    while (kb_flag_acquire(flk) < tkc + 1) __nanosleep(64);
+  __syncthreads();
+  kb_load_tile_async(Ds, P.dinv + ((size_t)b * P.g.nb + tkc) * (KB_TILE * KB_TILE), KB_TILE);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+}
+
+__device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& sm) {
+  double (*Cs)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.ring[0][0]);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
+  const int NT = P.g.NT, ld = P.g.ld, nb = P.g.nb;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) sm.task = atomicAdd(&P.ctl[0], 1);
+    __syncthreads();
+    const int tk = sm.task;
+    if (tk >= P.ntasks) break;
+    const int4 T = P.tasks[tk];
+    const int b = T.x, ti = T.y, tkc = T.z, type = T.w & 0xff, kstart = T.w >> 8;
+    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
+    if (P.trace && tid == 0) tr0 = kb_globaltimer();
+    double* A = P.aug + (size_t)b * P.g.stride;
+    int* fl = P.prog + (size_t)b * NT;
+    const bool is_pre = (type == KB_TASK_PRE || type == KB_TASK_PRE_A);
+    const bool is_schur = (type == KB_TASK_SCHUR || type == KB_TASK_SCHUR_THIN);
+    const bool thin = (type == KB_TASK_THIN || type == KB_TASK_SCHUR_THIN);
+    const bool two = (type == KB_TASK_OFF2);
+    const int brow = is_pre ? ti - 1 : tkc;
+    const int kend = (type == KB_TASK_PRE_A) ? ti - 2 : (is_pre ? ti - 1 : (tkc < nb ? tkc : nb));
+    const double* Arow = A + (size_t)ti * KB_TILE * ld;
+    const double* Brow = A + (size_t)brow * KB_TILE * ld;
+    double* Atile = A + (size_t)ti * KB_TILE * ld + (size_t)(is_pre ? ti - 1 : tkc) * KB_TILE;
+    const int* fa = &fl[ti];
+    const int* fa2 = two ? &fl[ti + 1] : fa;
+    const int* fb = &fl[brow];
+    // the tile(s) this task updates are read once, after the K loop: pull them towards L2 now
+    {
+      const int nrows = thin ? 16 : (two ? 128 : 64);
+      const int lines = (is_pre ? 8 : 4);          // 128-byte lines per row (PRE touches two tiles)
+      for (int e = tid; e < nrows * lines; e += KB_THREADS) {
+        const double* p = Atile + (size_t)(e / lines) * ld + (e % lines) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    }
+    int ready_cols = 0;
+    if (type == KB_TASK_PRE && kstart > 0) {       // the early part of this PRE task must be in
+      if (tid == 0)
+        while (kb_flag_acquire(&P.pre_a[(size_t)b * nb + ti]) == 0) __nanosleep(64);
+      __syncthreads();
+    }
+    if (kend > kstart) ready_cols = kb_wait_rows(sm, fa, fa2, fb, kstart + 1);
+    if (P.trace && tid == 0) tr1 = kb_globaltimer();
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    unsigned need2 = 0;
+    if (is_pre) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          if (wc * 4 + ni <= wr * 2 + mi) need2 |= 1u << (mi * 4 + ni);
+      kb_kloop<1>(sm, Arow, Brow, false, ld, kstart, kend, fa, fa2, fb, ready_cols, need2, acc);
+    } else if (thin) {
+      kb_kloop<2>(sm, Arow, Brow, false, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
+    } else if (two) {
+      kb_kloop<4>(sm, Arow, Brow, false, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
+    } else {
+      kb_kloop<0>(sm, Arow, Brow, ti == tkc, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
+    }
+    if (P.trace && tid == 0) tr2 = kb_globaltimer();
+
+    if (is_pre) {
+      // C1 = A[r,r-1] - acc (full tile), C2 = A[r,r] - acc2 (lower 8x8 blocks), both in place
+      double* T1 = Atile;
+      double* T2 = T1 + KB_TILE;
+      // all loads first (the compiler cannot hoist them over possibly aliasing stores), then all stores
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(&T1[(size_t)r * ld + c]));
+          acc[mi][ni][0] = v.x - acc[mi][ni][0];
+          acc[mi][ni][1] = v.y - acc[mi][ni][1];
+          if (need2 & (1u << (mi * 4 + ni))) {
+            const double2 u = __ldcg(reinterpret_cast<const double2*>(&T2[(size_t)r * ld + c]));
+            acc[2 + mi][ni][0] = u.x - acc[2 + mi][ni][0];
+            acc[2 + mi][ni][1] = u.y - acc[2 + mi][ni][1];
+          }
+        }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
+          *reinterpret_cast<double2*>(&T1[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          if (need2 & (1u << (mi * 4 + ni)))
+            *reinterpret_cast<double2*>(&T2[(size_t)r * ld + c]) = make_double2(acc[2 + mi][ni][0], acc[2 + mi][ni][1]);
+        }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        kb_flag_release(type == KB_TASK_PRE_A ? &P.pre_a[(size_t)b * nb + ti] : &P.pre[(size_t)b * nb + ti], 1);
+      }
+    } else if (thin) {
+      // 16 x 64 strip; warp w owns column block w
+      double c0v[2][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]));
+        c0v[mi][0] = v.x - acc[mi][0][0];
+        c0v[mi][1] = v.y - acc[mi][0][1];
+      }
+      if (is_schur) {
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+          *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
+              make_double2(c0v[mi][0], c0v[mi][1]);
+      } else {
+        double (*Ds)[KB_LDC] = Cs + KB_TILE;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+          *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]) = make_double2(c0v[mi][0], c0v[mi][1]);
+        kb_fetch_dinv(P, Ds, &fl[tkc], b, tkc);
+        if (P.trace && tid == 0) tr3 = kb_globaltimer();
+        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const int kmax = 2 * (warp + 1);
+        for (int ks = 0; ks < kmax; ++ks) {
+          const double bf = Ds[warp * 8 + gq][ks * 4 + tq];
+          kb_dmma(o[0][0], o[0][1], Cs[gq][ks * 4 + tq], bf);
+          kb_dmma(o[1][0], o[1][1], Cs[8 + gq][ks * 4 + tq], bf);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+          *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
+              make_double2(o[mi][0], o[mi][1]);
+      }
+    } else if (two) {
+      // 128 x 64: C = A[i..i+1, k] - acc -> shared, one triangular multiply for both tile rows
+      double (*Ds)[KB_LDC] = Cs + 2 * KB_TILE;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int r = wr * 32 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(&Atile[(size_t)r * ld + c]));
+          *reinterpret_cast<double2*>(&Cs[r][c]) = make_double2(v.x - acc[mi][ni][0], v.y - acc[mi][ni][1]);
+        }
+      kb_fetch_dinv(P, Ds, &fl[tkc], b, tkc);
+      if (P.trace && tid == 0) tr3 = kb_globaltimer();
+      kb_tri_multiply<4>(Cs, Ds, acc);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int r = wr * 32 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+          *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    } else {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(&Atile[(size_t)r * ld + c]));
+          acc[mi][ni][0] = v.x - acc[mi][ni][0];
+          acc[mi][ni][1] = v.y - acc[mi][ni][1];
+        }
+      if (is_schur) {
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) {
             const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
-            *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) =
-                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
           }
       } else {
-        // ---- diagonal tile: blocked (16) POTRF + inverse, DMMA for every block update ----
-        kb_diag_factor_inverse(Cs, Ds, Ts_base, &info[b], tkc * KB_TILE);
-        double* Dg = dinv + ((size_t)b * g.nb + tkc) * (KB_TILE * KB_TILE);
-        for (int e = tid; e < KB_TILE * KB_TILE; e += KB_THREADS) {
-          const int r = e >> 6, c = e & 63;
-          Atile[(size_t)r * ld + c] = (c <= r) ? Cs[r][c] : 0.0;
-          Dg[e] = Ds[r][c];
-        }
+        // L[i,k] = C * inv(L[k,k])^T : wait for the chain, then one triangular 64^3 DMMA multiply
+        double (*Ds)[KB_LDC] = Cs + KB_TILE;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
+            *reinterpret_cast<double2*>(&Cs[r][c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          }
+        kb_fetch_dinv(P, Ds, &fl[tkc], b, tkc);
+        if (P.trace && tid == 0) tr3 = kb_globaltimer();
+        kb_tri_multiply<2>(Cs, Ds, acc);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int r = wr * 16 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+            *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          }
       }
     }
-    // ---- publish the tile ---------------------------------------------------
-    __syncthreads();
-    if (tid == 0 && type != KB_TASK_SCHUR) {
-      __threadfence();
-      kb_flag_release(&fl[ti], ebase + tkc + 1);
+    // ---- publish the tile(s) ------------------------------------------------
+    if (!is_pre && !is_schur) {
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        kb_flag_release(&fl[ti], tkc + 1);
+        if (two) kb_flag_release(&fl[ti + 1], tkc + 1);
+      }
     }
-    if (trace && tid == 0) {
+    if (P.trace && tid == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long* t = trace + (size_t)tk * 8;
+      unsigned long long* t = P.trace + (size_t)tk * 8;
       t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = tr3; t[4] = kb_globaltimer();
       t[5] = ((unsigned long long)b << 40) | ((unsigned long long)ti << 24) | ((unsigned long long)tkc << 8) | type;
       t[6] = smid; t[7] = blockIdx.x;
@@ -399,36 +636,144 @@ kb_chol_kernel(KbAugGeom g, double* __restrict__ aug, double* __restrict__ dinv,
   }
 }
 
+__global__ void __launch_bounds__(KB_THREADS, 2)
+kb_chol_kernel(KbCholArgs P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  KbCholSmem& sm = *reinterpret_cast<KbCholSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  // ---- role: the first chain_sms SMs to start a CTA host the chain workers ----
+  if (tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    int* arrivals = P.ctl + 8;
+    int* smrole = P.ctl + 8 + 512;
+    const int slot = atomicAdd(&arrivals[smid], 1);
+    int role;
+    if (slot == 0) {
+      const int t = atomicAdd(&P.ctl[1], 1);
+      role = (t < P.chain_sms) ? t + 1 : -1;
+      kb_flag_release(&smrole[smid], role);
+    } else {
+      while ((role = kb_flag_acquire(&smrole[smid])) == 0) __nanosleep(32);
+    }
+    sm.misc[0] = role;
+    sm.misc[1] = slot;
+  }
+  __syncthreads();
+  const int role = sm.misc[0], slot = sm.misc[1];
+  if (role > 0) {
+    if (slot < P.chain_wps) {
+      kb_chain_worker(P, sm, (role - 1) * P.chain_wps + slot, P.chain_sms * P.chain_wps);
+    } else {
+      // spare CTA on a chain SM: stay off the FP64 pipe until every chain has finished
+      if (tid == 0)
+        while (kb_flag_acquire(&P.ctl[2]) < P.B) __nanosleep(500);
+      __syncthreads();
+    }
+  }
+  kb_bulk_worker(P, sm);
+}
+
 cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* aug, double* dinv,
-                           int* flags, int epoch, const int4* tasks, int ntasks, int* counter,
-                           int* info, int num_sms) {
-  (void)B;
+                           int* sync_words, const int4* tasks, int ntasks, int* info, int num_sms) {
   const size_t smem = sizeof(KbCholSmem);
-  cudaError_t e = cudaFuncSetAttribute(kb_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kb_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(counter, 0, sizeof(int), st);
+  const size_t nwords = kb_chol_sync_words(g, B);
+  e = cudaMemsetAsync(sync_words, 0, sizeof(int) * nwords, st);
   if (e != cudaSuccess) return e;
+  KbCholArgs P{};
+  P.g = g; P.aug = aug; P.dinv = dinv;
+  P.ctl = sync_words;
+  P.prog = sync_words + KB_CHOL_CTL_WORDS;
+  P.pre = P.prog + (size_t)B * g.NT;
+  P.pre_a = P.pre + (size_t)B * g.nb;
+  P.tasks = tasks; P.ntasks = ntasks; P.B = B; P.info = info;
+  // chain SMs: up to 16; one worker per SM while that covers the population, else two; a
+  // worker serves at most 8 candidates
+  int csm = B < 16 ? B : 16;
+  int wps = (B > csm) ? 2 : 1;
+  while (csm * wps * 8 < B && csm < num_sms / 2) ++csm;
+  static const char* csm_env = getenv("KB_CHOL_CHAIN_SMS");     // debug aids
+  static const char* wps_env = getenv("KB_CHOL_CHAIN_WPS");
+  if (csm_env && atoi(csm_env) > 0) csm = atoi(csm_env);
+  if (wps_env && atoi(wps_env) > 0) wps = atoi(wps_env);
+  if (csm * wps > B) csm = (B + wps - 1) / wps;
+  while (csm * wps * 8 < B) ++csm;
+  P.chain_sms = csm;
+  P.chain_wps = wps;
   int grid = num_sms * 2;
-  if (grid > ntasks) grid = ntasks;
-  if (grid < 1) grid = 1;
+  static const char* grid_env = getenv("KB_CHOL_CTAS_PER_SM");   // debug aid: 1 or 2
+  if (grid_env && atoi(grid_env) == 1) { grid = num_sms; P.chain_wps = 1; }
   // Debug aid: KB_CHOL_TRACE=<file> dumps per-task timestamps (ns) of this launch.
   static const char* trace_path = getenv("KB_CHOL_TRACE");
-  unsigned long long* trace = nullptr;
+  const size_t nrec = (size_t)ntasks + (size_t)B * g.nb;
+  P.trace = nullptr;
   if (trace_path) {
-    e = cudaMalloc(&trace, sizeof(unsigned long long) * 8 * (size_t)ntasks);
+    e = cudaMalloc(&P.trace, sizeof(unsigned long long) * 8 * nrec);
     if (e != cudaSuccess) return e;
-    cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 8 * (size_t)ntasks, st);
+    cudaMemsetAsync(P.trace, 0, sizeof(unsigned long long) * 8 * nrec, st);
   }
-  kb_chol_kernel<<<grid, KB_THREADS, smem, st>>>(g, aug, dinv, flags, epoch, tasks, ntasks, counter, info, trace);
-  e = cudaGetLastError();
-  if (trace_path && e == cudaSuccess) {
-    std::vector<unsigned long long> h((size_t)ntasks * 8);
+  // Cooperative launch: every CTA is resident, so the chain workers exist while bulk CTAs spin.
+  void* params[] = {&P};
+  e = cudaLaunchCooperativeKernel((const void*)kb_chol_kernel, dim3(grid), dim3(KB_THREADS), params, smem, st);
+  if (e != cudaSuccess) return e;
+  if (trace_path) {
+    std::vector<unsigned long long> h(nrec * 8);
     cudaStreamSynchronize(st);
-    cudaMemcpy(h.data(), trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data(), P.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     FILE* f = fopen(trace_path, "wb");
     if (f) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
-    cudaFree(trace);
+    cudaFree(P.trace);
   }
-  return e;
+  return cudaSuccess;
+}
+
+size_t kb_chol_sync_words(const KbAugGeom& g, int B) {
+  return (size_t)KB_CHOL_CTL_WORDS + (size_t)B * g.NT + 2 * (size_t)B * g.nb;
+}
+
+// Bulk task queue: every dependency precedes its user.  Column k holds the tile tasks (i,k),
+// i >= k+2 (the sub-diagonal tile belongs to the chain), with the tile the chain needs next
+// (k+2,k) and the PRE task of row k+2 first.
+void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
+  out.clear();
+  struct T3 { int i, k, type; };
+  auto emit = [&](const std::vector<T3>& seg) {
+    for (int b = 0; b < B; ++b)
+      for (const T3& t : seg) out.push_back(make_int4(b, t.i, t.k, t.type));
+  };
+  const int rhs0 = g.nb, id0 = g.nb + g.sb;
+  const bool thin_rhs = (g.sb == 1 && g.q <= 16);
+  for (int k = 0; k < g.nb; ++k) {
+    if (k + 2 < g.nb) emit({{k + 2, k, KB_TASK_OFF}});
+    std::vector<T3> seg;
+    // remaining tile rows of R and the full right-hand-side rows, two tile rows per task
+    {
+      std::vector<int> rows;
+      for (int i = k + 3; i < g.nb; ++i) rows.push_back(i);
+      if (!thin_rhs)
+        for (int i = rhs0; i < id0; ++i) rows.push_back(i);
+      size_t r = 0;
+      for (; r + 1 < rows.size(); r += 2) {
+        if (rows[r + 1] == rows[r] + 1) seg.push_back({rows[r], k, KB_TASK_OFF2});
+        else { seg.push_back({rows[r], k, KB_TASK_OFF}); seg.push_back({rows[r + 1], k, KB_TASK_OFF}); }
+      }
+      if (r < rows.size()) seg.push_back({rows[r], k, KB_TASK_OFF});
+    }
+    if (thin_rhs) seg.push_back({rhs0, k, KB_TASK_THIN});
+    // identity rows (fit mode): row j of I is zero left of tile column j
+    for (int j = 0; j <= k && j < g.ib; ++j) seg.push_back({id0 + j, k, KB_TASK_OFF | (j << 8)});
+    emit(seg);
+    // early part of the PRE task of tile row k+3 (tile columns 0..k): off the critical path
+    if (k + 3 < g.nb) emit({{k + 3, k, KB_TASK_PRE_A}});
+    // PRE of tile row r = k+2, last tile column (r-2 = k).  Placed at the END of the column: by the
+    // time the pool gets here its inputs (PRE_A of the previous column, the chain's L[k+1,k]) are
+    // in, so it never parks a CTA, and the chain still runs a good part of a column ahead.
+    if (k + 2 < g.nb) emit({{k + 2, k, KB_TASK_PRE | (k << 8)}});
+  }
+  std::vector<T3> seg;
+  for (int kk = rhs0; kk < id0; ++kk)
+    for (int i = kk; i < id0; ++i) seg.push_back({i, kk, thin_rhs ? KB_TASK_SCHUR_THIN : KB_TASK_SCHUR});
+  emit(seg);
 }

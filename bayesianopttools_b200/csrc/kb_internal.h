@@ -11,8 +11,10 @@
 #endif
 #define KB_MAX_D 200  // dimensions the shared-memory X tiles are sized for
 
-// Tile task kinds of the Cholesky task graph (kb_chol.cu).
-enum { KB_TASK_DIAG = 0, KB_TASK_OFF = 1, KB_TASK_SCHUR = 2 };
+// Bulk tile task kinds of the Cholesky task graph (kb_chol.cu); task.w = kind | first K tile column << 8.
+enum { KB_TASK_CHAIN = 0, KB_TASK_OFF = 1, KB_TASK_SCHUR = 2, KB_TASK_PRE = 3, KB_TASK_THIN = 4,
+       KB_TASK_SCHUR_THIN = 5, KB_TASK_OFF2 = 6, KB_TASK_PRE_A = 7 };
+#define KB_CHOL_CTL_WORDS (8 + 1024)
 
 // Geometry of one augmented matrix  [ R ; rhs rows ]  (row-major, lower tiles only).
 //   tile rows 0..nb-1        : R (n padded to nb*64 with identity)
@@ -60,9 +62,15 @@ cudaError_t kb_launch_corr_general(cudaStream_t st, int n, int m, int d, const d
 cudaError_t kb_launch_transpose_pad(cudaStream_t st, const double* X, int n, int d, double* XT, int n_pad);
 
 // --- kb_chol.cu --------------------------------------------------------------
+// sync_words: kb_chol_sync_words(g, B) ints (queue head, role tickets, row progress, PRE flags),
+// zeroed by the launcher on the stream before every launch.
+#ifdef __cplusplus
+#include <vector>
+size_t kb_chol_sync_words(const KbAugGeom& g, int B);
+void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out);
+#endif
 cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* aug, double* dinv,
-                           int* flags, int epoch, const int4* tasks, int ntasks, int* counter,
-                           int* info, int num_sms);
+                           int* sync_words, const int4* tasks, int ntasks, int* info, int num_sms);
 
 // --- kb_gls.cu ---------------------------------------------------------------
 cudaError_t kb_launch_gls(cudaStream_t st, const KbAugGeom& g, int B, const double* aug, int trainvar,

@@ -66,6 +66,9 @@ def predict_case(n, d, m):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nll1000":
+        nll_case(1000, 10, 64)
+        sys.exit(0)
     nll_case(1000, 10, 64)
     nll_case(1000, 10, 8)
     nll_case(2000, 10, 64)
