@@ -73,6 +73,7 @@ struct kb_model {
   KbSweepResult* partials = nullptr;
   KbSweepResult* result_dev = nullptr;
   int pred_grid = 0;
+  int pred_resident = 0;
   // host-API staging
   double* stage_x = nullptr;
   double* stage_out = nullptr;
@@ -85,7 +86,6 @@ struct kb_model {
   long long pop_calls = 0, pred_calls = 0;
 };
 
-extern int kb_predict_max_grid(int kmask, int d, int num_sms);
 
 // ---------------------------------------------------------------------------
 // helpers
@@ -486,11 +486,15 @@ kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const 
 }
 
 static kb_status ensure_predict_scratch(kb_model* m) {
-  if (m->psi_scratch) return KB_OK;
-  m->pred_grid = kb_predict_max_grid(m->kmask, m->d, m->num_sms);
-  if (m->pred_grid < 1) KB_FAIL(KB_ERR_CUDA, "predict kernel does not fit on this device (d=%d)", m->d);
   const int qx = 1 + m->nind;
-  CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * 64));
+  const int resident = kb_predict_can_reside(m->d, m->n_pad, qx, m->idx_dev ? 1 : 0) ? 1 : 0;
+  if (m->ex_scratch && resident == m->pred_resident) return KB_OK;
+  cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
+  m->psi_scratch = m->ex_scratch = nullptr; m->partials = nullptr;
+  m->pred_resident = resident;
+  m->pred_grid = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx);
+  if (m->pred_grid < 1) KB_FAIL(KB_ERR_CUDA, "predict kernel does not fit on this device (d=%d)", m->d);
+  if (!resident) CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * 64));
   CK(cudaMalloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * 64));
   CK(cudaMalloc(&m->partials, sizeof(KbSweepResult) * m->pred_grid));
   return KB_OK;
@@ -520,6 +524,7 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   a.acq = acq;
   for (int k = 0; k < KB_OUT_COUNT; ++k) a.out[k] = outs_dev ? outs_dev[k] : nullptr;
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
+  a.resident = m->pred_resident;
   const long long nstrips = (npts + 63) / 64;
   const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);
   if (m->profile) CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][0], m->stream));

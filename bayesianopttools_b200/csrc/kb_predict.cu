@@ -25,18 +25,31 @@
 #define PK_STAGES 4
 #define PK_LDA 132
 #define PK_LDB 68
+#define PK_QIN 8          // extra rows (alpha, R^-1 F columns) folded into the psi phase up to this many
 
+// Shared memory: [header][xs d x 64][gw d][1/theta d][big]
+//   streaming kernel: big = A ring [stages][16][132] | psi ring [stages][16][68]
+//   resident kernel : big = L^-1 (k-major) [n_pad][n_pad+4] | psi strip [n_pad][68] | extra-row partials
 struct KbPredSmem {
-  double a[PK_STAGES][PK_KC][PK_LDA];
-  double b[PK_STAGES][PK_KC][PK_LDB];
   double vv[4][PK_MT];
   double red_val[8];
   long long red_idx[8];
   double wk[4];
 };
 
-size_t kb_predict_smem_bytes(int d) {
-  return sizeof(KbPredSmem) + (size_t)d * (PK_MT + 2) * sizeof(double);
+size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx) {
+  size_t big;
+  if (resident)
+    big = sizeof(double) * ((size_t)n_pad * (n_pad + 4) + (size_t)n_pad * PK_LDB + 4 * (size_t)(qx < PK_QIN ? qx : PK_QIN) * PK_MT);
+  else
+    big = sizeof(double) * PK_STAGES * PK_KC * (PK_LDA + PK_LDB);
+  return sizeof(KbPredSmem) + (size_t)d * (PK_MT + 2) * sizeof(double) + big;
+}
+
+// The resident variant needs the whole inverse factor in shared memory.
+bool kb_predict_can_reside(int d, int n_pad, int qx, int nind_trend) {
+  return n_pad <= 128 && nind_trend == 0 && qx <= PK_QIN &&
+         kb_predict_smem_bytes(d, true, n_pad, qx) <= 220 * 1024;
 }
 
 __device__ __forceinline__ double kb_legendre_on(int o, double x) {
@@ -57,7 +70,13 @@ struct KbRunning {
   long long c0, c1, c2;
 };
 
-template <int MASK>
+// RESIDENT = false: any n; psi strips live in an L2-resident scratch slab and stream back through a
+//   cp.async ring together with the fit state.
+// RESIDENT = true : n_pad <= 128 (AK-MCS / early SOBO models): the inverse factor stays in shared
+//   memory for the life of the CTA, the psi strip never leaves shared memory, the triangular
+//   product runs without a single barrier and its row blocks are dealt to the warps in
+//   boustrophedon order so every warp carries the same number of DMMAs.
+template <int MASK, bool RESIDENT>
 __global__ void __launch_bounds__(KB_THREADS, 2)
 kb_predict_kernel(KbPredictArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -65,13 +84,28 @@ kb_predict_kernel(KbPredictArgs P) {
   double* xs = reinterpret_cast<double*>(smem_raw + sizeof(KbPredSmem));   // [d][64]
   double* sgw = xs + P.d * PK_MT;
   double* sith = sgw + P.d;
+  double* big = sith + P.d + ((P.d * (PK_MT + 2)) & 1);                     // 16-byte aligned
+  double (*sa)[PK_KC][PK_LDA] = reinterpret_cast<double (*)[PK_KC][PK_LDA]>(big);
+  double (*sb)[PK_KC][PK_LDB] = reinterpret_cast<double (*)[PK_KC][PK_LDB]>(big + PK_STAGES * PK_KC * PK_LDA);
+  const int lda_r = P.n_pad + 4;
+  double* ATs = big;                                                        // [n_pad][n_pad + 4]
+  double (*psiS)[PK_LDB] = reinterpret_cast<double (*)[PK_LDB]>(big + (size_t)P.n_pad * lda_r);
+  double* exs_r = big + (size_t)P.n_pad * lda_r + (size_t)P.n_pad * PK_LDB;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
   const int wr = warp >> 1, wc = warp & 1;
   const int n = P.n, d = P.d, n_pad = P.n_pad;
-  double* psi = P.psi_scratch + (size_t)blockIdx.x * n_pad * PK_MT;
+  double* psi = RESIDENT ? nullptr : P.psi_scratch + (size_t)blockIdx.x * n_pad * PK_MT;
   double* ex = P.ex_scratch + (size_t)blockIdx.x * P.qx * PK_MT;
+  if (RESIDENT) {
+    for (int e = tid; e < n_pad * (n_pad / 2); e += KB_THREADS) {
+      const int k = e / (n_pad / 2), seg = (e - k * (n_pad / 2)) * 2;
+      kb_cp_async16(&ATs[(size_t)k * lda_r + seg], P.AT + (size_t)k * P.ldat + seg);
+    }
+    kb_cp_async_commit();
+    kb_cp_async_wait<0>();
+  }
 
   for (int i = tid; i < d; i += blockDim.x) {
     sgw[i] = P.gw[i];
@@ -107,8 +141,16 @@ kb_predict_kernel(KbPredictArgs P) {
     }
     __syncthreads();
     // ---- A2. psi strip -> CTA-private scratch (stays in L2) ---------------
+    // With few extra rows (ordinary / low-order Kriging) psi' alpha and F' R^-1 psi are
+    // accumulated right here (2 DFMA per pair) instead of costing a 128-row GEMM block.
+    const bool qin = (P.qx <= PK_QIN);
+    // per row-group partial sums of the extra rows; aliases the (idle) GEMM pipeline buffers
+    double (*exs)[PK_QIN][PK_MT] = reinterpret_cast<double (*)[PK_QIN][PK_MT]>(RESIDENT ? exs_r : big);
     {
       const int p = tid & (PK_MT - 1), kg = tid >> 6;
+      double exa[PK_QIN];
+#pragma unroll
+      for (int j = 0; j < PK_QIN; ++j) exa[j] = 0.0;
       for (int k = kg; k < n_pad; k += KB_THREADS / PK_MT) {
         double val = 0.0;
         if (k < n) {
@@ -118,94 +160,154 @@ kb_predict_kernel(KbPredictArgs P) {
             kb_pair_dim(acc, xs[dim * PK_MT + p] - __ldg(&P.XT[(size_t)dim * n_pad + k]), sgw[dim],
                         sith[dim], MASK);
           val = kb_pair_finish(acc, sm.wk, MASK);
+          if (qin) {
+            const double* ext = P.AT + (size_t)k * P.ldat + n_pad;
+#pragma unroll
+            for (int j = 0; j < PK_QIN; ++j)
+              if (j < P.qx) exa[j] = fma(val, __ldg(&ext[j]), exa[j]);
+          }
         }
-        psi[(size_t)k * PK_MT + p] = val;
+        if (RESIDENT) psiS[k][p] = val;
+        else psi[(size_t)k * PK_MT + p] = val;
+      }
+      if (qin) {
+#pragma unroll
+        for (int j = 0; j < PK_QIN; ++j)
+          if (j < P.qx) (RESIDENT ? exs_r[((size_t)kg * P.qx + j) * PK_MT + p] : exs[kg][j][p]) = exa[j];
       }
     }
     __syncthreads();
+    if (qin) {
+      for (int e = tid; e < P.qx * PK_MT; e += KB_THREADS) {
+        const int j = e / PK_MT, p = e - j * PK_MT;
+        if (RESIDENT)
+          ex[(size_t)j * PK_MT + p] = (exs_r[((size_t)0 * P.qx + j) * PK_MT + p] + exs_r[((size_t)1 * P.qx + j) * PK_MT + p]) +
+                                      (exs_r[((size_t)2 * P.qx + j) * PK_MT + p] + exs_r[((size_t)3 * P.qx + j) * PK_MT + p]);
+        else
+          ex[(size_t)j * PK_MT + p] = (exs[0][j][p] + exs[1][j][p]) + (exs[2][j][p] + exs[3][j][p]);
+      }
+      __syncthreads();
+    }
 
     // ---- B. V = AT^T-blocks x psi on the FP64 tensor pipe -----------------
     double sq[4][2];
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) sq[ni][0] = sq[ni][1] = 0.0;
 
-    const int nblk = P.nrows / PK_BM;
-    for (int I = 0; I < nblk; ++I) {
-      const int kend = ((I + 1) * PK_BM > n_pad) ? n_pad : (I + 1) * PK_BM;
-      const int nch = kend / PK_KC;
-      const double* Ablk = P.AT + (size_t)I * PK_BM;
+    if (RESIDENT) {
+      // rows of L^-1 in 8-row blocks; row group wr takes blocks wr, 7-wr, 8+wr, 15-wr (equal work);
+      // block rb needs k < 8 (rb + 1) only
+      const int n8 = (n + 7) & ~7, nrb = n8 >> 3;
+      int rbs[4], klim[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        rbs[mi] = (mi & 1) ? (mi * 4 + 3 - wr) : (mi * 4 + wr);
+        klim[mi] = (rbs[mi] < nrb) ? 2 * (rbs[mi] + 1) : 0;
+      }
       double acc[4][4][2];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-      auto load_chunk = [&](int c, int stage) {
-        const int k0 = c * PK_KC;
+      const int nks = n8 >> 2;
+      for (int ks = 0; ks < nks; ++ks) {
+        double bf[4];
 #pragma unroll
-        for (int j = 0; j < (PK_KC * PK_BM / 2) / KB_THREADS; ++j) {
-          const int idx = tid + j * KB_THREADS;
-          const int kk = idx >> 6, seg = (idx & 63) * 2;
-          kb_cp_async16(&sm.a[stage][kk][seg], Ablk + (size_t)(k0 + kk) * P.ldat + seg);
-        }
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = psiS[ks * 4 + tq][wc * 32 + ni * 8 + gq];
 #pragma unroll
-        for (int j = 0; j < (PK_KC * PK_MT / 2) / KB_THREADS; ++j) {
-          const int idx = tid + j * KB_THREADS;
-          const int kk = idx >> 5, seg = (idx & 31) * 2;
-          kb_cp_async16(&sm.b[stage][kk][seg], psi + (size_t)(k0 + kk) * PK_MT + seg);
-        }
-      };
+        for (int mi = 0; mi < 4; ++mi)
+          if (ks < klim[mi]) {
+            const double af = ATs[(size_t)(ks * 4 + tq) * lda_r + rbs[mi] * 8 + gq];
 #pragma unroll
-      for (int s = 0; s < PK_STAGES - 1; ++s) {
-        if (s < nch) load_chunk(s, s);
-        kb_cp_async_commit();
-      }
-      for (int c = 0; c < nch; ++c) {
-        kb_cp_async_wait<PK_STAGES - 2>();
-        __syncthreads();
-        {
-          const int cn = c + PK_STAGES - 1;
-          if (cn < nch) load_chunk(cn, cn % PK_STAGES);
-          kb_cp_async_commit();
-        }
-        const int stg = c % PK_STAGES;
-#pragma unroll
-        for (int ks = 0; ks < PK_KC / 4; ++ks) {
-          double af[4], bf[4];
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi) af[mi] = sm.a[stg][ks * 4 + tq][wr * 32 + mi * 8 + gq];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) bf[ni] = sm.b[stg][ks * 4 + tq][wc * 32 + ni * 8 + gq];
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-        }
-      }
-      kb_cp_async_wait<0>();
-      __syncthreads();
-      // block epilogue: squares for L^-1 rows, raw values for the extra rows
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        const int row = I * PK_BM + wr * 32 + mi * 8 + gq;
-        if (row < n_pad) {
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            sq[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], sq[ni][0]);
-            sq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], sq[ni][1]);
+            for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
           }
-        } else {
-          const int j = row - n_pad;
-          if (j < P.qx) {
+      }
 #pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          sq[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], sq[ni][0]);
+          sq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], sq[ni][1]);
+        }
+    } else {
+    const int nblk = qin ? (n_pad + PK_BM - 1) / PK_BM : P.nrows / PK_BM;
+      // One continuous chunk stream over all row blocks: the ring keeps prefetching the next
+      // block's first chunks while the current block drains and runs its (register-only) epilogue.
+      auto nch_of = [&](int I) { return (((I + 1) * PK_BM > n_pad) ? n_pad : (I + 1) * PK_BM) / PK_KC; };
+      int Il = 0, cl = 0;                               // load cursor (row block, chunk)
+      auto issue_next = [&](int stage) {
+        if (Il < nblk) {
+          const double* Ablk = P.AT + (size_t)Il * PK_BM;
+          const int k0 = cl * PK_KC;
+  #pragma unroll
+          for (int j = 0; j < (PK_KC * PK_BM / 2) / KB_THREADS; ++j) {
+            const int idx = tid + j * KB_THREADS;
+            const int kk = idx >> 6, seg = (idx & 63) * 2;
+            kb_cp_async16(&sa[stage][kk][seg], Ablk + (size_t)(k0 + kk) * P.ldat + seg);
+          }
+  #pragma unroll
+          for (int j = 0; j < (PK_KC * PK_MT / 2) / KB_THREADS; ++j) {
+            const int idx = tid + j * KB_THREADS;
+            const int kk = idx >> 5, seg = (idx & 31) * 2;
+            kb_cp_async16(&sb[stage][kk][seg], psi + (size_t)(k0 + kk) * PK_MT + seg);
+          }
+          if (++cl == nch_of(Il)) { cl = 0; ++Il; }
+        }
+        kb_cp_async_commit();
+      };
+  #pragma unroll
+      for (int s = 0; s < PK_STAGES - 1; ++s) issue_next(s);
+      int gi = 0;                                       // chunks consumed so far
+      for (int I = 0; I < nblk; ++I) {
+        const int nch = nch_of(I);
+        double acc[4][4][2];
+  #pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+  #pragma unroll
+          for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int c = 0; c < nch; ++c, ++gi) {
+          kb_cp_async_wait<PK_STAGES - 2>();
+          __syncthreads();
+          issue_next((gi + PK_STAGES - 1) % PK_STAGES);
+          const int stg = gi % PK_STAGES;
+  #pragma unroll
+          for (int ks = 0; ks < PK_KC / 4; ++ks) {
+            double af[4], bf[4];
+  #pragma unroll
+            for (int mi = 0; mi < 4; ++mi) af[mi] = sa[stg][ks * 4 + tq][wr * 32 + mi * 8 + gq];
+  #pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bf[ni] = sb[stg][ks * 4 + tq][wc * 32 + ni * 8 + gq];
+  #pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+  #pragma unroll
+              for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+          }
+        }
+        // block epilogue: squares for L^-1 rows, raw values for the extra rows
+  #pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          const int row = I * PK_BM + wr * 32 + mi * 8 + gq;
+          if (row < n_pad) {
+  #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
-              const int col = wc * 32 + ni * 8 + 2 * tq;
-              ex[(size_t)j * PK_MT + col] = acc[mi][ni][0];
-              ex[(size_t)j * PK_MT + col + 1] = acc[mi][ni][1];
+              sq[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], sq[ni][0]);
+              sq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], sq[ni][1]);
+            }
+          } else if (!qin) {
+            const int j = row - n_pad;
+            if (j < P.qx) {
+  #pragma unroll
+              for (int ni = 0; ni < 4; ++ni) {
+                const int col = wc * 32 + ni * 8 + 2 * tq;
+                ex[(size_t)j * PK_MT + col] = acc[mi][ni][0];
+                ex[(size_t)j * PK_MT + col + 1] = acc[mi][ni][1];
+              }
             }
           }
         }
       }
+      kb_cp_async_wait<0>();
+      __syncthreads();
     }
     // column sums of squares: reduce over the 8 row-groups of the warp, then over wr
 #pragma unroll
@@ -339,12 +441,12 @@ __global__ void kb_sweep_final_kernel(const KbSweepResult* __restrict__ partials
   *result = r;
 }
 
-template <int MASK>
+template <int MASK, bool RESIDENT>
 static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kb_predict_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_kernel<MASK, RESIDENT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(a);
+  kb_predict_kernel<MASK, RESIDENT><<<grid, KB_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -358,9 +460,13 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
   }
 
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {
-  const size_t smem = kb_predict_smem_bytes(a.d);
+  const size_t smem = kb_predict_smem_bytes(a.d, a.resident != 0, a.n_pad, a.qx);
   cudaError_t err = cudaSuccess;
-  KB_DISPATCH_MASK_P(a.kmask, err = kb_predict_launch<M_>(st, a, grid, smem));
+  if (a.resident) {
+    KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, true>(st, a, grid, smem)));
+  } else {
+    KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, false>(st, a, grid, smem)));
+  }
   if (err != cudaSuccess) return err;
   if (result_dev) {
     kb_sweep_final_kernel<<<1, 32, 0, st>>>(a.partials, grid, a.m, result_dev);
@@ -370,15 +476,23 @@ cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid,
 }
 
 // Largest persistent grid for the predict kernel: SMs x resident CTAs per SM.
-int kb_predict_max_grid(int kmask, int d, int num_sms) {
-  const size_t smem = kb_predict_smem_bytes(d);
+int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx) {
+  const size_t smem = kb_predict_smem_bytes(d, resident != 0, n_pad, qx);
   int occ = 0;
   cudaError_t err = cudaSuccess;
-  KB_DISPATCH_MASK_P(kmask, {
-    err = cudaFuncSetAttribute(kb_predict_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess)
-      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_>, KB_THREADS, smem);
-  });
+  if (resident) {
+    KB_DISPATCH_MASK_P(kmask, {
+      err = cudaFuncSetAttribute(kb_predict_kernel<M_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err == cudaSuccess)
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_, true>, KB_THREADS, smem);
+    });
+  } else {
+    KB_DISPATCH_MASK_P(kmask, {
+      err = cudaFuncSetAttribute(kb_predict_kernel<M_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err == cudaSuccess)
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_, false>, KB_THREADS, smem);
+    });
+  }
   if (err != cudaSuccess) { cudaGetLastError(); return 0; }
   return occ * num_sms;
 }
