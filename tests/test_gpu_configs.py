@@ -1,0 +1,191 @@
+"""GPU parity at the shapes of BASELINE.json configs[2..4] (C3 trend Kriging,
+C4 KPLS, C5 AK-MCS) and for the code paths those shapes switch on in the CUDA kernels:
+
+  * right-hand sides wider than 16 rows (full 64-row tile tasks, paired 128-row tasks, several
+    Schur tiles) and wider than one tile (sb >= 2)                      -- kb_chol.cu
+  * populations larger than the number of chain workers                 -- kb_chol.cu
+  * the shared-memory resident predictor (n_pad <= 128) next to the streaming one -- kb_predict.cu
+
+Sizes are cut so the numpy oracle finishes in seconds; the full-size shapes are covered through
+size-independent properties (sub-population equality, shard additivity of the AK-MCS counters).
+Tolerances as in test_gpu_parity.py: relative 1e-9 on NLL / beta / sigma^2, scale-relative 5e-9 on
+predictor outputs, identical indices and counters.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import kriging_oracle as ko
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bayesianopttools_b200 import _lib
+    _lib.require_gpu()
+    return _lib
+
+
+def styb(X5):
+    return 0.5 * np.sum(X5 ** 4 - 16 * X5 ** 2 + 5 * X5, axis=1)
+
+
+def _trend_case(n, d, order, seed):
+    rng = np.random.default_rng(seed)
+    Xn = rng.uniform(-1, 1, (n, d))
+    y = styb(5 * Xn)
+    idx = ko.total_order_index(order, d)
+    F = ko.legendre_basis(idx, Xn)
+    return Xn, y, F, idx
+
+
+@pytest.mark.parametrize("n,d,order", [(300, 6, 2), (400, 10, 2), (130, 3, 3)])
+def test_c3_trend_nll_beta_sigma(lib, n, d, order):
+    """C3 shape (polynomial-trend Kriging): nind = 28 / 66 / 20 regressors -> the right-hand sides
+    take 1-2 full tile rows; NLL, beta and sigma^2 against the oracle."""
+    Xn, y, F, idx = _trend_case(n, d, order, seed=11)
+    assert F.shape[1] + 1 > 16
+    xpop = np.random.default_rng(12).uniform(-0.2, 0.6, (5, d))
+    mdl = lib.DeviceModel(Xn, y, F, ["gaussian"])
+    nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
+    assert np.all(info == 0)
+    beta, s2 = mdl.nll_extras(len(xpop))
+    for b in range(len(xpop)):
+        ref = ko.nll(xpop[b], Xn, y, F, full=True)
+        assert abs(nll[b] - ref["NegLnLike"]) / abs(ref["NegLnLike"]) < TOL, (b, nll[b], ref["NegLnLike"])
+        assert relerr(beta[b], ref["BE"]) < 1e-7, (b, relerr(beta[b], ref["BE"]))
+        assert abs(s2[b] - ref["SigmaSqr"]) / ref["SigmaSqr"] < 1e-8
+    mdl.close()
+
+
+def test_c3_trend_fit_and_predict(lib):
+    """Fit state + streaming predictor with q = 29 extra rows (the GEMM path for the extra rows)."""
+    n, d = 300, 6
+    Xn, y, F, idx = _trend_case(n, d, 2, seed=13)
+    x = np.full(d, 0.2)
+    mdl = lib.DeviceModel(Xn, y, F, ["gaussian"])
+    st = mdl.fit_state(x, False, -6.0)
+    fit = ko.nll(x, Xn, y, F, full=True)
+    assert abs(st["NegLnLike"] - fit["NegLnLike"]) / abs(fit["NegLnLike"]) < TOL
+    assert relerr(st["U"], fit["U"]) < TOL
+    mdl.set_trend(idx)
+    mdl.set_norm(lib.NORM_NONE)
+    xq = np.random.default_rng(14).uniform(-1, 1, (500, d))
+    outs, _ = mdl.predict(xq, ("pred", "ssqr", "fpc"))
+    ref = ko.predict(xq, Xn, y, F, idx, fit)
+    for k in ("pred", "ssqr", "fpc"):
+        assert relerr(outs[k], ref[k]) < 5e-9, (k, relerr(outs[k], ref[k]))
+    mdl.close()
+
+
+def test_c4_kpls_shape(lib):
+    """C4 shape cut to n=600 (d=100, h=3): KPLS-folded Gaussian correlation, NLL vs the oracle."""
+    from sklearn.cross_decomposition import PLSRegression
+    rng = np.random.default_rng(21)
+    n, d, h = 600, 100, 3
+    Xn = rng.uniform(-1, 1, (n, d))
+    y = styb(5 * Xn[:, :10]) + 0.1 * np.sum((5 * Xn[:, 10:]) ** 2, axis=1)
+    pls = PLSRegression(n_components=h).fit(Xn, y)
+    coef = np.asarray(pls.x_rotations_, dtype=np.float64)
+    F = np.ones((n, 1))
+    xpop = np.random.default_rng(22).uniform(-0.5, 1.0, (6, h))
+    mdl = lib.DeviceModel(Xn, y, F, ["gaussian"], model_type="kpls", plscoeff=coef)
+    nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
+    assert np.all(info == 0)
+    for b in range(len(xpop)):
+        ref = ko.nll(xpop[b], Xn, y, F, plscoeff=coef, n_princomp=h)
+        assert abs(nll[b] - ref) / abs(ref) < TOL, (b, nll[b], ref)
+    mdl.close()
+
+
+def test_population_larger_than_chain_workers(lib):
+    """B = 150 candidates: every chain worker walks several candidates; results equal the same
+    candidates evaluated in small populations (bitwise) and the oracle."""
+    rng = np.random.default_rng(31)
+    n, d, B = 200, 4, 150
+    Xn = rng.uniform(-1, 1, (n, d))
+    y = styb(5 * Xn)
+    F = np.ones((n, 1))
+    xpop = np.random.default_rng(32).uniform(-0.5, 0.8, (B, d))
+    mdl = lib.DeviceModel(Xn, y, F, ["matern52"])
+    nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
+    assert np.all(info == 0)
+    small = np.concatenate([mdl.nll_batch(xpop[i:i + 7], False, -6.0) for i in range(0, B, 7)])
+    assert np.array_equal(nll, small)
+    for b in (0, 77, 149):
+        ref = ko.nll(xpop[b], Xn, y, F, kernels=("matern52",))
+        assert abs(nll[b] - ref) / abs(ref) < TOL
+    mdl.close()
+
+
+@pytest.mark.parametrize("n,d,kernel", [(100, 3, "matern52"), (128, 2, "gaussian"), (65, 5, "exponential"),
+                                        (129, 2, "gaussian")])
+def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
+    """n_pad = 128 (resident: inverse factor in shared memory) and n_pad = 192 (streaming) around
+    the switch-over, all predictor outputs and the reductions."""
+    rng = np.random.default_rng(41)
+    Xn = rng.uniform(-1, 1, (n, d))
+    y = np.sum(Xn ** 2, axis=1) - 0.7 + 0.3 * np.sin(3 * Xn[:, 0])
+    F = np.ones((n, 1))
+    x = np.full(d, -0.1)
+    mdl = lib.DeviceModel(Xn, y, F, [kernel])
+    mdl.fit_state(x, False, -6.0, want_U=False, want_Psi=False)
+    fit = ko.nll(x, Xn, y, F, kernels=(kernel,), full=True)
+    mdl.set_norm(lib.NORM_NONE)
+    m = 64 * 300 + 11
+    xq = rng.uniform(-1, 1, (m, d))
+    names = ("pred", "ssqr", "s", "ei", "poi", "pof", "u")
+    outs, res = mdl.predict(xq, names, acq="u", ybest=float(y.min()), limit=0.2, limit_sign=1)
+    ref = ko.predict(xq, Xn, y, F, np.zeros((1, d), int), fit, kernels=(kernel,), limit=0.2)
+    ref["u"] = ref["U"]
+    for k in names:
+        assert relerr(outs[k], ref[k]) < 2e-8, (k, relerr(outs[k], ref[k]))
+    assert res["min_u_idx"] == int(np.argmin(outs["u"]))
+    assert res["n_fail"] == int(np.sum(outs["pred"] <= 0))
+    assert res["n_fail_minus"] == int(np.sum(outs["pred"] - 1.96 * outs["s"] <= 0))
+    assert res["n_fail_plus"] == int(np.sum(outs["pred"] + 1.96 * outs["s"] <= 0))
+    mdl.close()
+
+
+def test_c5_akmcs_counters_are_shard_additive(lib):
+    """C5 shape (four-branch limit state, d = 2, Monte-Carlo population): the three failure
+    counters and the arg-min of U over 2e6 points equal the merge of two shards (the multi-GPU
+    rule of parallel.py) and, on a 20000-point prefix, the oracle."""
+    rng = np.random.default_rng(51)
+    n, d, k7 = 40, 2, 7.0
+    X = rng.uniform(-5, 5, (n, d))
+
+    def fourbranch(x):
+        x1, x2 = x[:, 0], x[:, 1]
+        return np.minimum.reduce([3 + 0.1 * (x1 - x2) ** 2 - (x1 + x2) / np.sqrt(2),
+                                  3 + 0.1 * (x1 - x2) ** 2 + (x1 + x2) / np.sqrt(2),
+                                  (x1 - x2) + k7 / np.sqrt(2), (x2 - x1) + k7 / np.sqrt(2)])
+    y = fourbranch(X)
+    lb, ub = -5.0 * np.ones(d), 5.0 * np.ones(d)
+    Xn = ko.standardize_x(X, lb, ub)
+    F = np.ones((n, 1))
+    x = np.array([-0.3, -0.3])
+    mdl = lib.DeviceModel(Xn, y, F, ["gaussian"])
+    mdl.fit_state(x, False, -6.0, want_U=False, want_Psi=False)
+    fit = ko.nll(x, Xn, y, F, full=True)
+    mdl.set_norm(lib.NORM_DEFAULT, lb, ub)
+    N = 2_000_000
+    pop = rng.standard_normal((N, d))
+    _, whole = mdl.predict(pop, (), acq="u")
+    half = N // 2 + 13
+    _, a = mdl.predict(pop[:half], (), acq="u")
+    _, b = mdl.predict(pop[half:], (), acq="u")
+    b["min_u_idx"] += half                              # shard-local -> global index
+    for key in ("n_fail", "n_fail_minus", "n_fail_plus"):
+        assert whole[key] == a[key] + b[key], key
+    best = a if (a["min_u"], a["min_u_idx"]) <= (b["min_u"], b["min_u_idx"]) else b
+    assert whole["min_u_idx"] == best["min_u_idx"] and whole["min_u"] == best["min_u"]
+    sub = 20000
+    outs, r = mdl.predict(pop[:sub], ("pred", "s"), acq="u")
+    ref = ko.predict(ko.standardize_x(pop[:sub], lb, ub), Xn, y, F, np.zeros((1, d), int), fit)
+    assert relerr(outs["pred"], ref["pred"]) < TOL
+    assert r["n_fail"] == int(np.sum(ref["pred"] <= 0))
+    assert r["min_u_idx"] == int(np.argmin(ref["U"]))
+    mdl.close()
