@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -494,8 +495,9 @@ static kb_status ensure_predict_scratch(kb_model* m) {
   m->pred_resident = resident;
   m->pred_grid = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx);
   if (m->pred_grid < 1) KB_FAIL(KB_ERR_CUDA, "predict kernel does not fit on this device (d=%d)", m->d);
-  if (!resident) CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * 64));
-  CK(cudaMalloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * 64));
+  const size_t strip = kb_predict_strip(resident != 0);
+  if (!resident) CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip));
+  CK(cudaMalloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * strip));
   CK(cudaMalloc(&m->partials, sizeof(KbSweepResult) * m->pred_grid));
   return KB_OK;
 }
@@ -525,7 +527,8 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   for (int k = 0; k < KB_OUT_COUNT; ++k) a.out[k] = outs_dev ? outs_dev[k] : nullptr;
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
   a.resident = m->pred_resident;
-  const long long nstrips = (npts + 63) / 64;
+  const long long strip = kb_predict_strip(m->pred_resident != 0);
+  const long long nstrips = (npts + strip - 1) / strip;
   const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);
   if (m->profile) CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][0], m->stream));
   CK(kb_launch_predict(m->stream, a, grid, result_dev));

@@ -113,8 +113,8 @@ struct KbPredictArgs {
   // outputs (device, each m doubles or null)
   double* out[KB_OUT_COUNT];
   // scratch
-  double* psi_scratch;     // [grid][n_pad][64]
-  double* ex_scratch;      // [grid][qx][64]
+  double* psi_scratch;     // [grid][n_pad][strip]   (streaming variant only; strip = 128)
+  double* ex_scratch;      // [grid][qx][strip]
   int qx;                  // extra rows (1 + nind)
   int resident;            // 1: inverse factor and psi strip stay in shared memory (n_pad <= 128)
   KbSweepResult* partials; // [grid]
@@ -122,6 +122,7 @@ struct KbPredictArgs {
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev);
 size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx);
 bool kb_predict_can_reside(int d, int n_pad, int qx, int nind_trend);
+int kb_predict_strip(bool resident);
 int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx);
 
 // --- kb_peak.cu --------------------------------------------------------------

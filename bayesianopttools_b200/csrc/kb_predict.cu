@@ -19,31 +19,33 @@
 #include "kb_common.cuh"
 #include "kb_internal.h"
 
-#define PK_MT 64
 #define PK_BM 128
 #define PK_KC 16
 #define PK_STAGES 4
 #define PK_LDA 132
-#define PK_LDB 68
+#define PK_TK 16          // rows of the training set per psi-phase tile
 #define PK_QIN 8          // extra rows (alpha, R^-1 F columns) folded into the psi phase up to this many
 
 // Shared memory: [header][xs d x 64][gw d][1/theta d][big]
 //   streaming kernel: big = A ring [stages][16][132] | psi ring [stages][16][68]
 //   resident kernel : big = L^-1 (k-major) [n_pad][n_pad+4] | psi strip [n_pad][68] | extra-row partials
 struct KbPredSmem {
-  double vv[4][PK_MT];
-  double red_val[8];
-  long long red_idx[8];
+  double vv[4][128];
+  KbSweepResult red[4];
   double wk[4];
 };
 
+int kb_predict_strip(bool resident) { (void)resident; return 64; }
+int kb_predict_threads(bool resident) { (void)resident; return 256; }
+
 size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx) {
+  const size_t mt = kb_predict_strip(resident);
   size_t big;
   if (resident)
-    big = sizeof(double) * ((size_t)n_pad * (n_pad + 4) + (size_t)n_pad * PK_LDB + 4 * (size_t)(qx < PK_QIN ? qx : PK_QIN) * PK_MT);
+    big = sizeof(double) * ((size_t)n_pad * (n_pad + 4) + (size_t)n_pad * (mt + 4) + 4 * (size_t)(qx < PK_QIN ? qx : PK_QIN) * mt);
   else
-    big = sizeof(double) * PK_STAGES * PK_KC * (PK_LDA + PK_LDB);
-  return sizeof(KbPredSmem) + (size_t)d * (PK_MT + 2) * sizeof(double) + big;
+    big = sizeof(double) * PK_STAGES * PK_KC * (PK_LDA + mt + 4);
+  return sizeof(KbPredSmem) + ((size_t)d * (mt + 2) + 2 * (size_t)d * PK_TK + 2 * PK_TK * PK_QIN) * sizeof(double) + big;
 }
 
 // The resident variant needs the whole inverse factor in shared memory.
@@ -77,29 +79,37 @@ struct KbRunning {
 //   product runs without a single barrier and its row blocks are dealt to the warps in
 //   boustrophedon order so every warp carries the same number of DMMAs.
 template <int MASK, bool RESIDENT>
-__global__ void __launch_bounds__(KB_THREADS, 2)
+__global__ void __launch_bounds__(256, 2)
 kb_predict_kernel(KbPredictArgs P) {
+  // 256 threads, 64-site strips, 2 CTAs/SM (a single 512-thread CTA with 128-site strips was measured
+  // 10 % slower: the psi phase and the DMMA product of ONE CTA cannot overlap).
+  constexpr int MT = 64;                         // sites per strip
+  constexpr int NT = 256;                        // threads
+  constexpr int LDB = MT + 4;                    // padded psi row (== 4 mod 16)
+  constexpr int WCN = MT / 32;                   // warps across the strip
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KbPredSmem& sm = *reinterpret_cast<KbPredSmem*>(smem_raw);
   double* xs = reinterpret_cast<double*>(smem_raw + sizeof(KbPredSmem));   // [d][64]
-  double* sgw = xs + P.d * PK_MT;
+  double* sgw = xs + P.d * MT;
   double* sith = sgw + P.d;
-  double* big = sith + P.d + ((P.d * (PK_MT + 2)) & 1);                     // 16-byte aligned
+  double* xtile = sith + P.d;                                             // [2][d][16] training-site tiles
+  double* etile = xtile + 2 * P.d * PK_TK;                                // [2][16][PK_QIN] extra columns
+  double* big = etile + 2 * PK_TK * PK_QIN;
   double (*sa)[PK_KC][PK_LDA] = reinterpret_cast<double (*)[PK_KC][PK_LDA]>(big);
-  double (*sb)[PK_KC][PK_LDB] = reinterpret_cast<double (*)[PK_KC][PK_LDB]>(big + PK_STAGES * PK_KC * PK_LDA);
+  double (*sb)[PK_KC][LDB] = reinterpret_cast<double (*)[PK_KC][LDB]>(big + PK_STAGES * PK_KC * PK_LDA);
   const int lda_r = P.n_pad + 4;
   double* ATs = big;                                                        // [n_pad][n_pad + 4]
-  double (*psiS)[PK_LDB] = reinterpret_cast<double (*)[PK_LDB]>(big + (size_t)P.n_pad * lda_r);
-  double* exs_r = big + (size_t)P.n_pad * lda_r + (size_t)P.n_pad * PK_LDB;
+  double (*psiS)[LDB] = reinterpret_cast<double (*)[LDB]>(big + (size_t)P.n_pad * lda_r);
+  double* exs_r = big + (size_t)P.n_pad * lda_r + (size_t)P.n_pad * LDB;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
-  const int wr = warp >> 1, wc = warp & 1;
+  const int wr = warp / WCN, wc = warp % WCN;
   const int n = P.n, d = P.d, n_pad = P.n_pad;
-  double* psi = RESIDENT ? nullptr : P.psi_scratch + (size_t)blockIdx.x * n_pad * PK_MT;
-  double* ex = P.ex_scratch + (size_t)blockIdx.x * P.qx * PK_MT;
+  double* psi = RESIDENT ? nullptr : P.psi_scratch + (size_t)blockIdx.x * n_pad * MT;
+  double* ex = P.ex_scratch + (size_t)blockIdx.x * P.qx * MT;
   if (RESIDENT) {
-    for (int e = tid; e < n_pad * (n_pad / 2); e += KB_THREADS) {
+    for (int e = tid; e < n_pad * (n_pad / 2); e += NT) {
       const int k = e / (n_pad / 2), seg = (e - k * (n_pad / 2)) * 2;
       kb_cp_async16(&ATs[(size_t)k * lda_r + seg], P.AT + (size_t)k * P.ldat + seg);
     }
@@ -119,13 +129,13 @@ kb_predict_kernel(KbPredictArgs P) {
   run.best_idx = 0x7fffffffffffffffLL; run.min_u_idx = 0x7fffffffffffffffLL;
   run.c0 = run.c1 = run.c2 = 0;
 
-  const long long nstrips = (P.m + PK_MT - 1) / PK_MT;
+  const long long nstrips = (P.m + MT - 1) / MT;
   for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
-    const long long p0 = strip * PK_MT;
-    const int npt = (int)((P.m - p0 < PK_MT) ? (P.m - p0) : PK_MT);
+    const long long p0 = strip * MT;
+    const int npt = (int)((P.m - p0 < MT) ? (P.m - p0) : MT);
     __syncthreads();
     // ---- A1. load + standardise the strip -------------------------------
-    for (int e = tid; e < PK_MT * d; e += blockDim.x) {
+    for (int e = tid; e < MT * d; e += blockDim.x) {
       const int p = e / d, dim = e - p * d;
       double v = 0.0;
       if (p < npt) {
@@ -137,7 +147,7 @@ kb_predict_kernel(KbPredictArgs P) {
           v = (v - P.p0[dim]) / P.p1[dim];
         }
       }
-      xs[dim * PK_MT + p] = v;
+      xs[dim * MT + p] = v;
     }
     __syncthreads();
     // ---- A2. psi strip -> CTA-private scratch (stays in L2) ---------------
@@ -145,46 +155,81 @@ kb_predict_kernel(KbPredictArgs P) {
     // accumulated right here (2 DFMA per pair) instead of costing a 128-row GEMM block.
     const bool qin = (P.qx <= PK_QIN);
     // per row-group partial sums of the extra rows; aliases the (idle) GEMM pipeline buffers
-    double (*exs)[PK_QIN][PK_MT] = reinterpret_cast<double (*)[PK_QIN][PK_MT]>(RESIDENT ? exs_r : big);
+    double (*exs)[PK_QIN][MT] = reinterpret_cast<double (*)[PK_QIN][MT]>(RESIDENT ? exs_r : big);
     {
-      const int p = tid & (PK_MT - 1), kg = tid >> 6;
+      // Training sites and the extra columns of the fit state arrive in 16-row tiles through a
+      // double-buffered cp.async stage; a thread owns one site and 4 rows of the tile, i.e. four
+      // independent correlation chains (the phase is FP64-issue bound, not latency bound).
+      const int p = tid & (MT - 1), kg = tid / MT;
       double exa[PK_QIN];
 #pragma unroll
       for (int j = 0; j < PK_QIN; ++j) exa[j] = 0.0;
-      for (int k = kg; k < n_pad; k += KB_THREADS / PK_MT) {
-        double val = 0.0;
-        if (k < n) {
-          KbPairAcc acc;
-          kb_pair_init(acc);
-          for (int dim = 0; dim < d; ++dim)
-            kb_pair_dim(acc, xs[dim * PK_MT + p] - __ldg(&P.XT[(size_t)dim * n_pad + k]), sgw[dim],
-                        sith[dim], MASK);
-          val = kb_pair_finish(acc, sm.wk, MASK);
-          if (qin) {
-            const double* ext = P.AT + (size_t)k * P.ldat + n_pad;
-#pragma unroll
-            for (int j = 0; j < PK_QIN; ++j)
-              if (j < P.qx) exa[j] = fma(val, __ldg(&ext[j]), exa[j]);
+      const int ntile = n_pad / PK_TK;
+      auto issue_tile = [&](int t, int buf) {
+        double* xt = xtile + (size_t)buf * d * PK_TK;
+        for (int e = tid; e < d * (PK_TK / 2); e += NT) {
+          const int dim = e / (PK_TK / 2), seg = (e - dim * (PK_TK / 2)) * 2;
+          kb_cp_async16(&xt[dim * PK_TK + seg], P.XT + (size_t)dim * n_pad + t * PK_TK + seg);
+        }
+        if (qin) {
+          double* et = etile + (size_t)buf * PK_TK * PK_QIN;
+          const int nseg = (P.qx + 1) >> 1;
+          for (int e = tid; e < PK_TK * nseg; e += NT) {
+            const int r = e / nseg, seg = (e - r * nseg) * 2;
+            kb_cp_async16(&et[r * PK_QIN + seg], P.AT + (size_t)(t * PK_TK + r) * P.ldat + n_pad + seg);
           }
         }
-        if (RESIDENT) psiS[k][p] = val;
-        else psi[(size_t)k * PK_MT + p] = val;
+        kb_cp_async_commit();
+      };
+      issue_tile(0, 0);
+      for (int t = 0; t < ntile; ++t) {
+        kb_cp_async_wait<0>();
+        __syncthreads();
+        if (t + 1 < ntile) issue_tile(t + 1, (t + 1) & 1);
+        const double* xt = xtile + (size_t)(t & 1) * d * PK_TK + kg * 4;
+        const double* et = etile + (size_t)(t & 1) * PK_TK * PK_QIN + kg * 4 * PK_QIN;
+        KbPairAcc acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kb_pair_init(acc[i]);
+#pragma unroll 2
+        for (int dim = 0; dim < d; ++dim) {
+          const double x = xs[dim * MT + p], gw = sgw[dim], ith = sith[dim];
+          const double2 xa = *reinterpret_cast<const double2*>(&xt[dim * PK_TK]);
+          const double2 xb = *reinterpret_cast<const double2*>(&xt[dim * PK_TK + 2]);
+          kb_pair_dim(acc[0], x - xa.x, gw, ith, MASK);
+          kb_pair_dim(acc[1], x - xa.y, gw, ith, MASK);
+          kb_pair_dim(acc[2], x - xb.x, gw, ith, MASK);
+          kb_pair_dim(acc[3], x - xb.y, gw, ith, MASK);
+        }
+        const int k0 = t * PK_TK + kg * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double val = kb_pair_finish(acc[i], sm.wk, MASK);
+          if (k0 + i >= n) val = 0.0;
+          if (qin) {
+#pragma unroll
+            for (int j = 0; j < PK_QIN; ++j)
+              if (j < P.qx) exa[j] = fma(val, et[i * PK_QIN + j], exa[j]);
+          }
+          if (RESIDENT) psiS[k0 + i][p] = val;
+          else psi[(size_t)(k0 + i) * MT + p] = val;
+        }
       }
       if (qin) {
 #pragma unroll
         for (int j = 0; j < PK_QIN; ++j)
-          if (j < P.qx) (RESIDENT ? exs_r[((size_t)kg * P.qx + j) * PK_MT + p] : exs[kg][j][p]) = exa[j];
+          if (j < P.qx) (RESIDENT ? exs_r[((size_t)kg * P.qx + j) * MT + p] : exs[kg][j][p]) = exa[j];
       }
     }
     __syncthreads();
     if (qin) {
-      for (int e = tid; e < P.qx * PK_MT; e += KB_THREADS) {
-        const int j = e / PK_MT, p = e - j * PK_MT;
+      for (int e = tid; e < P.qx * MT; e += NT) {
+        const int j = e / MT, p = e - j * MT;
         if (RESIDENT)
-          ex[(size_t)j * PK_MT + p] = (exs_r[((size_t)0 * P.qx + j) * PK_MT + p] + exs_r[((size_t)1 * P.qx + j) * PK_MT + p]) +
-                                      (exs_r[((size_t)2 * P.qx + j) * PK_MT + p] + exs_r[((size_t)3 * P.qx + j) * PK_MT + p]);
+          ex[(size_t)j * MT + p] = (exs_r[((size_t)0 * P.qx + j) * MT + p] + exs_r[((size_t)1 * P.qx + j) * MT + p]) +
+                                      (exs_r[((size_t)2 * P.qx + j) * MT + p] + exs_r[((size_t)3 * P.qx + j) * MT + p]);
         else
-          ex[(size_t)j * PK_MT + p] = (exs[0][j][p] + exs[1][j][p]) + (exs[2][j][p] + exs[3][j][p]);
+          ex[(size_t)j * MT + p] = (exs[0][j][p] + exs[1][j][p]) + (exs[2][j][p] + exs[3][j][p]);
       }
       __syncthreads();
     }
@@ -240,23 +285,24 @@ kb_predict_kernel(KbPredictArgs P) {
           const double* Ablk = P.AT + (size_t)Il * PK_BM;
           const int k0 = cl * PK_KC;
   #pragma unroll
-          for (int j = 0; j < (PK_KC * PK_BM / 2) / KB_THREADS; ++j) {
-            const int idx = tid + j * KB_THREADS;
+          for (int j = 0; j < (PK_KC * PK_BM / 2) / NT; ++j) {
+            const int idx = tid + j * NT;
             const int kk = idx >> 6, seg = (idx & 63) * 2;
             kb_cp_async16(&sa[stage][kk][seg], Ablk + (size_t)(k0 + kk) * P.ldat + seg);
           }
   #pragma unroll
-          for (int j = 0; j < (PK_KC * PK_MT / 2) / KB_THREADS; ++j) {
-            const int idx = tid + j * KB_THREADS;
-            const int kk = idx >> 5, seg = (idx & 31) * 2;
-            kb_cp_async16(&sb[stage][kk][seg], psi + (size_t)(k0 + kk) * PK_MT + seg);
+          for (int j = 0; j < (PK_KC * MT / 2) / NT; ++j) {
+            const int idx = tid + j * NT;
+            const int kk = idx / (MT / 2), seg = (idx % (MT / 2)) * 2;
+            kb_cp_async16(&sb[stage][kk][seg], psi + (size_t)(k0 + kk) * MT + seg);
           }
           if (++cl == nch_of(Il)) { cl = 0; ++Il; }
         }
         kb_cp_async_commit();
       };
   #pragma unroll
-      for (int s = 0; s < PK_STAGES - 1; ++s) issue_next(s);
+  #pragma unroll
+    for (int s = 0; s < PK_STAGES - 1; ++s) issue_next(s);
       int gi = 0;                                       // chunks consumed so far
       for (int I = 0; I < nblk; ++I) {
         const int nch = nch_of(I);
@@ -299,8 +345,8 @@ kb_predict_kernel(KbPredictArgs P) {
   #pragma unroll
               for (int ni = 0; ni < 4; ++ni) {
                 const int col = wc * 32 + ni * 8 + 2 * tq;
-                ex[(size_t)j * PK_MT + col] = acc[mi][ni][0];
-                ex[(size_t)j * PK_MT + col + 1] = acc[mi][ni][1];
+                ex[(size_t)j * MT + col] = acc[mi][ni][0];
+                ex[(size_t)j * MT + col + 1] = acc[mi][ni][1];
               }
             }
           }
@@ -323,13 +369,13 @@ kb_predict_kernel(KbPredictArgs P) {
     __syncthreads();
 
     // ---- C. per-site outputs ------------------------------------------------
-    if (tid < PK_MT && tid < npt) {
+    if (tid < MT && tid < npt) {
       const int p = tid;
       const double vv = sm.vv[0][p] + sm.vv[1][p] + sm.vv[2][p] + sm.vv[3][p];
       double fpc, t2;
       if (P.idx == nullptr) {
         fpc = P.beta[0];
-        const double u = (ex[PK_MT + p] - 1.0) / P.LM[0];
+        const double u = (ex[MT + p] - 1.0) / P.LM[0];
         t2 = u * u;
       } else {
         fpc = 0.0;
@@ -339,13 +385,13 @@ kb_predict_kernel(KbPredictArgs P) {
           double pc = 1.0;
           for (int dim = 0; dim < d; ++dim) {
             const int o = P.idx[a * d + dim];
-            if (o) pc *= kb_legendre_on(o, xs[dim * PK_MT + p]);
+            if (o) pc *= kb_legendre_on(o, xs[dim * MT + p]);
           }
           fpc = fma(pc, P.beta[a], fpc);
-          double u = ex[(size_t)(1 + a) * PK_MT + p] - pc;
-          for (int c = 0; c < a; ++c) u = fma(-P.LM[(size_t)a * nind + c], ex[(size_t)(1 + c) * PK_MT + p], u);
+          double u = ex[(size_t)(1 + a) * MT + p] - pc;
+          for (int c = 0; c < a; ++c) u = fma(-P.LM[(size_t)a * nind + c], ex[(size_t)(1 + c) * MT + p], u);
           u /= P.LM[(size_t)a * nind + a];
-          ex[(size_t)(1 + a) * PK_MT + p] = u;   // w = LM^-1 u, in place
+          ex[(size_t)(1 + a) * MT + p] = u;   // w = LM^-1 u, in place
           t2 = fma(u, u, t2);
         }
       }
@@ -383,7 +429,7 @@ kb_predict_kernel(KbPredictArgs P) {
 
   // ---- CTA partial: (min, lowest index) + counters over threads 0..63 ------
   __syncthreads();
-  if (warp < 2) {
+  if (warp < MT / 32) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ov = __shfl_xor_sync(0xffffffffu, run.best_val, o);
@@ -397,27 +443,26 @@ kb_predict_kernel(KbPredictArgs P) {
       run.c2 += __shfl_xor_sync(0xffffffffu, run.c2, o);
     }
     if (lane == 0) {
-      sm.red_val[warp * 2] = run.best_val; sm.red_idx[warp * 4] = run.best_idx;
-      sm.red_val[warp * 2 + 1] = run.min_u; sm.red_idx[warp * 4 + 1] = run.min_u_idx;
-      sm.red_idx[warp * 4 + 2] = run.c0; sm.red_idx[warp * 4 + 3] = run.c1;
-      sm.red_val[4 + warp] = (double)run.c2;
+      KbSweepResult r;
+      r.best_val = run.best_val; r.best_idx = run.best_idx;
+      r.min_u = run.min_u; r.min_u_idx = run.min_u_idx;
+      r.n_fail = run.c0; r.n_fail_minus = run.c1; r.n_fail_plus = run.c2; r.n_points = 0;
+      sm.red[warp] = r;
     }
   }
   __syncthreads();
   if (tid == 0) {
-    KbSweepResult r;
-    r.best_val = sm.red_val[0]; r.best_idx = sm.red_idx[0];
-    if (sm.red_val[2] < r.best_val || (sm.red_val[2] == r.best_val && sm.red_idx[4] < r.best_idx)) {
-      r.best_val = sm.red_val[2]; r.best_idx = sm.red_idx[4];
+    KbSweepResult r = sm.red[0];
+    for (int wv = 1; wv < MT / 32; ++wv) {
+      const KbSweepResult q = sm.red[wv];
+      if (q.best_val < r.best_val || (q.best_val == r.best_val && q.best_idx < r.best_idx)) {
+        r.best_val = q.best_val; r.best_idx = q.best_idx;
+      }
+      if (q.min_u < r.min_u || (q.min_u == r.min_u && q.min_u_idx < r.min_u_idx)) {
+        r.min_u = q.min_u; r.min_u_idx = q.min_u_idx;
+      }
+      r.n_fail += q.n_fail; r.n_fail_minus += q.n_fail_minus; r.n_fail_plus += q.n_fail_plus;
     }
-    r.min_u = sm.red_val[1]; r.min_u_idx = sm.red_idx[1];
-    if (sm.red_val[3] < r.min_u || (sm.red_val[3] == r.min_u && sm.red_idx[5] < r.min_u_idx)) {
-      r.min_u = sm.red_val[3]; r.min_u_idx = sm.red_idx[5];
-    }
-    r.n_fail = sm.red_idx[2] + sm.red_idx[6];
-    r.n_fail_minus = sm.red_idx[3] + sm.red_idx[7];
-    r.n_fail_plus = (long long)(sm.red_val[4] + sm.red_val[5]);
-    r.n_points = 0;
     P.partials[blockIdx.x] = r;
   }
 }
@@ -446,7 +491,7 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
   cudaError_t e = cudaFuncSetAttribute(kb_predict_kernel<MASK, RESIDENT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_kernel<MASK, RESIDENT><<<grid, KB_THREADS, smem, st>>>(a);
+  kb_predict_kernel<MASK, RESIDENT><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -484,13 +529,13 @@ int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, 
     KB_DISPATCH_MASK_P(kmask, {
       err = cudaFuncSetAttribute(kb_predict_kernel<M_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err == cudaSuccess)
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_, true>, KB_THREADS, smem);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_, true>, 256, smem);
     });
   } else {
     KB_DISPATCH_MASK_P(kmask, {
       err = cudaFuncSetAttribute(kb_predict_kernel<M_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err == cudaSuccess)
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_, false>, KB_THREADS, smem);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_predict_kernel<M_, false>, 256, smem);
     });
   }
   if (err != cudaSuccess) { cudaGetLastError(); return 0; }
