@@ -48,6 +48,7 @@
 #define KB_RING_ROWS 384
 struct KbCholSmem {
   double ring[KB_RING_ROWS][KB_LDK];
+  int4 tdesc;
   int task;
   int ready;
   int misc[6];
@@ -334,10 +335,12 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
     kb_cp_async_wait<NS - 2>();
     __syncthreads();
     if (poll) ready_cols = sm.ready;
-    {
+    // the stage freed by the barrier is refilled after the first group of products is queued,
+    // so the copy instructions issue in the shadow of the DMMAs instead of in front of them
+    auto refill = [&]() {
       if (cn < c_end) load_chunk(cn, (cn - c_begin) % NS);
       kb_cp_async_commit();
-    }
+    };
     const int stg = (c - c_begin) % NS;
     const double (*as)[KB_LDK] = &sm.ring[stg * SROWS];
     const double (*bs)[KB_LDK] = same ? as : &sm.ring[stg * SROWS + AROWS];
@@ -348,6 +351,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
         const double bf = bs[warp * 8 + gq][ks * 4 + tq];
         kb_dmma(acc[0][0][0], acc[0][0][1], a0, bf);
         kb_dmma(acc[1][0][0], acc[1][0][1], a1, bf);
+        if (ks == 0) refill();
       }
     } else if (MODE == 4) {
 #pragma unroll
@@ -361,6 +365,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        if (ks == 0) refill();
       }
     } else {
 #pragma unroll
@@ -384,6 +389,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
             for (int ni = 0; ni < 4; ++ni)
               if (need2 & (1u << (mi * 4 + ni))) kb_dmma(acc[2 + mi][ni][0], acc[2 + mi][ni][1], af[mi], b2[ni]);
         }
+        if (ks == 0) refill();
       }
     }
   }
@@ -408,13 +414,16 @@ __device__ __forceinline__ int kb_wait_rows(KbCholSmem& sm, const int* fa, const
   return sm.ready;
 }
 
-// wait for the chain's Dinv_k, stage it behind the C tile(s)
-__device__ __forceinline__ void kb_fetch_dinv(const KbCholArgs& P, double (*Ds)[KB_LDC], const int* flk, int b, int tkc) {
+// wait for the chain's Dinv_k and start staging it behind the C tile(s); the copy overlaps the
+// read of the tile being updated.  kb_dinv_land() completes it.
+__device__ __forceinline__ void kb_dinv_issue(const KbCholArgs& P, double (*Ds)[KB_LDC], const int* flk, int b, int tkc) {
   if (threadIdx.x == 0)
     while (kb_flag_acquire(flk) < tkc + 1) __nanosleep(64);
   __syncthreads();
   kb_load_tile_async(Ds, P.dinv + ((size_t)b * P.g.nb + tkc) * (KB_TILE * KB_TILE), KB_TILE);
   kb_cp_async_commit();
+}
+__device__ __forceinline__ void kb_dinv_land() {
   kb_cp_async_wait<0>();
   __syncthreads();
 }
@@ -425,13 +434,19 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
   const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
   const int NT = P.g.NT, ld = P.g.ld, nb = P.g.nb;
 
+  // (Claiming the next ticket early, during the current K loop, was measured 10 % SLOWER: a claimed
+  // but unstarted task delays the urgent head-of-column tasks behind a long K loop.)
   while (true) {
     __syncthreads();
-    if (tid == 0) sm.task = atomicAdd(&P.ctl[0], 1);
+    if (tid == 0) {
+      const int nx = atomicAdd(&P.ctl[0], 1);
+      sm.task = nx;
+      if (nx < P.ntasks) sm.tdesc = P.tasks[nx];
+    }
     __syncthreads();
     const int tk = sm.task;
     if (tk >= P.ntasks) break;
-    const int4 T = P.tasks[tk];
+    const int4 T = sm.tdesc;
     const int b = T.x, ti = T.y, tkc = T.z, type = T.w & 0xff, kstart = T.w >> 8;
     unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
     if (P.trace && tid == 0) tr0 = kb_globaltimer();
@@ -538,10 +553,11 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
               make_double2(c0v[mi][0], c0v[mi][1]);
       } else {
         double (*Ds)[KB_LDC] = Cs + KB_TILE;
+        kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
           *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]) = make_double2(c0v[mi][0], c0v[mi][1]);
-        kb_fetch_dinv(P, Ds, &fl[tkc], b, tkc);
+        kb_dinv_land();
         if (P.trace && tid == 0) tr3 = kb_globaltimer();
         double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
         const int kmax = 2 * (warp + 1);
@@ -558,6 +574,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
     } else if (two) {
       // 128 x 64: C = A[i..i+1, k] - acc -> shared, one triangular multiply for both tile rows
       double (*Ds)[KB_LDC] = Cs + 2 * KB_TILE;
+      kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -566,7 +583,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
           const double2 v = __ldcg(reinterpret_cast<const double2*>(&Atile[(size_t)r * ld + c]));
           *reinterpret_cast<double2*>(&Cs[r][c]) = make_double2(v.x - acc[mi][ni][0], v.y - acc[mi][ni][1]);
         }
-      kb_fetch_dinv(P, Ds, &fl[tkc], b, tkc);
+      kb_dinv_land();
       if (P.trace && tid == 0) tr3 = kb_globaltimer();
       kb_tri_multiply<4>(Cs, Ds, acc);
 #pragma unroll
@@ -597,6 +614,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
       } else {
         // L[i,k] = C * inv(L[k,k])^T : wait for the chain, then one triangular 64^3 DMMA multiply
         double (*Ds)[KB_LDC] = Cs + KB_TILE;
+        kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -604,7 +622,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
             const int r = wr * 16 + mi * 8 + gq, c = wc * 32 + ni * 8 + 2 * tq;
             *reinterpret_cast<double2*>(&Cs[r][c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
           }
-        kb_fetch_dinv(P, Ds, &fl[tkc], b, tkc);
+        kb_dinv_land();
         if (P.trace && tid == 0) tr3 = kb_globaltimer();
         kb_tri_multiply<2>(Cs, Ds, acc);
 #pragma unroll

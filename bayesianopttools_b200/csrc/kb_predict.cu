@@ -279,57 +279,67 @@ kb_predict_kernel(KbPredictArgs P) {
       // One continuous chunk stream over all row blocks: the ring keeps prefetching the next
       // block's first chunks while the current block drains and runs its (register-only) epilogue.
       auto nch_of = [&](int I) { return (((I + 1) * PK_BM > n_pad) ? n_pad : (I + 1) * PK_BM) / PK_KC; };
-      int Il = 0, cl = 0;                               // load cursor (row block, chunk)
+      // load cursor: running per-thread source pointers (one add per chunk; the chunk/row-block
+      // bookkeeping is kept off the address path so the copies issue in the shadow of the DMMAs)
+      int Il = 0, cl = 0, ncl = nch_of(0);
+      const size_t a_step = (size_t)PK_KC * P.ldat, a_j = (size_t)4 * P.ldat;
+      const double* gA0 = P.AT + (size_t)(tid >> 6) * P.ldat + (tid & 63) * 2;
+      const double* gB0 = psi + (size_t)(tid >> 5) * MT + (tid & 31) * 2;
+      const double* gA = gA0;
+      const double* gB = gB0;
+      const uint32_t sA0 = kb_smem_u32(&sa[0][tid >> 6][(tid & 63) * 2]);
+      const uint32_t sB0 = kb_smem_u32(&sb[0][tid >> 5][(tid & 31) * 2]);
       auto issue_next = [&](int stage) {
         if (Il < nblk) {
-          const double* Ablk = P.AT + (size_t)Il * PK_BM;
-          const int k0 = cl * PK_KC;
-  #pragma unroll
-          for (int j = 0; j < (PK_KC * PK_BM / 2) / NT; ++j) {
-            const int idx = tid + j * NT;
-            const int kk = idx >> 6, seg = (idx & 63) * 2;
-            kb_cp_async16(&sa[stage][kk][seg], Ablk + (size_t)(k0 + kk) * P.ldat + seg);
+          const uint32_t da = sA0 + stage * (uint32_t)(PK_KC * PK_LDA * 8), db = sB0 + stage * (uint32_t)(PK_KC * LDB * 8);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(da + j * (uint32_t)(4 * PK_LDA * 8)), "l"(gA + j * a_j));
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(db + j * (uint32_t)(8 * LDB * 8)), "l"(gB + j * (8 * MT)));
+          gA += a_step;
+          gB += PK_KC * MT;
+          if (++cl == ncl) {
+            cl = 0;
+            ++Il;
+            ncl = nch_of(Il);
+            gA = gA0 + (size_t)Il * PK_BM;
+            gB = gB0;
           }
-  #pragma unroll
-          for (int j = 0; j < (PK_KC * MT / 2) / NT; ++j) {
-            const int idx = tid + j * NT;
-            const int kk = idx / (MT / 2), seg = (idx % (MT / 2)) * 2;
-            kb_cp_async16(&sb[stage][kk][seg], psi + (size_t)(k0 + kk) * MT + seg);
-          }
-          if (++cl == nch_of(Il)) { cl = 0; ++Il; }
         }
         kb_cp_async_commit();
       };
-  #pragma unroll
-  #pragma unroll
-    for (int s = 0; s < PK_STAGES - 1; ++s) issue_next(s);
+#pragma unroll
+      for (int s = 0; s < PK_STAGES - 1; ++s) issue_next(s);
       int gi = 0;                                       // chunks consumed so far
       for (int I = 0; I < nblk; ++I) {
         const int nch = nch_of(I);
         double acc[4][4][2];
-  #pragma unroll
+#pragma unroll
         for (int mi = 0; mi < 4; ++mi)
-  #pragma unroll
+#pragma unroll
           for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         for (int c = 0; c < nch; ++c, ++gi) {
           kb_cp_async_wait<PK_STAGES - 2>();
           __syncthreads();
-          issue_next((gi + PK_STAGES - 1) % PK_STAGES);
           const int stg = gi % PK_STAGES;
-  #pragma unroll
+#pragma unroll
           for (int ks = 0; ks < PK_KC / 4; ++ks) {
             double af[4], bf[4];
-  #pragma unroll
+#pragma unroll
             for (int mi = 0; mi < 4; ++mi) af[mi] = sa[stg][ks * 4 + tq][wr * 32 + mi * 8 + gq];
-  #pragma unroll
+#pragma unroll
             for (int ni = 0; ni < 4; ++ni) bf[ni] = sb[stg][ks * 4 + tq][wc * 32 + ni * 8 + gq];
-  #pragma unroll
+#pragma unroll
             for (int mi = 0; mi < 4; ++mi)
-  #pragma unroll
+#pragma unroll
               for (int ni = 0; ni < 4; ++ni) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            // refill the stage freed by the barrier above once the first products are queued
+            if (ks == 0) issue_next((gi + PK_STAGES - 1) % PK_STAGES);
           }
         }
-        // block epilogue: squares for L^-1 rows, raw values for the extra rows
+      // block epilogue: squares for L^-1 rows, raw values for the extra rows
   #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
           const int row = I * PK_BM + wr * 32 + mi * 8 + gq;

@@ -1,1 +1,2 @@
-KB_PRED_DEBUG=3 ncu --set full --clock-control none --import-source on -k regex:kb_predict_kernel -s 1 -c 1 -o gpurun_out/prof_pred_dbg3 python tools/profile_run.py predict 2 > gpurun_out/ncu_pred_dbg3.log 2>&1; echo "rc=$?"
+timeout -k 5 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2_15.log 2>&1; echo "pytest rc=$?"
+timeout -k 5 200 python tools/quick_perf.py > gpurun_out/quick_perf_s2_15.log 2>&1; echo "perf rc=$?"
