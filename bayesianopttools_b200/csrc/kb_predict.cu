@@ -21,7 +21,7 @@
 
 #define PK_BM 128
 #define PK_KC 16
-#define PK_STAGES 4
+#define PK_STAGES 3
 #define PK_LDA 132
 #define PK_TK 16          // rows of the training set per psi-phase tile
 #define PK_QIN 8          // extra rows (alpha, R^-1 F columns) folded into the psi phase up to this many
@@ -324,6 +324,13 @@ kb_predict_kernel(KbPredictArgs P) {
           kb_cp_async_wait<PK_STAGES - 2>();
           __syncthreads();
           const int stg = gi % PK_STAGES;
+          // L^-1 is lower triangular: the 32 rows of this warp need k < 128 I + 32 (wr + 1) only, so
+          // in the diagonal range of the row block the upper warps drop out (their share of the
+          // tensor pipe goes to the co-resident CTA)
+          if (c * PK_KC >= I * PK_BM + 32 * (wr + 1)) {
+            issue_next((gi + PK_STAGES - 1) % PK_STAGES);
+            continue;
+          }
 #pragma unroll
           for (int ks = 0; ks < PK_KC / 4; ++ks) {
             double af[4], bf[4];

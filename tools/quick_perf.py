@@ -35,13 +35,15 @@ def nll_case(n, d, B, nind=1):
     mdl = _lib.DeviceModel(X, y, F, ["gaussian"])
     mdl.set_stream(torch.cuda.current_stream().cuda_stream)
     mdl.reserve_population(B)
+    mdl.set_profiling(True)
     xpop = torch.tensor(np.random.default_rng(2).uniform(-0.3, 0.7, (B, d)), device="cuda")
     nll = torch.empty(B, dtype=torch.float64, device="cuda")
     ms = time_it(lambda: mdl.nll_batch_dev(xpop.data_ptr(), B, d, False, -6.0, nll.data_ptr()))
     npad = (n + 63) // 64 * 64
     flops = B * (npad ** 3 / 3.0)
     print(f"NLL n={n} d={d} B={B} nind={nind}: {ms:.3f} ms/pop  {B / ms * 1e3:.1f} evals/s  "
-          f"chol {flops / ms / 1e9:.2f} TFLOP/s (n_pad^3/3)", flush=True)
+          f"chol {flops / ms / 1e9:.2f} TFLOP/s (n_pad^3/3)  stages(decode,build,chol,gls) ms "
+          + " ".join("%.3f" % v for v in mdl.stage_ms(0)[:4]), flush=True)
     mdl.close()
 
 
