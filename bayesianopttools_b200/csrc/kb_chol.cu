@@ -453,11 +453,12 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
     double* A = P.aug + (size_t)b * P.g.stride;
     int* fl = P.prog + (size_t)b * NT;
     const bool is_pre = (type == KB_TASK_PRE || type == KB_TASK_PRE_A);
-    const bool is_schur = (type == KB_TASK_SCHUR || type == KB_TASK_SCHUR_THIN);
-    const bool thin = (type == KB_TASK_THIN || type == KB_TASK_SCHUR_THIN);
+    const bool is_schur = (type == KB_TASK_SCHUR || type == KB_TASK_SCHUR_THIN || type == KB_TASK_SCHUR_THIN_A);
+    const bool thin = (type == KB_TASK_THIN || type == KB_TASK_SCHUR_THIN || type == KB_TASK_SCHUR_THIN_A);
     const bool two = (type == KB_TASK_OFF2);
     const int brow = is_pre ? ti - 1 : tkc;
-    const int kend = (type == KB_TASK_PRE_A) ? ti - 2 : (is_pre ? ti - 1 : (tkc < nb ? tkc : nb));
+    const int kend = (type == KB_TASK_PRE_A) ? ti - 2
+                     : (is_pre ? ti - 1 : (type == KB_TASK_SCHUR_THIN_A ? nb - 1 : (tkc < nb ? tkc : nb)));
     const double* Arow = A + (size_t)ti * KB_TILE * ld;
     const double* Brow = A + (size_t)brow * KB_TILE * ld;
     double* Atile = A + (size_t)ti * KB_TILE * ld + (size_t)(is_pre ? ti - 1 : tkc) * KB_TILE;
@@ -477,6 +478,11 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
     if (type == KB_TASK_PRE && kstart > 0) {       // the early part of this PRE task must be in
       if (tid == 0)
         while (kb_flag_acquire(&P.pre_a[(size_t)b * nb + ti]) == 0) __nanosleep(64);
+      __syncthreads();
+    }
+    if (type == KB_TASK_SCHUR_THIN && kstart > 0) {   // ... and so must the early part of the Schur sum
+      if (tid == 0)
+        while (kb_flag_acquire(&P.pre_a[(size_t)b * nb]) == 0) __nanosleep(64);
       __syncthreads();
     }
     if (kend > kstart) ready_cols = kb_wait_rows(sm, fa, fa2, fb, kstart + 1);
@@ -551,6 +557,13 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
         for (int mi = 0; mi < 2; ++mi)
           *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
               make_double2(c0v[mi][0], c0v[mi][1]);
+        if (type == KB_TASK_SCHUR_THIN_A) {
+          __syncthreads();
+          if (tid == 0) {
+            __threadfence();
+            kb_flag_release(&P.pre_a[(size_t)b * nb], 1);     // slot 0 of pre_a is free (PRE_A starts at row 3)
+          }
+        }
       } else {
         double (*Ds)[KB_LDC] = Cs + KB_TILE;
         kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
@@ -780,6 +793,8 @@ void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
       if (r < rows.size()) seg.push_back({rows[r], k, KB_TASK_OFF});
     }
     if (thin_rhs) seg.push_back({rhs0, k, KB_TASK_THIN});
+    // Schur sum over all but the last tile column, so that only two chunks are left for the tail
+    if (thin_rhs && g.nb >= 3 && k == g.nb - 2) seg.push_back({rhs0, rhs0, KB_TASK_SCHUR_THIN_A});
     // identity rows (fit mode): row j of I is zero left of tile column j
     for (int j = 0; j <= k && j < g.ib; ++j) seg.push_back({id0 + j, k, KB_TASK_OFF | (j << 8)});
     emit(seg);
@@ -792,6 +807,7 @@ void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
   }
   std::vector<T3> seg;
   for (int kk = rhs0; kk < id0; ++kk)
-    for (int i = kk; i < id0; ++i) seg.push_back({i, kk, thin_rhs ? KB_TASK_SCHUR_THIN : KB_TASK_SCHUR});
+    for (int i = kk; i < id0; ++i)
+      seg.push_back({i, kk, thin_rhs ? (KB_TASK_SCHUR_THIN | (g.nb >= 3 ? (g.nb - 1) << 8 : 0)) : KB_TASK_SCHUR});
   emit(seg);
 }
