@@ -55,6 +55,7 @@ struct kb_model {
   int n = 0, d = 0, nind = 0, nkernel = 0, model_type = 0, h = 0, kmask = 0, n_pad = 0, nb = 0;
   std::vector<int> kernel_ids;
   double *XT = nullptr, *y = nullptr, *F = nullptr, *pls = nullptr;
+  double* kpls_dtiles = nullptr;   // KPLS: theta-independent per-component squared distances, tile-major
   int* kernel_ids_dev = nullptr;
   KbPopWs pop, fit;
   // predictor state
@@ -109,7 +110,7 @@ static KbAugGeom make_geom(int n, int nind, bool fit_mode) {
 static void free_ws(KbPopWs& w) {
   cudaFree(w.aug); cudaFree(w.dinv); cudaFree(w.sync_words); cudaFree(w.tasks);
   cudaFree(w.info); cudaFree(w.hp.gw); cudaFree(w.hp.ith); cudaFree(w.hp.wk); cudaFree(w.hp.eps);
-  cudaFree(w.hp.sigma2); cudaFree(w.hp.nugget); cudaFree(w.Mbuf); cudaFree(w.beta); cudaFree(w.sigma2);
+  cudaFree(w.hp.sigma2); cudaFree(w.hp.nugget); cudaFree(w.hp.gk); cudaFree(w.Mbuf); cudaFree(w.beta); cudaFree(w.sigma2);
   cudaFree(w.nll); cudaFree(w.lndet); cudaFree(w.xpop);
   w = KbPopWs{};
 }
@@ -147,6 +148,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   CK(cudaMalloc(&w.hp.eps, sizeof(double) * B));
   CK(cudaMalloc(&w.hp.sigma2, sizeof(double) * B));
   CK(cudaMalloc(&w.hp.nugget, sizeof(double) * B));
+  CK(cudaMalloc(&w.hp.gk, sizeof(double) * B * KB_KPLS_MAX_H));
   CK(cudaMalloc(&w.Mbuf, sizeof(double) * (size_t)B * nind * nind));
   CK(cudaMalloc(&w.beta, sizeof(double) * (size_t)B * nind));
   CK(cudaMalloc(&w.sigma2, sizeof(double) * B));
@@ -186,7 +188,8 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
                       fixed_nugget, m->nkernel, m->kernel_ids_dev,
                       (m->model_type == KB_TYPE_KPLS) ? m->pls : nullptr, w.hp));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][1], m->stream));
-  CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug));
+  if (m->kpls_dtiles) CK(kb_launch_build_aug_kpls(m->stream, md, w.g, B, m->h, w.hp, m->kpls_dtiles, w.aug));
+  else CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug, 0));
   CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
   CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.sync_words, w.tasks, w.ntasks, w.info, m->num_sms));
@@ -195,7 +198,7 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
                    w.info, rt_out, w.lndet));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][4], m->stream));
   if (prof) m->pop_calls += 1;
-  g_launches += 4;
+  g_launches += m->kpls_dtiles ? 5 : 4;
   return KB_OK;
 }
 
@@ -275,6 +278,15 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
     CK(cudaMalloc(&m->pls, sizeof(double) * (size_t)d * h));
     CK(cudaMemcpy(m->pls, plscoeff, sizeof(double) * (size_t)d * h, cudaMemcpyHostToDevice));
   }
+  if (model_type == KB_TYPE_KPLS && h <= KB_KPLS_MAX_H) {
+    // kernelfunc.py:43-49: the per-component distance sums do not depend on theta -> once per design
+    const size_t ntile = (size_t)m->nb * (m->nb + 1) / 2;
+    CK(cudaMalloc(&m->kpls_dtiles, sizeof(double) * ntile * h * KB_TILE * KB_TILE));
+    KbModelDev md{m->n, m->d, m->nind, m->n_pad, m->nb, m->kmask, m->XT, m->y, m->F};
+    CK(kb_launch_kpls_dist(m->stream, md, h, m->pls, m->kpls_dtiles));
+    g_launches += 1;
+    CK(cudaStreamSynchronize(m->stream));
+  }
   CK(cudaMalloc(&m->result_dev, sizeof(KbSweepResult)));
   *out = m;
   return KB_OK;
@@ -286,7 +298,7 @@ void kb_model_destroy(kb_model* m) {
   cudaStreamSynchronize(m->stream);
   free_ws(m->pop);
   free_ws(m->fit);
-  cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kernel_ids_dev);
+  cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kpls_dtiles); cudaFree(m->kernel_ids_dev);
   cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
   cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
   cudaFree(m->result_dev); cudaFree(m->stage_x); cudaFree(m->stage_out);

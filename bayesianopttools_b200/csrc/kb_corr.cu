@@ -55,6 +55,11 @@ __global__ void kb_decode_kernel(int B, int nbhyp, const double* __restrict__ xp
       wk[kernel_ids[0]] = 1.0;
     }
     for (int j = 0; j < 4; ++j) hp.wk[b * 4 + j] = wk[j];
+    if (pls != nullptr)
+      for (int k = 0; k < nth && k < KB_KPLS_MAX_H; ++k) {
+        const double th = pow(10.0, x[k]);
+        hp.gk[b * KB_KPLS_MAX_H + k] = 0.5 / (th * th);
+      }
     hp.eps[b] = pow(10.0, nug);
     hp.nugget[b] = nug;
     hp.sigma2[b] = s2;
@@ -157,7 +162,7 @@ __device__ __forceinline__ void kb_stage_x_tiles(const double* __restrict__ XTi,
 // ---------------------------------------------------------------------------
 template <int MASK>
 __global__ void __launch_bounds__(KB_THREADS)
-kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ aug) {
+kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ aug, int t_begin) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sX = reinterpret_cast<double*>(smem_raw);            // [2][d][64]
   double* sgw = sX + 2 * m.d * KB_TILE;                        // [d]
@@ -168,7 +173,7 @@ kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ 
   const int b = blockIdx.y;
   double* A = aug + (size_t)b * g.stride;
   const int nR = g.nb * (g.nb + 1) / 2;
-  int t = blockIdx.x;
+  int t = blockIdx.x + t_begin;
   const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
 
   if (t < nR) {
@@ -267,22 +272,154 @@ static size_t kb_corr_smem(int d) {
 
 template <int MASK>
 static cudaError_t kb_build_aug_launch(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B,
-                                       KbHyper hp, double* aug) {
+                                       KbHyper hp, double* aug, int skip_r_tiles) {
   const size_t smem = kb_corr_smem(m.d);
   cudaError_t e = cudaFuncSetAttribute(kb_build_aug_kernel<MASK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int ntiles = g.nb * (g.nb + 1) / 2 + (g.sb + g.ib) * (g.nb + g.sb);
-  dim3 grid(ntiles, B);
-  kb_build_aug_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(m, g, hp, aug);
+  const int nR = g.nb * (g.nb + 1) / 2;
+  const int ntiles = nR + (g.sb + g.ib) * (g.nb + g.sb);
+  const int t_begin = skip_r_tiles ? nR : 0;
+  dim3 grid(ntiles - t_begin, B);
+  kb_build_aug_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(m, g, hp, aug, t_begin);
   return cudaGetLastError();
 }
 
 cudaError_t kb_launch_build_aug(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B,
-                                KbHyper hp, double* aug) {
+                                KbHyper hp, double* aug, int skip_r_tiles) {
   cudaError_t err = cudaSuccess;
-  KB_DISPATCH_MASK(m.kmask, err = kb_build_aug_launch<M_>(st, m, g, B, hp, aug));
+  KB_DISPATCH_MASK(m.kmask, err = kb_build_aug_launch<M_>(st, m, g, B, hp, aug, skip_r_tiles));
   return err;
+}
+
+// ---------------------------------------------------------------------------
+// KPLS fast path.  kernelfunc.py:43-49 evaluates exp(-1/2 sum_k [sum_i w_ik^2 (a_i-b_i)^2] / theta_k^2):
+// the inner sums do not depend on theta, so they are computed ONCE per design (h values per pair,
+// tile-major: dtiles[tile][k][64][64]) and a candidate's correlation tile costs h FMAs and one exp
+// per entry instead of 3 d flops.  Thread (tr, tc) owns the same 4x4 entries as kb_corr_tile.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void kb_tile_of(int t, int& ti, int& tj) {
+  ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  tj = t - ti * (ti + 1) / 2;
+}
+
+__global__ void __launch_bounds__(KB_THREADS)
+kb_kpls_dist_kernel(KbModelDev m, int h, const double* __restrict__ pls, double* __restrict__ dtiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sX = reinterpret_cast<double*>(smem_raw);            // [2][d][64]
+  double* sw2 = sX + 2 * m.d * KB_TILE;                        // [d][h] squared PLS weights
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sw2 + m.d * KB_KPLS_MAX_H);
+  int ti, tj;
+  kb_tile_of(blockIdx.x, ti, tj);
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  for (int e = threadIdx.x; e < m.d * h; e += blockDim.x) {
+    const double w = pls[e];
+    sw2[(e / h) * KB_KPLS_MAX_H + (e % h)] = w * w;
+  }
+  kb_stage_x_tiles(m.XT, m.n_pad, ti, m.XT, m.n_pad, tj, m.d, sX, bar);
+  __syncthreads();
+  const double* sXi = sX;
+  const double* sXj = sX + m.d * KB_TILE;
+  for (int k = 0; k < h; ++k) {
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    for (int dim = 0; dim < m.d; ++dim) {
+      const double w2 = sw2[dim * KB_KPLS_MAX_H + k];
+      double xi[4], xj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xi[a] = sXi[dim * KB_TILE + tr * 4 + a];
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const double2 v = *reinterpret_cast<const double2*>(&sXj[dim * KB_TILE + 2 * tc + 32 * a2]);
+        xj[2 * a2] = v.x; xj[2 * a2 + 1] = v.y;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double df = xi[a] - xj[c];
+          acc[a][c] = fma(df * df, w2, acc[a][c]);
+        }
+    }
+    double* out = dtiles + ((size_t)blockIdx.x * h + k) * (KB_TILE * KB_TILE);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2)
+        *reinterpret_cast<double2*>(&out[(tr * 4 + a) * KB_TILE + 2 * tc + 32 * a2]) =
+            make_double2(acc[a][2 * a2], acc[a][2 * a2 + 1]);
+  }
+}
+
+cudaError_t kb_launch_kpls_dist(cudaStream_t st, const KbModelDev& m, int h, const double* pls, double* dtiles) {
+  const size_t smem = (size_t)(2 * m.d * KB_TILE + m.d * KB_KPLS_MAX_H) * sizeof(double) + 16;
+  cudaError_t e = cudaFuncSetAttribute(kb_kpls_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kb_kpls_dist_kernel<<<m.nb * (m.nb + 1) / 2, KB_THREADS, smem, st>>>(m, h, pls, dtiles);
+  return cudaGetLastError();
+}
+
+#define KB_KPLS_GROUP 8    // candidates per CTA: the D tiles are read once per group
+__global__ void __launch_bounds__(KB_THREADS)
+kb_build_aug_kpls_kernel(KbModelDev m, KbAugGeom g, int B, int h, KbHyper hp, const double* __restrict__ dtiles,
+                         double* __restrict__ aug) {
+  __shared__ double sgk[KB_KPLS_GROUP][KB_KPLS_MAX_H];
+  __shared__ double seps[KB_KPLS_GROUP];
+  int ti, tj;
+  kb_tile_of(blockIdx.x, ti, tj);
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  const int b0 = blockIdx.y * KB_KPLS_GROUP;
+  const int nb_here = (B - b0 < KB_KPLS_GROUP) ? (B - b0) : KB_KPLS_GROUP;
+  if (threadIdx.x < KB_KPLS_GROUP * KB_KPLS_MAX_H) {
+    const int bb = threadIdx.x / KB_KPLS_MAX_H, k = threadIdx.x % KB_KPLS_MAX_H;
+    sgk[bb][k] = (bb < nb_here && k < h) ? hp.gk[(b0 + bb) * KB_KPLS_MAX_H + k] : 0.0;
+    if (k == 0) seps[bb] = (bb < nb_here) ? hp.eps[b0 + bb] : 0.0;
+  }
+  __syncthreads();
+  const bool inside = (ti + 1) * KB_TILE <= m.n;            // no padding row/column in this tile
+  const double* dt = dtiles + (size_t)blockIdx.x * h * (KB_TILE * KB_TILE);
+#pragma unroll 1
+  for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll 1
+    for (int a = 0; a < 4; ++a) {
+      const int r = tr * 4 + a, c = 2 * tc + 32 * a2;
+      double2 dv[KB_KPLS_MAX_H];
+#pragma unroll
+      for (int k = 0; k < KB_KPLS_MAX_H; ++k)
+        dv[k] = (k < h) ? __ldg(reinterpret_cast<const double2*>(&dt[(size_t)k * (KB_TILE * KB_TILE) + r * KB_TILE + c]))
+                        : make_double2(0.0, 0.0);
+      const int row = ti * KB_TILE + r, col = tj * KB_TILE + c;
+      for (int bb = 0; bb < nb_here; ++bb) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < KB_KPLS_MAX_H; ++k) {
+          s0 = fma(dv[k].x, sgk[bb][k], s0);
+          s1 = fma(dv[k].y, sgk[bb][k], s1);
+        }
+        double2 v = make_double2(exp(-s0), exp(-s1));
+        if (row == col) v.x += seps[bb];
+        if (row == col + 1) v.y += seps[bb];
+        if (!inside) {
+          if (row >= m.n || col >= m.n) v.x = (row == col) ? 1.0 : 0.0;
+          if (row >= m.n || col + 1 >= m.n) v.y = (row == col + 1) ? 1.0 : 0.0;
+        }
+        *reinterpret_cast<double2*>(&aug[(size_t)(b0 + bb) * g.stride + (size_t)row * g.ld + col]) = v;
+      }
+    }
+}
+
+cudaError_t kb_launch_build_aug_kpls(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B, int h,
+                                     KbHyper hp, const double* dtiles, double* aug) {
+  dim3 grid(g.nb * (g.nb + 1) / 2, (B + KB_KPLS_GROUP - 1) / KB_KPLS_GROUP);
+  kb_build_aug_kpls_kernel<<<grid, KB_THREADS, 0, st>>>(m, g, B, h, hp, dtiles, aug);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return kb_launch_build_aug(st, m, g, B, hp, aug, 1);       // right-hand-side / identity rows
 }
 
 // ---------------------------------------------------------------------------

@@ -39,7 +39,9 @@ struct KbHyper {
   double* eps;     // [B]      10^nugget
   double* sigma2;  // [B]      10^x[nth] when trainvar
   double* nugget;  // [B]      log10 nugget actually used
+  double* gk;      // [B][8]   KPLS only: 1/(2 theta_k^2) per PLS component (k < h <= 8)
 };
+#define KB_KPLS_MAX_H 8
 
 struct KbModelDev {
   int n, d, nind, n_pad, nb;
@@ -55,7 +57,13 @@ cudaError_t kb_launch_decode(cudaStream_t st, int B, int nbhyp, const double* xp
                              int nkernel, const int* kernel_ids_dev, const double* pls_dev /*d*h or null*/,
                              KbHyper hp);
 cudaError_t kb_launch_build_aug(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B,
-                                KbHyper hp, double* aug);
+                                KbHyper hp, double* aug, int skip_r_tiles);
+// KPLS fast path (kernelfunc.py:43-49): the theta-independent per-component squared distances
+// D_k[a][b] = sum_i w_ik^2 (x_ai - x_bi)^2 of every lower tile are computed once per design ...
+cudaError_t kb_launch_kpls_dist(cudaStream_t st, const KbModelDev& m, int h, const double* pls, double* dtiles);
+// ... and each candidate's correlation tiles are exp(-sum_k D_k gk_k) from them.
+cudaError_t kb_launch_build_aug_kpls(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B, int h,
+                                     KbHyper hp, const double* dtiles, double* aug);
 cudaError_t kb_launch_corr_general(cudaStream_t st, int n, int m, int d, const double* XNT, int ldn,
                                    const double* XMT, int ldm, const double* gw, const double* ith,
                                    const double* wk, int kmask, double* out, int ldo);

@@ -47,6 +47,23 @@ def nll_case(n, d, B, nind=1):
     mdl.close()
 
 
+def kpls_case(n, d, h, B):
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, (n, d))
+    y = styb(X[:, :10]) + 0.1 * np.sum((5 * X[:, 10:]) ** 2, axis=1)
+    coef = rng.normal(size=(d, h)) / np.sqrt(d)
+    mdl = _lib.DeviceModel(X, y, np.ones((n, 1)), ["gaussian"], model_type="kpls", plscoeff=coef)
+    mdl.set_stream(torch.cuda.current_stream().cuda_stream)
+    mdl.reserve_population(B)
+    mdl.set_profiling(True)
+    xpop = torch.tensor(np.random.default_rng(2).uniform(-0.3, 0.7, (B, h)), device="cuda")
+    nll = torch.empty(B, dtype=torch.float64, device="cuda")
+    ms = time_it(lambda: mdl.nll_batch_dev(xpop.data_ptr(), B, h, False, -6.0, nll.data_ptr()))
+    print(f"KPLS NLL n={n} d={d} h={h} B={B}: {ms:.3f} ms/pop  {B / ms * 1e3:.1f} evals/s  stages(decode,build,chol,gls) ms "
+          + " ".join("%.3f" % v for v in mdl.stage_ms(0)[:4]), flush=True)
+    mdl.close()
+
+
 def predict_case(n, d, m):
     rng = np.random.default_rng(4)
     X = rng.uniform(-1, 1, (n, d))
@@ -68,6 +85,9 @@ def predict_case(n, d, m):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "kpls":
+        kpls_case(2000, 100, 3, 64)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pred1000":
         predict_case(1000, 10, 1 << 20)
         sys.exit(0)
