@@ -119,7 +119,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   if (B <= w.B_cap) {
     if (w.tasks_B != B) {
       std::vector<int4> tasks;
-      kb_chol_build_tasks(w.g, B, tasks);
+      kb_chol_build_tasks(w.g, B, 2 * m->num_sms, tasks);
       CK(cudaMemcpyAsync(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, m->stream));
       CK(cudaStreamSynchronize(m->stream));
       w.ntasks = (int)tasks.size();
@@ -136,7 +136,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   CK(cudaMalloc(&w.dinv, sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE));
   CK(cudaMalloc(&w.sync_words, sizeof(int) * kb_chol_sync_words(g, B)));
   std::vector<int4> tasks;
-  kb_chol_build_tasks(g, B, tasks);
+  kb_chol_build_tasks(g, B, 2 * m->num_sms, tasks);
   CK(cudaMalloc(&w.tasks, tasks.size() * sizeof(int4)));
   CK(cudaMemcpy(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
   w.ntasks = (int)tasks.size();

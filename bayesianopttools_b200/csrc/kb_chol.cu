@@ -767,7 +767,7 @@ size_t kb_chol_sync_words(const KbAugGeom& g, int B) {
 // Bulk task queue: every dependency precedes its user.  Column k holds the tile tasks (i,k),
 // i >= k+2 (the sub-diagonal tile belongs to the chain), with the tile the chain needs next
 // (k+2,k) and the PRE task of row k+2 first.
-void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
+void kb_chol_build_tasks(const KbAugGeom& g, int B, int num_ctas, std::vector<int4>& out) {
   out.clear();
   struct T3 { int i, k, type; };
   auto emit = [&](const std::vector<T3>& seg) {
@@ -786,11 +786,13 @@ void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out) {
       if (!thin_rhs)
         for (int i = rhs0; i < id0; ++i) rows.push_back(i);
       size_t r = 0;
-      for (; r + 1 < rows.size(); r += 2) {
+      // two tile rows per task only while that still leaves every CTA a task in this column
+      const bool pair = (size_t)B * rows.size() / 2 >= (size_t)num_ctas;
+      for (; pair && r + 1 < rows.size(); r += 2) {
         if (rows[r + 1] == rows[r] + 1) seg.push_back({rows[r], k, KB_TASK_OFF2});
         else { seg.push_back({rows[r], k, KB_TASK_OFF}); seg.push_back({rows[r + 1], k, KB_TASK_OFF}); }
       }
-      if (r < rows.size()) seg.push_back({rows[r], k, KB_TASK_OFF});
+      for (; r < rows.size(); ++r) seg.push_back({rows[r], k, KB_TASK_OFF});
     }
     if (thin_rhs) seg.push_back({rhs0, k, KB_TASK_THIN});
     // Schur sum over all but the last tile column, so that only two chunks are left for the tail

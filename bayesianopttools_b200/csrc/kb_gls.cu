@@ -13,11 +13,20 @@
 #include "kb_common.cuh"
 #include "kb_internal.h"
 
+// M (nind x nind) is factored in shared memory, packed lower triangular by rows (row r holds r+1
+// contiguous entries), whenever it fits (nind <= 230 or so: 216 KB at nind = 231); otherwise in place in
+// global memory.  Population mode with many regressors takes r~'r~ from the Schur tile,
+//   r~'r~ = z_y'z_y - BE' (Z_F' z_y),
+// instead of an O(n nind) pass over the right-hand-side rows; the fit (which needs r~ itself) and
+// ordinary / low-order Kriging keep the direct residual.
+#define KB_GLS_SCHUR_RR_MIN 17
+template <bool SMEM>
 __global__ void __launch_bounds__(KB_THREADS)
 kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
               const double* __restrict__ sigma2_in, double* __restrict__ Mbuf,
               double* __restrict__ beta, double* __restrict__ sigma2_out, double* __restrict__ nll,
               int* __restrict__ info, double* __restrict__ rt_out, double* __restrict__ lndet_out) {
+  extern __shared__ __align__(16) double gsm[];
   __shared__ double red[32];
   __shared__ double s_piv;
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -26,6 +35,9 @@ kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
   const size_t rhs0 = (size_t)g.nb * KB_TILE;
   double* Mb = Mbuf + (size_t)b * nind * nind;
   double* be = beta + (size_t)b * nind;
+  double* Ms = gsm;                                   // packed lower triangle (SMEM only)
+  double* colj = gsm + (size_t)nind * (nind + 1) / 2; // current column, contiguous
+  double* bes = colj + nind;                          // right-hand side / solution
 
   // 1. ln-det from the diagonal of L
   double part = 0.0;
@@ -35,59 +47,138 @@ kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
   // 2. normal equations from the Schur tile  S = -Z^T Z
   for (int e = tid; e < nind * nind; e += blockDim.x) {
     const int a = e / nind, c = e % nind;
-    if (c <= a) Mb[e] = -A[(rhs0 + 1 + a) * ld + rhs0 + 1 + c];
+    if (c <= a) {
+      const double v = -A[(rhs0 + 1 + a) * ld + rhs0 + 1 + c];
+      if (SMEM) Ms[(size_t)a * (a + 1) / 2 + c] = v;
+      else Mb[e] = v;
+    }
   }
-  for (int a = tid; a < nind; a += blockDim.x) be[a] = -A[(rhs0 + 1 + a) * ld + rhs0];
+  for (int a = tid; a < nind; a += blockDim.x) {
+    const double v = -A[(rhs0 + 1 + a) * ld + rhs0];
+    if (SMEM) bes[a] = v;
+    else be[a] = v;
+  }
   __syncthreads();
+  const double syy = -A[rhs0 * ld + rhs0];            // z_y' z_y
+  double bb0 = 0.0;                                   // BE' b accumulates below (SMEM path)
 
-  // 3. Cholesky of M (nind x nind, lower, in place; nind is 1 for ordinary Kriging)
-  for (int j = 0; j < nind; ++j) {
-    __syncthreads();
-    if (tid == 0) {
-      double dj = Mb[(size_t)j * nind + j];
-      if (!(dj > 0.0)) {
-        atomicCAS(&info[b], 0, g.n_pad + j + 1);
-        dj = 1.0;
+  if (SMEM) {
+    // 3s. right-looking Cholesky on the packed triangle: per column one pivot, the scaled column
+    //     copied to a contiguous vector, then row-wise rank-1 updates (contiguous in both operands)
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int j = 0; j < nind; ++j) {
+      if (tid == 0) {
+        double dj = Ms[(size_t)j * (j + 1) / 2 + j];
+        if (!(dj > 0.0)) {
+          atomicCAS(&info[b], 0, g.n_pad + j + 1);
+          dj = 1.0;
+        }
+        s_piv = sqrt(dj);
+        Ms[(size_t)j * (j + 1) / 2 + j] = s_piv;
       }
-      s_piv = sqrt(dj);
-      Mb[(size_t)j * nind + j] = s_piv;
+      __syncthreads();
+      const double inv = 1.0 / s_piv;
+      for (int r = j + 1 + tid; r < nind; r += blockDim.x) {
+        const double v = Ms[(size_t)r * (r + 1) / 2 + j] * inv;
+        Ms[(size_t)r * (r + 1) / 2 + j] = v;
+        colj[r] = v;
+      }
+      __syncthreads();
+      for (int r = j + 1 + warp; r < nind; r += nw) {
+        double* row = Ms + (size_t)r * (r + 1) / 2;
+        const double lr = colj[r];
+        for (int c = j + 1 + lane; c <= r; c += 32) row[c] = fma(-lr, colj[c], row[c]);
+      }
+      __syncthreads();
+    }
+    // 4s. BE = M^-1 b: forward (row oriented, one warp-reduced dot per row) and backward substitution
+    for (int a = tid; a < nind; a += blockDim.x) colj[a] = bes[a];   // keep b for BE' b
+    __syncthreads();
+    if (tid < 32) {
+      for (int j = 0; j < nind; ++j) {
+        const double* row = Ms + (size_t)j * (j + 1) / 2;
+        double s = 0.0;
+        for (int c = lane; c < j; c += 32) s = fma(row[c], bes[c], s);
+        s = kb_warp_sum(s);
+        if (lane == 0) bes[j] = (bes[j] - s) / row[j];
+        __syncwarp();
+      }
+      for (int j = nind - 1; j >= 0; --j) {
+        const double xj = bes[j] / Ms[(size_t)j * (j + 1) / 2 + j];
+        __syncwarp();
+        if (lane == 0) bes[j] = xj;
+        for (int r = lane; r < j; r += 32) bes[r] = fma(-Ms[(size_t)j * (j + 1) / 2 + r], xj, bes[r]);
+        __syncwarp();
+      }
     }
     __syncthreads();
-    const double inv = 1.0 / s_piv;
-    for (int r = j + 1 + tid; r < nind; r += blockDim.x) Mb[(size_t)r * nind + j] *= inv;
-    __syncthreads();
-    const int rem = nind - 1 - j;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      const int r = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= r) Mb[(size_t)r * nind + c] -= Mb[(size_t)r * nind + j] * Mb[(size_t)c * nind + j];
+    double p2 = 0.0;
+    for (int a = tid; a < nind; a += blockDim.x) {
+      be[a] = bes[a];
+      p2 = fma(bes[a], colj[a], p2);
     }
+    bb0 = kb_block_sum(p2, red);
+    // the factor goes back to global memory (the predictor needs LM)
+    for (int e = tid; e < nind * nind; e += blockDim.x) {
+      const int a = e / nind, c = e % nind;
+      if (c <= a) Mb[e] = Ms[(size_t)a * (a + 1) / 2 + c];
+    }
+    __syncthreads();
+  } else {
+    // 3. Cholesky of M (nind x nind, lower, in place; nind is 1 for ordinary Kriging)
+    for (int j = 0; j < nind; ++j) {
+      __syncthreads();
+      if (tid == 0) {
+        double dj = Mb[(size_t)j * nind + j];
+        if (!(dj > 0.0)) {
+          atomicCAS(&info[b], 0, g.n_pad + j + 1);
+          dj = 1.0;
+        }
+        s_piv = sqrt(dj);
+        Mb[(size_t)j * nind + j] = s_piv;
+      }
+      __syncthreads();
+      const double inv = 1.0 / s_piv;
+      for (int r = j + 1 + tid; r < nind; r += blockDim.x) Mb[(size_t)r * nind + j] *= inv;
+      __syncthreads();
+      const int rem = nind - 1 - j;
+      for (int e = tid; e < rem * rem; e += blockDim.x) {
+        const int r = j + 1 + e / rem, c = j + 1 + e % rem;
+        if (c <= r) Mb[(size_t)r * nind + c] -= Mb[(size_t)r * nind + j] * Mb[(size_t)c * nind + j];
+      }
+    }
+    // 4. BE = M^-1 b : forward then backward substitution, column oriented
+    for (int j = 0; j < nind; ++j) {
+      __syncthreads();
+      const double xj = be[j] / Mb[(size_t)j * nind + j];
+      __syncthreads();
+      if (tid == 0) be[j] = xj;
+      for (int r = j + 1 + tid; r < nind; r += blockDim.x) be[r] -= Mb[(size_t)r * nind + j] * xj;
+    }
+    for (int j = nind - 1; j >= 0; --j) {
+      __syncthreads();
+      const double xj = be[j] / Mb[(size_t)j * nind + j];
+      __syncthreads();
+      if (tid == 0) be[j] = xj;
+      for (int r = tid; r < j; r += blockDim.x) be[r] -= Mb[(size_t)j * nind + r] * xj;
+    }
+    __syncthreads();
   }
-  // 4. BE = M^-1 b : forward then backward substitution, column oriented
-  for (int j = 0; j < nind; ++j) {
-    __syncthreads();
-    const double xj = be[j] / Mb[(size_t)j * nind + j];
-    __syncthreads();
-    if (tid == 0) be[j] = xj;
-    for (int r = j + 1 + tid; r < nind; r += blockDim.x) be[r] -= Mb[(size_t)r * nind + j] * xj;
-  }
-  for (int j = nind - 1; j >= 0; --j) {
-    __syncthreads();
-    const double xj = be[j] / Mb[(size_t)j * nind + j];
-    __syncthreads();
-    if (tid == 0) be[j] = xj;
-    for (int r = tid; r < j; r += blockDim.x) be[r] -= Mb[(size_t)j * nind + r] * xj;
-  }
-  __syncthreads();
 
   // 5. r~ = z_y - Z_F BE ;  rr = r~' r~
-  double rr = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) {
-    double z = A[rhs0 * ld + i];
-    for (int a = 0; a < nind; ++a) z = fma(-be[a], A[(rhs0 + 1 + a) * ld + i], z);
-    rr = fma(z, z, rr);
-    if (rt_out) rt_out[i] = z;
+  double rr;
+  if (SMEM && rt_out == nullptr && nind >= KB_GLS_SCHUR_RR_MIN) {
+    rr = syy - bb0;
+  } else {
+    rr = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+      double z = A[rhs0 * ld + i];
+      for (int a = 0; a < nind; ++a) z = fma(-be[a], A[(rhs0 + 1 + a) * ld + i], z);
+      rr = fma(z, z, rr);
+      if (rt_out) rt_out[i] = z;
+    }
+    rr = kb_block_sum(rr, red);
   }
-  rr = kb_block_sum(rr, red);
 
   // 6. NLL
   if (tid == 0) {
@@ -112,8 +203,16 @@ kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
 cudaError_t kb_launch_gls(cudaStream_t st, const KbAugGeom& g, int B, const double* aug, int trainvar,
                           const double* sigma2_in, double* Mbuf, double* beta, double* sigma2_out,
                           double* nll, int* info, double* rt_out, double* lndet_out) {
-  kb_gls_kernel<<<B, KB_THREADS, 0, st>>>(g, aug, trainvar, sigma2_in, Mbuf, beta, sigma2_out, nll, info,
-                                          rt_out, lndet_out);
+  const size_t smem = sizeof(double) * ((size_t)g.nind * (g.nind + 1) / 2 + 2 * (size_t)g.nind + 2);
+  if (g.nind > 1 && smem <= 220 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kb_gls_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kb_gls_kernel<true><<<B, KB_THREADS, smem, st>>>(g, aug, trainvar, sigma2_in, Mbuf, beta, sigma2_out, nll, info,
+                                                     rt_out, lndet_out);
+  } else {
+    kb_gls_kernel<false><<<B, KB_THREADS, 0, st>>>(g, aug, trainvar, sigma2_in, Mbuf, beta, sigma2_out, nll, info,
+                                                   rt_out, lndet_out);
+  }
   return cudaGetLastError();
 }
 

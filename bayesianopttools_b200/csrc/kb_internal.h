@@ -75,7 +75,7 @@ cudaError_t kb_launch_transpose_pad(cudaStream_t st, const double* X, int n, int
 #ifdef __cplusplus
 #include <vector>
 size_t kb_chol_sync_words(const KbAugGeom& g, int B);
-void kb_chol_build_tasks(const KbAugGeom& g, int B, std::vector<int4>& out);
+void kb_chol_build_tasks(const KbAugGeom& g, int B, int num_ctas, std::vector<int4>& out);
 #endif
 cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* aug, double* dinv,
                            int* sync_words, const int4* tasks, int ntasks, int* info, int num_sms);

@@ -1,2 +1,2 @@
-timeout -k 5 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2_18.log 2>&1; echo "pytest rc=$?"
-timeout -k 5 200 python tools/quick_perf.py kpls > gpurun_out/quick_perf_kpls2.log 2>&1; echo "perf rc=$?"
+timeout -k 5 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2_19.log 2>&1; echo "pytest rc=$?"
+timeout -k 5 200 python tools/quick_perf.py > gpurun_out/quick_perf_s2_20.log 2>&1; echo "perf rc=$?"
