@@ -162,8 +162,7 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
       }
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
-      kb_flag_release(&fl[k], k);
+      kb_flag_release(&fl[k], k);      // st.release.gpu: cumulative over the CTA barrier above
       if (stamps) stamps[2] = kb_globaltimer();
     }
     // C2 -= L L^T on the lower 8x8 blocks (each thread owns its accumulator positions)
@@ -218,10 +217,7 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
     *reinterpret_cast<double2*>(&Dg[r * KB_TILE + c]) = *reinterpret_cast<double2*>(&Dk[r][c]);
   }
   __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    kb_flag_release(&fl[k], k + 1);
-  }
+  if (tid == 0) kb_flag_release(&fl[k], k + 1);
 }
 
 __device__ __forceinline__ void kb_chain_worker(const KbCholArgs& P, KbCholSmem& sm, int wid, int nworkers) {
@@ -436,13 +432,12 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
 
   // (Claiming the next ticket early, during the current K loop, was measured 10 % SLOWER: a claimed
   // but unstarted task delays the urgent head-of-column tasks behind a long K loop.)
+  if (tid == 32) {
+    const int nx = atomicAdd(&P.ctl[0], 1);
+    sm.task = nx;
+    if (nx < P.ntasks) sm.tdesc = P.tasks[nx];
+  }
   while (true) {
-    __syncthreads();
-    if (tid == 0) {
-      const int nx = atomicAdd(&P.ctl[0], 1);
-      sm.task = nx;
-      if (nx < P.ntasks) sm.tdesc = P.tasks[nx];
-    }
     __syncthreads();
     const int tk = sm.task;
     if (tk >= P.ntasks) break;
@@ -538,11 +533,6 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
           if (need2 & (1u << (mi * 4 + ni)))
             *reinterpret_cast<double2*>(&T2[(size_t)r * ld + c]) = make_double2(acc[2 + mi][ni][0], acc[2 + mi][ni][1]);
         }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        kb_flag_release(type == KB_TASK_PRE_A ? &P.pre_a[(size_t)b * nb + ti] : &P.pre[(size_t)b * nb + ti], 1);
-      }
     } else if (thin) {
       // 16 x 64 strip; warp w owns column block w
       double c0v[2][2];
@@ -557,13 +547,6 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
         for (int mi = 0; mi < 2; ++mi)
           *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
               make_double2(c0v[mi][0], c0v[mi][1]);
-        if (type == KB_TASK_SCHUR_THIN_A) {
-          __syncthreads();
-          if (tid == 0) {
-            __threadfence();
-            kb_flag_release(&P.pre_a[(size_t)b * nb], 1);     // slot 0 of pre_a is free (PRE_A starts at row 3)
-          }
-        }
       } else {
         double (*Ds)[KB_LDC] = Cs + KB_TILE;
         kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
@@ -647,14 +630,22 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
           }
       }
     }
-    // ---- publish the tile(s) ------------------------------------------------
-    if (!is_pre && !is_schur) {
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
+    // ---- publish (st.release.gpu is cumulative over the CTA barrier) and, in parallel on another
+    //      warp, claim the next ticket --------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+      if (type == KB_TASK_PRE) kb_flag_release(&P.pre[(size_t)b * nb + ti], 1);
+      else if (type == KB_TASK_PRE_A) kb_flag_release(&P.pre_a[(size_t)b * nb + ti], 1);
+      else if (type == KB_TASK_SCHUR_THIN_A) kb_flag_release(&P.pre_a[(size_t)b * nb], 1);   // slot 0 is free
+      else if (!is_schur) {
         kb_flag_release(&fl[ti], tkc + 1);
         if (two) kb_flag_release(&fl[ti + 1], tkc + 1);
       }
+    }
+    if (tid == 32) {
+      const int nx = atomicAdd(&P.ctl[0], 1);
+      sm.task = nx;
+      if (nx < P.ntasks) sm.tdesc = P.tasks[nx];
     }
     if (P.trace && tid == 0) {
       unsigned smid;
