@@ -77,10 +77,14 @@ struct kb_model {
   int pred_grid = 0;
   int pred_resident = 0;
   // host-API staging
-  double* stage_x = nullptr;
-  double* stage_out = nullptr;
+  double* stage_x[2] = {nullptr, nullptr};
+  double* stage_out[2] = {nullptr, nullptr};
   long long stage_pts = 0;
   int stage_nout = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {}, ev_swept[2] = {};
+  KbSweepResult* results_dev = nullptr;   // one reduction record per chunk of a host sweep
+  long long results_cap = 0;
   // optional per-stage timing (bench roofline): decode|build|chol|gls boundaries, predict
   int profile = 0;
   cudaEvent_t ev[KB_PROF_RING][5] = {};
@@ -301,7 +305,13 @@ void kb_model_destroy(kb_model* m) {
   cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kpls_dtiles); cudaFree(m->kernel_ids_dev);
   cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
   cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
-  cudaFree(m->result_dev); cudaFree(m->stage_x); cudaFree(m->stage_out);
+  cudaFree(m->result_dev); cudaFree(m->results_dev);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(m->stage_x[i]); cudaFree(m->stage_out[i]);
+    if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+    if (m->ev_swept[i]) cudaEventDestroy(m->ev_swept[i]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   cudaStreamDestroy(m->own_stream);
   delete m;
 }
@@ -561,6 +571,10 @@ static void merge_result(KbSweepResult& r, const KbSweepResult& q, bool first) {
   r.n_points += q.n_points;
 }
 
+// Host-buffer sweep: 2^20-site chunks through two staging buffers; the host->device copy of chunk
+// i+1 runs on a second stream while chunk i is swept, per-chunk reductions stay on the device and
+// come back in one copy at the end.  (With pageable host memory the CUDA runtime stages the copies
+// itself and the overlap shrinks; pinned buffers give the full overlap.)
 kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_params* ap,
                      double* const* outs, int acq, KbSweepResult* result) {
   if (!m || !x || npts < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
@@ -569,36 +583,62 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
   int slot[KB_OUT_COUNT];
   for (int k = 0; k < KB_OUT_COUNT; ++k) slot[k] = (outs && outs[k]) ? nout++ : -1;
   const long long chunk = npts < (1LL << 20) ? npts : (1LL << 20);
+  const long long nchunks = (npts + chunk - 1) / chunk;
+  if (!m->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&m->ev_swept[i], cudaEventDisableTiming));
+    }
+  }
   if (chunk > m->stage_pts || nout > m->stage_nout) {
     CK(cudaStreamSynchronize(m->stream));
-    cudaFree(m->stage_x); cudaFree(m->stage_out);
-    m->stage_x = m->stage_out = nullptr;
+    CK(cudaStreamSynchronize(m->copy_stream));
     const long long cp = chunk > m->stage_pts ? chunk : m->stage_pts;
     const int no = nout > m->stage_nout ? nout : m->stage_nout;
-    CK(cudaMalloc(&m->stage_x, sizeof(double) * (size_t)cp * m->d));
-    if (no > 0) CK(cudaMalloc(&m->stage_out, sizeof(double) * (size_t)cp * no));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(m->stage_x[i]); cudaFree(m->stage_out[i]);
+      m->stage_x[i] = m->stage_out[i] = nullptr;
+      CK(cudaMalloc(&m->stage_x[i], sizeof(double) * (size_t)cp * m->d));
+      if (no > 0) CK(cudaMalloc(&m->stage_out[i], sizeof(double) * (size_t)cp * no));
+    }
     m->stage_pts = cp; m->stage_nout = no;
   }
-  KbSweepResult total{};
-  bool first = true;
-  for (long long off = 0; off < npts; off += chunk) {
+  if (nchunks > m->results_cap) {
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(m->results_dev);
+    m->results_dev = nullptr;
+    CK(cudaMalloc(&m->results_dev, sizeof(KbSweepResult) * (size_t)nchunks));
+    m->results_cap = nchunks;
+  }
+  // the caller's stream may still be using the staging buffers of a previous call
+  CK(cudaEventRecord(m->ev_swept[0], m->stream));
+  CK(cudaEventRecord(m->ev_swept[1], m->stream));
+  for (long long i = 0; i < nchunks; ++i) {
+    const int buf = (int)(i & 1);
+    const long long off = i * chunk;
     const long long cur = (npts - off < chunk) ? (npts - off) : chunk;
-    CK(cudaMemcpyAsync(m->stage_x, x + (size_t)off * m->d, sizeof(double) * (size_t)cur * m->d,
-                       cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamWaitEvent(m->copy_stream, m->ev_swept[buf], 0));
+    CK(cudaMemcpyAsync(m->stage_x[buf], x + (size_t)off * m->d, sizeof(double) * (size_t)cur * m->d,
+                       cudaMemcpyHostToDevice, m->copy_stream));
+    CK(cudaEventRecord(m->ev_h2d[buf], m->copy_stream));
+    CK(cudaStreamWaitEvent(m->stream, m->ev_h2d[buf], 0));
     double* od[KB_OUT_COUNT];
     for (int k = 0; k < KB_OUT_COUNT; ++k)
-      od[k] = (slot[k] >= 0) ? m->stage_out + (size_t)slot[k] * m->stage_pts : nullptr;
-    kb_status s = kb_predict_dev(m, cur, m->stage_x, off, ap, od, acq, m->result_dev);
+      od[k] = (slot[k] >= 0) ? m->stage_out[buf] + (size_t)slot[k] * m->stage_pts : nullptr;
+    kb_status s = kb_predict_dev(m, cur, m->stage_x[buf], off, ap, od, acq, m->results_dev + i);
     if (s != KB_OK) return s;
+    CK(cudaEventRecord(m->ev_swept[buf], m->stream));
     for (int k = 0; k < KB_OUT_COUNT; ++k)
       if (slot[k] >= 0)
         CK(cudaMemcpyAsync(outs[k] + off, od[k], sizeof(double) * (size_t)cur, cudaMemcpyDeviceToHost, m->stream));
-    KbSweepResult part;
-    CK(cudaMemcpyAsync(&part, m->result_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-    merge_result(total, part, first);
-    first = false;
   }
+  std::vector<KbSweepResult> parts((size_t)nchunks);
+  CK(cudaMemcpyAsync(parts.data(), m->results_dev, sizeof(KbSweepResult) * (size_t)nchunks, cudaMemcpyDeviceToHost,
+                     m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  KbSweepResult total{};
+  for (long long i = 0; i < nchunks; ++i) merge_result(total, parts[(size_t)i], i == 0);
   if (result) *result = total;
   return KB_OK;
 }
