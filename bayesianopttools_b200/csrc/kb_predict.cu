@@ -45,7 +45,7 @@ size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx) {
     big = sizeof(double) * ((size_t)n_pad * (n_pad + 4) + (size_t)n_pad * (mt + 4) + 4 * (size_t)(qx < PK_QIN ? qx : PK_QIN) * mt);
   else
     big = sizeof(double) * PK_STAGES * PK_KC * (PK_LDA + mt + 4);
-  return sizeof(KbPredSmem) + ((size_t)d * (mt + 2) + 2 * (size_t)d * PK_TK + 2 * PK_TK * PK_QIN) * sizeof(double) + big;
+  return sizeof(KbPredSmem) + ((size_t)d * (mt + 2) + 2 * (size_t)d * PK_TK + 2 * PK_TK * PK_QIN + 2 * mt * (size_t)d) * sizeof(double) + big;
 }
 
 // The resident variant needs the whole inverse factor in shared memory.
@@ -94,7 +94,8 @@ kb_predict_kernel(KbPredictArgs P) {
   double* sith = sgw + P.d;
   double* xtile = sith + P.d;                                             // [2][d][16] training-site tiles
   double* etile = xtile + 2 * P.d * PK_TK;                                // [2][16][PK_QIN] extra columns
-  double* big = etile + 2 * PK_TK * PK_QIN;
+  double* xraw = etile + 2 * PK_TK * PK_QIN;                                // [2][64 d] raw sites, prefetched
+  double* big = xraw + 2 * MT * P.d;
   double (*sa)[PK_KC][PK_LDA] = reinterpret_cast<double (*)[PK_KC][PK_LDA]>(big);
   double (*sb)[PK_KC][LDB] = reinterpret_cast<double (*)[PK_KC][LDB]>(big + PK_STAGES * PK_KC * PK_LDA);
   const int lda_r = P.n_pad + 4;
@@ -130,16 +131,32 @@ kb_predict_kernel(KbPredictArgs P) {
   run.c0 = run.c1 = run.c2 = 0;
 
   const long long nstrips = (P.m + MT - 1) / MT;
-  for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+  // raw sites of the NEXT strip are prefetched (cp.async, two buffers) while this one is processed
+  const bool x_aligned = ((reinterpret_cast<uintptr_t>(P.x) & 15) == 0);
+  auto prefetch_x = [&](long long strip, int buf) {
+    if (x_aligned && strip < nstrips && (strip + 1) * MT <= P.m) {
+      const double* src = P.x + (size_t)strip * MT * d;
+      double* dst = xraw + (size_t)buf * MT * d;
+      for (int e = tid; e < MT * d / 2; e += NT) kb_cp_async16(dst + 2 * e, src + 2 * e);
+    }
+    kb_cp_async_commit();
+  };
+  prefetch_x(blockIdx.x, 0);
+  int xbuf = 0;
+  for (long long strip = blockIdx.x; strip < nstrips; strip += gridDim.x, xbuf ^= 1) {
     const long long p0 = strip * MT;
     const int npt = (int)((P.m - p0 < MT) ? (P.m - p0) : MT);
+    kb_cp_async_wait<0>();
     __syncthreads();
-    // ---- A1. load + standardise the strip -------------------------------
+    prefetch_x(strip + gridDim.x, xbuf ^ 1);
+    // ---- A1. standardise the strip ---------------------------------------
+    const bool staged = x_aligned && npt == MT;
+    const double* xr = xraw + (size_t)xbuf * MT * d;
     for (int e = tid; e < MT * d; e += blockDim.x) {
       const int p = e / d, dim = e - p * d;
       double v = 0.0;
       if (p < npt) {
-        v = P.x[(size_t)(p0 + p) * d + dim];
+        v = staged ? xr[e] : P.x[(size_t)(p0 + p) * d + dim];
         if (P.norm_type == KB_NORM_DEFAULT) {
           const double lo = P.p0[dim], hi = P.p1[dim];
           v = ((v - lo) / (hi - lo) - 0.5) * 2.0;

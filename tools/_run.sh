@@ -1,2 +1,2 @@
-timeout -k 5 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2_20.log 2>&1; echo "pytest rc=$?"
-python bench.py --steps 5 > gpurun_out/bench_s2_4.json 2> gpurun_out/bench_s2_4.err; echo "bench rc=$?"
+timeout -k 5 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2_21.log 2>&1; echo "pytest rc=$?"
+timeout -k 5 200 python tools/quick_perf.py > gpurun_out/quick_perf_s2_22.log 2>&1; echo "perf rc=$?"

@@ -85,6 +85,9 @@ def predict_case(n, d, m):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nll2000":
+        nll_case(2000, 10, 64)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "kpls":
         kpls_case(2000, 100, 3, 64)
         sys.exit(0)
