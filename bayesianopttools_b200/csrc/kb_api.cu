@@ -510,12 +510,15 @@ kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const 
 
 static kb_status ensure_predict_scratch(kb_model* m) {
   const int qx = 1 + m->nind;
-  const int resident = kb_predict_can_reside(m->d, m->n_pad, qx, m->idx_dev ? 1 : 0) ? 1 : 0;
+  const int resident = kb_predict_can_warp(m->d, m->n, qx, m->idx_dev ? 1 : 0)
+                           ? 2
+                           : (kb_predict_can_reside(m->d, m->n_pad, qx, m->idx_dev ? 1 : 0) ? 1 : 0);
   if (m->ex_scratch && resident == m->pred_resident) return KB_OK;
   cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
   m->psi_scratch = m->ex_scratch = nullptr; m->partials = nullptr;
   m->pred_resident = resident;
-  m->pred_grid = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx);
+  m->pred_grid = (resident == 2) ? kb_predict_warp_ctas_per_sm(m->d, m->n, qx) * m->num_sms
+                                 : kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx);
   if (m->pred_grid < 1) KB_FAIL(KB_ERR_CUDA, "predict kernel does not fit on this device (d=%d)", m->d);
   const size_t strip = kb_predict_strip(resident != 0);
   if (!resident) CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip));
@@ -549,7 +552,7 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   for (int k = 0; k < KB_OUT_COUNT; ++k) a.out[k] = outs_dev ? outs_dev[k] : nullptr;
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
   a.resident = m->pred_resident;
-  const long long strip = kb_predict_strip(m->pred_resident != 0);
+  const long long strip = (m->pred_resident == 2) ? 256 : kb_predict_strip(m->pred_resident != 0);
   const long long nstrips = (npts + strip - 1) / strip;
   const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);
   if (m->profile) CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][0], m->stream));

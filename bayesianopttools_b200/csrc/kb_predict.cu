@@ -72,6 +72,84 @@ struct KbRunning {
   long long c0, c1, c2;
 };
 
+// Per-site outputs from the four sufficient statistics (prediction.py:209-285, akmcs.py:208-238):
+//   fpc = p(x)' BE,  psia = psi' R^-1 (y - F BE),  vv = psi' R^-1 psi,  t2 = u' (F'R^-1F)^-1 u.
+// erf / exp are evaluated only when an output or the arg-min needs them.
+__device__ __forceinline__ void kb_acq_site(const KbPredictArgs& P, double fpc, double psia, double vv, double t2,
+                                            long long gi, KbRunning& run) {
+  const double f = fpc + psia;
+  const double ssqr = P.sigma2 * ((1.0 - vv) + t2);
+  const double s = sqrt(fabs(ssqr));
+  const bool want_ei = P.out[KB_OUT_EI] || P.out[KB_OUT_POI] || P.acq == KB_OUT_EI || P.acq == KB_OUT_POI;
+  const bool want_pof = P.out[KB_OUT_POF] || P.acq == KB_OUT_POF;
+  double ei = 0.0, poi = 0.0, pof = 0.0;
+  if (want_ei) {
+    const double diff = P.ybest - f;
+    const double z = diff / s;
+    const double cdf = 0.5 + 0.5 * erf(0.7071067811865475 * z);
+    ei = -(diff * cdf + s / 2.5066282746310002 * exp(-0.5 * (diff * diff) / ssqr) + DBL_MIN);
+    poi = -cdf;
+  }
+  if (want_pof) pof = 0.5 + 0.5 * erf(0.7071067811865475 * ((double)P.limit_sign * (f - P.limit) / s));
+  const double lcb = f - P.sigmalcb * ssqr;
+  const double U = fabs(f) / s;
+  double vals[KB_OUT_COUNT];
+  vals[KB_OUT_PRED] = f; vals[KB_OUT_SSQR] = ssqr; vals[KB_OUT_S] = s; vals[KB_OUT_EI] = ei;
+  vals[KB_OUT_POI] = poi; vals[KB_OUT_POF] = pof; vals[KB_OUT_LCB] = lcb; vals[KB_OUT_EBE] = -ssqr;
+  vals[KB_OUT_U] = U; vals[KB_OUT_FPC] = fpc;
+#pragma unroll
+  for (int k = 0; k < KB_OUT_COUNT; ++k)
+    if (P.out[k]) P.out[k][gi] = vals[k];
+  double av = vals[KB_OUT_PRED];
+#pragma unroll
+  for (int k = 0; k < KB_OUT_COUNT; ++k)
+    if (P.acq == k) av = vals[k];
+  const long long ggi = gi + P.idx_offset;
+  if (av < run.best_val) { run.best_val = av; run.best_idx = ggi; }
+  if (U < run.min_u) { run.min_u = U; run.min_u_idx = ggi; }
+  run.c0 += (f <= 0.0);
+  run.c1 += (f - 1.96 * s <= 0.0);
+  run.c2 += (f + 1.96 * s <= 0.0);
+}
+
+__device__ __forceinline__ void kb_run_init(KbRunning& run) {
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  run.best_val = INF; run.min_u = INF;
+  run.best_idx = 0x7fffffffffffffffLL; run.min_u_idx = 0x7fffffffffffffffLL;
+  run.c0 = run.c1 = run.c2 = 0;
+}
+
+// warp-level reduction of the running (min, lowest index) pairs and counters; lane 0 holds the result
+__device__ __forceinline__ KbSweepResult kb_run_warp_reduce(KbRunning run) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, run.best_val, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, run.best_idx, o);
+    if (ov < run.best_val || (ov == run.best_val && oi < run.best_idx)) { run.best_val = ov; run.best_idx = oi; }
+    const double uv = __shfl_xor_sync(0xffffffffu, run.min_u, o);
+    const long long ui = __shfl_xor_sync(0xffffffffu, run.min_u_idx, o);
+    if (uv < run.min_u || (uv == run.min_u && ui < run.min_u_idx)) { run.min_u = uv; run.min_u_idx = ui; }
+    run.c0 += __shfl_xor_sync(0xffffffffu, run.c0, o);
+    run.c1 += __shfl_xor_sync(0xffffffffu, run.c1, o);
+    run.c2 += __shfl_xor_sync(0xffffffffu, run.c2, o);
+  }
+  KbSweepResult r;
+  r.best_val = run.best_val; r.best_idx = run.best_idx;
+  r.min_u = run.min_u; r.min_u_idx = run.min_u_idx;
+  r.n_fail = run.c0; r.n_fail_minus = run.c1; r.n_fail_plus = run.c2; r.n_points = 0;
+  return r;
+}
+
+__device__ __forceinline__ void kb_result_merge(KbSweepResult& r, const KbSweepResult& q) {
+  if (q.best_val < r.best_val || (q.best_val == r.best_val && q.best_idx < r.best_idx)) {
+    r.best_val = q.best_val; r.best_idx = q.best_idx;
+  }
+  if (q.min_u < r.min_u || (q.min_u == r.min_u && q.min_u_idx < r.min_u_idx)) {
+    r.min_u = q.min_u; r.min_u_idx = q.min_u_idx;
+  }
+  r.n_fail += q.n_fail; r.n_fail_minus += q.n_fail_minus; r.n_fail_plus += q.n_fail_plus;
+}
+
 // RESIDENT = false: any n; psi strips live in an L2-resident scratch slab and stream back through a
 //   cp.async ring together with the fit state.
 // RESIDENT = true : n_pad <= 128 (AK-MCS / early SOBO models): the inverse factor stays in shared
@@ -429,35 +507,7 @@ kb_predict_kernel(KbPredictArgs P) {
           t2 = fma(u, u, t2);
         }
       }
-      const double f = fpc + ex[p];
-      const double ssqr = P.sigma2 * ((1.0 - vv) + t2);
-      const double s = sqrt(fabs(ssqr));
-      const double diff = P.ybest - f;
-      const double z = diff / s;
-      const double cdf = 0.5 + 0.5 * erf(0.7071067811865475 * z);
-      const double ei = -(diff * cdf + s / 2.5066282746310002 * exp(-0.5 * (diff * diff) / ssqr) + DBL_MIN);
-      const double poi = -cdf;
-      const double pof = 0.5 + 0.5 * erf(0.7071067811865475 * ((double)P.limit_sign * (f - P.limit) / s));
-      const double lcb = f - P.sigmalcb * ssqr;
-      const double U = fabs(f) / s;
-      const long long gi = p0 + p;
-      double vals[KB_OUT_COUNT];
-      vals[KB_OUT_PRED] = f; vals[KB_OUT_SSQR] = ssqr; vals[KB_OUT_S] = s; vals[KB_OUT_EI] = ei;
-      vals[KB_OUT_POI] = poi; vals[KB_OUT_POF] = pof; vals[KB_OUT_LCB] = lcb; vals[KB_OUT_EBE] = -ssqr;
-      vals[KB_OUT_U] = U; vals[KB_OUT_FPC] = fpc;
-#pragma unroll
-      for (int k = 0; k < KB_OUT_COUNT; ++k)
-        if (P.out[k]) P.out[k][gi] = vals[k];
-      double av = vals[KB_OUT_PRED];
-#pragma unroll
-      for (int k = 0; k < KB_OUT_COUNT; ++k)
-        if (P.acq == k) av = vals[k];
-      const long long ggi = gi + P.idx_offset;
-      if (av < run.best_val) { run.best_val = av; run.best_idx = ggi; }
-      if (U < run.min_u) { run.min_u = U; run.min_u_idx = ggi; }
-      run.c0 += (f <= 0.0);
-      run.c1 += (f - 1.96 * s <= 0.0);
-      run.c2 += (f + 1.96 * s <= 0.0);
+      kb_acq_site(P, fpc, ex[p], vv, t2, p0 + p, run);
     }
   }
 
@@ -501,6 +551,156 @@ kb_predict_kernel(KbPredictArgs P) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Warp-autonomous variant for very small models (n <= 64, d <= 8, ordinary Kriging): the AK-MCS
+// population sweep (akmcs.py:77-89 over 1e8 points with tens of training points) is bound by the
+// exp() of the correlations, not by memory or the tensor pipe, so the goal is to keep every
+// issue slot busy: no CTA barrier in the loop, a warp owns 32 sites (one per lane), builds its
+// psi tile in a warp-private shared buffer, multiplies by the resident L^-1 with DMMA and
+// finishes its sites, all with __syncwarp only.
+// ---------------------------------------------------------------------------
+#define PW_LDP 36          // padded psi row: 32 sites + 4 (== 4 mod 16 -> conflict-free B fragments)
+#define PW_MAXD 8
+
+size_t kb_predict_warp_smem_bytes(int d, int n8, int qx) {
+  return sizeof(double) * ((size_t)d * n8 + 2 * (size_t)d + (size_t)qx * n8 + (size_t)n8 * (n8 + 4) +
+                           8 * (size_t)n8 * PW_LDP + 8 * 32) + sizeof(KbSweepResult) * 8 + 64;
+}
+bool kb_predict_can_warp(int d, int n, int qx, int nind_trend) {
+  const int n8 = (n + 7) & ~7;
+  return n8 <= 64 && d <= PW_MAXD && nind_trend == 0 && qx == 2 &&
+         kb_predict_warp_smem_bytes(d, n8, qx) + 1024 <= 227 * 1024;
+}
+int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
+  return (2 * (kb_predict_warp_smem_bytes(d, (n + 7) & ~7, qx) + 1024) <= 227 * 1024) ? 2 : 1;
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(256, 2)
+kb_predict_warp_kernel(KbPredictArgs P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = P.n, d = P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
+  KbSweepResult* red = reinterpret_cast<KbSweepResult*>(smem_raw);
+  double* swk = reinterpret_cast<double*>(smem_raw + sizeof(KbSweepResult) * 8);   // [4] (+4 pad)
+  double* XTs = swk + 8;                    // [d][n8]
+  double* sgw = XTs + (size_t)d * n8;       // [d]
+  double* sith = sgw + d;                   // [d]
+  double* exts = sith + d;                  // [2][n8]  alpha | R^-1 1
+  double* ATs = exts + 2 * (size_t)n8;      // [n8][n8 + 4]  k-major L^-1
+  double* psiAll = ATs + (size_t)n8 * lda;  // [8 warps][n8][PW_LDP]
+  double* vvAll = psiAll + 8 * (size_t)n8 * PW_LDP;   // [8 warps][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  for (int e = tid; e < d * n8; e += 256) {
+    const int dim = e / n8, k = e - dim * n8;
+    XTs[e] = (k < n) ? P.XT[(size_t)dim * P.n_pad + k] : 0.0;
+  }
+  for (int e = tid; e < d; e += 256) { sgw[e] = P.gw[e]; sith[e] = P.ith[e]; }
+  if (tid < 4) swk[tid] = P.wk[tid];
+  for (int e = tid; e < 2 * n8; e += 256) {
+    const int j = e / n8, k = e - j * n8;
+    exts[e] = (k < n) ? P.AT[(size_t)k * P.ldat + P.n_pad + j] : 0.0;
+  }
+  for (int e = tid; e < n8 * n8; e += 256) {
+    const int k = e / n8, i = e - k * n8;
+    ATs[(size_t)k * lda + i] = P.AT[(size_t)k * P.ldat + i];
+  }
+  __syncthreads();
+
+  double (*psiW)[PW_LDP] = reinterpret_cast<double (*)[PW_LDP]>(psiAll + (size_t)warp * n8 * PW_LDP);
+  double* vvW = vvAll + warp * 32;
+  const double beta0 = P.beta[0], lm0 = P.LM[0];
+  const int nrb = n8 >> 3;
+  KbRunning run;
+  kb_run_init(run);
+
+  const long long ngroups = (P.m + 31) / 32;
+  for (long long grp = (long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (long long)gridDim.x * 8) {
+    const long long site = grp * 32 + lane;
+    const bool valid = site < P.m;
+    // ---- this lane's site, standardised ------------------------------------
+    double xv[PW_MAXD];
+#pragma unroll
+    for (int dim = 0; dim < PW_MAXD; ++dim) {
+      double v = 0.0;
+      if (dim < d && valid) {
+        v = P.x[(size_t)site * d + dim];
+        if (P.norm_type == KB_NORM_DEFAULT) {
+          const double lo = P.p0[dim], hi = P.p1[dim];
+          v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
+        } else if (P.norm_type == KB_NORM_STD) {
+          v = (v - P.p0[dim]) / P.p1[dim];
+        }
+      }
+      xv[dim] = v;
+    }
+    // ---- psi column of this site; psi' alpha and 1' R^-1 psi on the way --------
+    double ex0 = 0.0, ex1 = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < n8; ++k) {
+      KbPairAcc acc;
+      kb_pair_init(acc);
+#pragma unroll
+      for (int dim = 0; dim < PW_MAXD; ++dim)
+        if (dim < d) kb_pair_dim(acc, xv[dim] - XTs[dim * n8 + k], sgw[dim], sith[dim], MASK);
+      double val = kb_pair_finish(acc, swk, MASK);
+      if (k >= n) val = 0.0;
+      ex0 = fma(val, exts[k], ex0);
+      ex1 = fma(val, exts[n8 + k], ex1);
+      psiW[k][lane] = val;
+    }
+    __syncwarp();
+    // ---- v = L^-1 psi for the 32 sites, keep the column sums of squares --------
+    double sq[4][2];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) sq[cb][0] = sq[cb][1] = 0.0;
+    for (int rb = 0; rb < nrb; ++rb) {
+      double acc[4][2];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
+      const int kmax = 2 * (rb + 1);
+      for (int ks = 0; ks < kmax; ++ks) {
+        const double af = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + gq];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
+      }
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        sq[cb][0] = fma(acc[cb][0], acc[cb][0], sq[cb][0]);
+        sq[cb][1] = fma(acc[cb][1], acc[cb][1], sq[cb][1]);
+      }
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = sq[cb][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (gq == 0) vvW[cb * 8 + 2 * tq + e] = v;
+      }
+    __syncwarp();
+    const double vv = vvW[lane];
+    __syncwarp();
+    // ---- outputs of this lane's site ------------------------------------------
+    if (valid) {
+      const double u = (ex1 - 1.0) / lm0;
+      kb_acq_site(P, beta0, ex0, vv, u * u, site, run);
+    }
+  }
+  // ---- CTA partial -------------------------------------------------------------
+  const KbSweepResult wr_ = kb_run_warp_reduce(run);
+  if (lane == 0) red[warp] = wr_;
+  __syncthreads();
+  if (tid == 0) {
+    KbSweepResult r = red[0];
+    for (int w = 1; w < 8; ++w) kb_result_merge(r, red[w]);
+    P.partials[blockIdx.x] = r;
+  }
+}
+
 // Deterministic final reduction over the per-CTA partials (lowest index on ties).
 __global__ void kb_sweep_final_kernel(const KbSweepResult* __restrict__ partials, int nparts,
                                       long long npoints, KbSweepResult* __restrict__ result) {
@@ -538,10 +738,22 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
     default: { constexpr int M_ = 15; CALL; } break;                     \
   }
 
+template <int MASK>
+static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  kb_predict_warp_kernel<MASK><<<grid, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {
-  const size_t smem = kb_predict_smem_bytes(a.d, a.resident != 0, a.n_pad, a.qx);
+  const size_t smem = (a.resident == 2) ? kb_predict_warp_smem_bytes(a.d, (a.n + 7) & ~7, a.qx)
+                                        : kb_predict_smem_bytes(a.d, a.resident != 0, a.n_pad, a.qx);
   cudaError_t err = cudaSuccess;
-  if (a.resident) {
+  if (a.resident == 2) {
+    KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_warp_launch<M_>(st, a, grid, smem)));
+  } else if (a.resident) {
     KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, true>(st, a, grid, smem)));
   } else {
     KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, false>(st, a, grid, smem)));

@@ -121,10 +121,12 @@ def test_population_larger_than_chain_workers(lib):
 
 
 @pytest.mark.parametrize("n,d,kernel", [(100, 3, "matern52"), (128, 2, "gaussian"), (65, 5, "exponential"),
-                                        (129, 2, "gaussian")])
+                                        (129, 2, "gaussian"), (40, 2, "gaussian"), (64, 3, "matern32"),
+                                        (24, 8, "gaussian"), (30, 9, "gaussian"), (7, 1, "exponential")])
 def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
-    """n_pad = 128 (resident: inverse factor in shared memory) and n_pad = 192 (streaming) around
-    the switch-over, all predictor outputs and the reductions."""
+    """The three predictor variants around their switch-over points: warp-autonomous (n <= 64, d <= 8;
+    two CTAs/SM up to n = 40, one above), shared-memory resident (n_pad <= 128) and streaming
+    (n_pad = 192) -- all predictor outputs and the reductions."""
     rng = np.random.default_rng(41)
     Xn = rng.uniform(-1, 1, (n, d))
     y = np.sum(Xn ** 2, axis=1) - 0.7 + 0.3 * np.sin(3 * Xn[:, 0])

@@ -1,1 +1,1 @@
-timeout -k 5 600 python tools/bench_configs.py > gpurun_out/bench_configs.jsonl 2> gpurun_out/bench_configs.err; echo "rc=$?"
+timeout -k 5 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2_23.log 2>&1; echo "pytest rc=$?"

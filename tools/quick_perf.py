@@ -105,4 +105,6 @@ if __name__ == "__main__":
     predict_case(1000, 10, 1 << 20)
     predict_case(2000, 10, 1 << 19)
     predict_case(32, 2, 1 << 24)
+    predict_case(40, 2, 1 << 24)
+    predict_case(64, 2, 1 << 23)
     predict_case(128, 2, 1 << 23)
