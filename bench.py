@@ -307,7 +307,7 @@ def run_gpu(args):
                       "roofline": {"kernel": "kb_predict_kernel", "bound": "tensor",
                                    "achieved": pred_flops / (pred_ms * 1e-3) / 1e12, "peak": dmma_peak,
                                    "unit": "TFLOP/s", "frac": pred_flops / (pred_ms * 1e-3) / 1e12 / dmma_peak,
-                                   "traffic": traffic.get("kb_predict_kernel"),
+                                   "traffic": (traffic.get("kb_predict_kernel_bytes_per_site") or 0) * SWEEP_PTS or None,
                                    "algorithmic": "1e7 sites x n^2 flop (n=1000); HBM input 8*d B/site = %.1f GB/s"
                                                   % (SWEEP_PTS * DIM * 8 / (pred_ms * 1e-3) / 1e9)},
                       "e2e": {"value": world * SWEEP_PTS * e2e_steps / e_swp, "unit": "points/s",

@@ -14,9 +14,9 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 X, Xn, y, F = bench.make_design()
 if which == "small":
     rng = np.random.default_rng(0)
-    Xn = rng.uniform(-1, 1, (64, 2))
+    Xn = rng.uniform(-1, 1, (40, 2))
     y = np.sum(Xn ** 2, axis=1)
-    F = np.ones((64, 1))
+    F = np.ones((40, 1))
 mdl = _lib.DeviceModel(Xn, y, F, ["gaussian"], device=0)
 mdl.set_stream(torch.cuda.current_stream().cuda_stream)
 d = Xn.shape[1]
