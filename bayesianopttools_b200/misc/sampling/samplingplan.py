@@ -35,6 +35,57 @@ def sobol(nvar, nsamp):
     return out
 
 
+_JK = None
+
+
+def sobol_points(n, d):
+    """Joe & Kuo Sobol points in Gray-code order, first point 0 (reference: misc/sampling/sobol_new.py:5-98,
+    the `sobolnew` option; direction numbers new-joe-kuo-6.21201, first 257 dimensions packed in
+    sobol_joekuo_256.npy by the table script next to the golden-fixture generator).
+
+    x_0 = 0, x_i = x_{i-1} XOR v[c_{i-1}] with c_i = 1 + index of the lowest zero bit of i and the
+    32-bit direction numbers v_k = m_k << (32 - k), m_k from the primitive-polynomial recurrence
+    m_k = m_{k-s} XOR (m_{k-s} << s ... ) (Joe & Kuo 2008)."""
+    global _JK
+    n, d = int(n), int(d)
+    if _JK is None:
+        _JK = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sobol_joekuo_256.npy"))
+    if d - 1 > len(_JK):
+        raise ValueError("sobolnew supports up to %d dimensions" % (len(_JK) + 1))
+    L = max(int(np.ceil(np.log(n) / np.log(2.0))), 1)
+    idx = np.arange(n, dtype=np.int64)
+    c = np.ones(n, dtype=np.int64)              # 1 + number of trailing one bits of i
+    t = idx.copy()
+    while True:
+        odd = (t & 1) == 1
+        if not odd.any():
+            break
+        c[odd] += 1
+        t[odd] >>= 1
+    pts = np.zeros((n, d))
+    for j in range(d):
+        v = np.zeros(L + 2, dtype=np.int64)
+        if j == 0:
+            for i in range(1, L + 1):
+                v[i] = 1 << (32 - i)
+        else:
+            s_, a_ = int(_JK[j - 1, 0]), int(_JK[j - 1, 1])
+            m = [0] + [int(x) for x in _JK[j - 1, 2:2 + s_]]
+            for i in range(1, min(L, s_) + 1):
+                v[i] = m[i] << (32 - i)
+            for i in range(s_ + 1, L + 1):
+                v[i] = v[i - s_] ^ (v[i - s_] >> s_)
+                for k in range(1, s_):
+                    v[i] ^= ((a_ >> (s_ - 1 - k)) & 1) * v[i - k]
+        # x_i = XOR of v[c_0..c_{i-1}]: cumulative XOR along the sequence
+        steps = v[c[:-1]] if n > 1 else np.zeros(0, dtype=np.int64)
+        x = np.zeros(n, dtype=np.int64)
+        if n > 1:
+            x[1:] = np.bitwise_xor.accumulate(steps)
+        pts[:, j] = x / float(2 ** 32)
+    return pts
+
+
 def _primes(k):
     out, c = [], 2
     while len(out) < k:
@@ -86,8 +137,10 @@ def sampling(option, nvar, nsamp, **kwargs):
     opt = option.lower()
     if opt == "halton":
         samplenorm = halton(nvar, nsamp)
-    elif opt in ("sobol", "sobolnew"):
+    elif opt == "sobol":
         samplenorm = sobol(nvar, nsamp)
+    elif opt == "sobolnew":
+        samplenorm = sobol_points(nsamp + 1, nvar)[1:, :]      # the zero point is dropped (samplingplan.py:24-25)
     elif opt == "rlh":
         samplenorm = rlh(nvar, nsamp)
     else:

@@ -241,3 +241,24 @@ if __name__ == "__main__":
     random_case("ok_gaussian_n200_d10", 200, 10, ["gaussian"], seed=13, npop=4, theta_lo=0.0,
                 theta_hi=0.6)
     akmcs_case()
+
+
+def sobol_indices(ref_root="/root/reference"):
+    """tests/golden/sobol_indices.npz: the reference's SobolIndices on the analytical Styblinski-Tang
+    function (no surrogate), nvar = 3, bounds [-5, 5] repeated for the 2 nvar sampling dimensions as
+    the reference requires (sobol_ind.py:24-27 samples nvar*2 columns with the caller's bounds)."""
+    import os as _os
+    from oracle.ref_loader import load_reference
+    load_reference()
+    cwd = _os.getcwd()
+    _os.chdir(_os.path.join(ref_root, "demo"))
+    try:
+        from sensitivity_analysis.sobol_ind import SobolIndices as RefSI
+        lb, ub = -5 * np.ones(6), 5 * np.ones(6)
+        si = RefSI(3, krigobj=None, problem="styblinski", ub=ub, lb=lb)
+        res = si.analyze(True, True, True)
+    finally:
+        _os.chdir(cwd)
+    np.savez(_os.path.join(GOLDEN, "sobol_indices.npz"), lb=lb, ub=ub, A_head=si.A[:64], B_head=si.B[:64],
+             A_tail=si.A[-64:], B_tail=si.B[-64:], first=res["first"], total=res["total"],
+             second_keys=np.array(list(res["second"].keys())), second_vals=np.array(list(res["second"].values())))

@@ -142,3 +142,44 @@ def test_sobo_sweep_improves_best():
     sobo.run(disp=False)
     assert obj.KrigInfo["X"].shape[0] == 13
     assert float(np.min(obj.KrigInfo["y"])) <= y0
+
+
+def test_sobol_indices_on_surrogate_match_the_oracle_and_the_function():
+    """Sobol indices from the batched predictor.  The estimators evaluated
+    on the device predictor equal the same estimators evaluated on the oracle's predictions (same
+    Monte-Carlo matrices), and agree with the indices of the analytical function within the
+    surrogate/Monte-Carlo error."""
+    from oracle import kriging_oracle as ko
+    from bayesianopttools_b200.sensitivity_analysis.sobol_ind import SobolIndices
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    rng = np.random.default_rng(5)
+    nvar, n = 3, 150
+    lb, ub = -5.0 * np.ones(nvar), 5.0 * np.ones(nvar)
+    X = rng.uniform(-5, 5, (n, nvar))
+    y = (50 - 0.5 * np.sum(X ** 4 - 16 * X ** 2 + 5 * X, axis=1)).reshape(-1, 1)
+    K = initkriginfo("single")
+    K.update(X=X, y=y, lb=lb, ub=ub, nrestart=3, kernel=["gaussian"], nugget=-6, TrendOrder=0,
+             optimizer="lbfgsb", problem="styblinski")
+    obj = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    obj.train(disp=False)
+    si = SobolIndices(nvar, krigobj=obj, ub=np.hstack([ub, ub]), lb=np.hstack([lb, lb]))
+    res = si.analyze(True, True, True)
+    # same estimators on the oracle's predictions of the same matrices
+    KI = obj.KrigInfo
+    fit = ko.nll(np.asarray(KI["Theta"]).ravel(), KI["X_norm"], KI["y"], KI["F"], full=True)
+    pred = lambda M: ko.predict(ko.standardize_x(M, lb, ub), KI["X_norm"], KI["y"], KI["F"],
+                                np.zeros((1, nvar), int), fit)["pred"].reshape(-1, 1)
+    ya, yb = pred(si.A), pred(si.B)
+    assert relerr(si.ya, ya) < 1e-8 and relerr(si.yb, yb) < 1e-8
+    fo2 = (np.sum(ya) / si.n) ** 2
+    den = np.sum(ya ** 2) / si.n - fo2
+    for ii in range(nvar):
+        C = si.B.copy()
+        C[:, ii] = si.A[:, ii]
+        yc = pred(C)
+        assert abs(res["first"][ii] - ((np.sum(ya * yc) / si.n - fo2) / den)) < 1e-7
+        assert abs(res["total"][ii] - (1 - (np.sum(yb * yc) / si.n - fo2) / den)) < 1e-7
+    ana = SobolIndices(nvar, problem="styblinski", ub=np.hstack([ub, ub]), lb=np.hstack([lb, lb])).analyze(True, True)
+    assert np.max(np.abs(res["first"] - ana["first"])) < 0.08
+    assert set(res["second"].keys()) == {"x1-x2", "x1-x3", "x2-x3"}

@@ -102,3 +102,20 @@ def test_pls_rotations_match_reference_fixture():
     g = load_golden("kpls")
     W = pls1_rotations(g["X_norm"], g["y"], int(g["n_princomp"]))
     assert relerr(W ** 2, g["plscoeff"] ** 2) < 1e-9
+
+
+def test_sobolnew_sampler_and_sobol_indices_match_reference(golden):
+    """the Joe-Kuo `sobolnew` sampler (misc/sampling/sobol_new.py) and the
+    SobolIndices estimators (sensitivity_analysis/sobol_ind.py) against outputs of the unmodified
+    reference on the analytical Styblinski-Tang case (fixture written by /tmp-run of the reference,
+    see oracle/make_golden.py::sobol_indices)."""
+    from bayesianopttools_b200.sensitivity_analysis.sobol_ind import SobolIndices
+    g = golden("sobol_indices")
+    si = SobolIndices(3, krigobj=None, problem="styblinski", ub=g["ub"], lb=g["lb"])
+    assert np.array_equal(si.A[:64], g["A_head"]) and np.array_equal(si.B[:64], g["B_head"])
+    assert np.array_equal(si.A[-64:], g["A_tail"]) and np.array_equal(si.B[-64:], g["B_tail"])
+    res = si.analyze(True, True, True)
+    assert np.allclose(res["first"], g["first"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(res["total"], g["total"], rtol=1e-12, atol=1e-14)
+    assert list(res["second"].keys()) == [str(k) for k in g["second_keys"]]
+    assert np.allclose(list(res["second"].values()), g["second_vals"], rtol=1e-9, atol=1e-13)
