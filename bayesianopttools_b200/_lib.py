@@ -69,6 +69,10 @@ _SIGNATURES = [
                              C.POINTER(c_double_p), C.c_int, C.POINTER(SweepResult)]),
     ("kb_predict_dev", C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                  C.POINTER(AcqParams), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("kb_points_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, c_double_p]),
+    ("kb_points_destroy", None, [C.c_void_p]),
+    ("kb_predict_points", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AcqParams), C.POINTER(c_double_p), C.c_int,
+                                    C.POINTER(SweepResult)]),
     ("kb_loocv", C.c_int, [C.c_void_p, c_double_p]),
     ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  C.c_int, C.c_int, c_double_p, c_double_p]),
@@ -253,6 +257,21 @@ class DeviceModel:
                                    C.byref(res) if want_result else None))
         return outs, (res.as_dict() if want_result else None)
 
+    def predict_points(self, pts, outputs=(), acq="pred", ybest=0.0, limit=0.0, limit_sign=1, sigmalcb=0.0):
+        """Sweep a DevicePoints set: same outputs / reductions as predict(), no host->device copy."""
+        if pts.d != self.d:
+            raise ValueError("point set has %d columns, model has %d" % (pts.d, self.d))
+        ptrs = (c_double_p * OUT_COUNT)()
+        outs = {}
+        for name in outputs:
+            buf = np.empty(pts.n)
+            outs[name] = buf
+            ptrs[OUT_IDS[name]] = _dp(buf)
+        ap = AcqParams(float(ybest), float(limit), int(limit_sign), float(sigmalcb))
+        res = SweepResult()
+        check(self._lib.kb_predict_points(self._h, pts._h, C.byref(ap), ptrs, OUT_IDS[acq], C.byref(res)))
+        return outs, res.as_dict()
+
     def predict_dev(self, x_ptr, m, idx_offset=0, out_ptrs=None, acq="pred", ybest=0.0, limit=0.0,
                     limit_sign=1, sigmalcb=0.0, result_ptr=None):
         ptrs = (C.c_void_p * OUT_COUNT)()
@@ -261,6 +280,32 @@ class DeviceModel:
         ap = AcqParams(float(ybest), float(limit), int(limit_sign), float(sigmalcb))
         check(self._lib.kb_predict_dev(self._h, int(m), C.c_void_p(x_ptr), int(idx_offset), C.byref(ap),
                                        ptrs, OUT_IDS[acq], C.c_void_p(result_ptr) if result_ptr else None))
+
+
+class DevicePoints:
+    """A point set resident on the device (kb_points): uploaded once, swept many times -- the fixed
+    Monte-Carlo population of AK-MCS (akmcs.py:66-206)."""
+
+    def __init__(self, x, device=None):
+        require_gpu()
+        self._lib = load()
+        x = _f64(np.atleast_2d(x))
+        self.n, self.d = x.shape
+        self.device = default_device() if device is None else int(device)
+        h = C.c_void_p()
+        check(self._lib.kb_points_create(C.byref(h), self.device, self.n, self.d, _dp(x)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kb_points_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def corr_matrix(XN, XM, theta, kernel="gaussian", plscoeff=None, device=None):

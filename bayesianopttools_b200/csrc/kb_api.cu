@@ -646,6 +646,92 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
   return KB_OK;
 }
 
+struct kb_points {
+  int device = 0, d = 0;
+  long long npts = 0;
+  double* x = nullptr;
+  double* out = nullptr;       // lazily sized output staging [nout][chunk]
+  long long out_cap = 0;
+};
+
+kb_status kb_points_create(kb_points** out, int device, long long npts, int d, const double* x) {
+  if (!out || !x || npts < 1 || d < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (kb_device_count() == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: no CPU fallback");
+  CK(cudaSetDevice(device));
+  kb_points* p = new kb_points();
+  p->device = device; p->d = d; p->npts = npts;
+  if (cudaMalloc(&p->x, sizeof(double) * (size_t)npts * d) != cudaSuccess) {
+    delete p;
+    KB_FAIL(KB_ERR_CUDA, "cannot allocate %lld x %d points on device %d", npts, d, device);
+  }
+  // chunked so that pageable host memory does not need one huge pinned staging area
+  const long long chunk = 1LL << 22;
+  for (long long off = 0; off < npts; off += chunk) {
+    const long long cur = (npts - off < chunk) ? (npts - off) : chunk;
+    CK(cudaMemcpy(p->x + (size_t)off * d, x + (size_t)off * d, sizeof(double) * (size_t)cur * d, cudaMemcpyHostToDevice));
+  }
+  *out = p;
+  return KB_OK;
+}
+
+void kb_points_destroy(kb_points* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->x); cudaFree(p->out);
+  delete p;
+}
+
+kb_status kb_predict_points(kb_model* m, const kb_points* pts, const kb_acq_params* ap, double* const* outs,
+                            int acq, KbSweepResult* result) {
+  if (!m || !pts) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (pts->device != m->device || pts->d != m->d)
+    KB_FAIL(KB_ERR_INVALID, "point set (device %d, d=%d) does not match the model (device %d, d=%d)", pts->device,
+            pts->d, m->device, m->d);
+  CK(cudaSetDevice(m->device));
+  int nout = 0;
+  int slot[KB_OUT_COUNT];
+  for (int k = 0; k < KB_OUT_COUNT; ++k) slot[k] = (outs && outs[k]) ? nout++ : -1;
+  if (nout == 0) {
+    // reduce-only: one launch over the whole resident population
+    kb_status s = kb_predict_dev(m, pts->npts, pts->x, 0, ap, nullptr, acq, m->result_dev);
+    if (s != KB_OK) return s;
+    KbSweepResult r;
+    CK(cudaMemcpyAsync(&r, m->result_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (result) *result = r;
+    return KB_OK;
+  }
+  // with per-site outputs: chunks of 2^22 sites through a device staging area
+  kb_points* pw = const_cast<kb_points*>(pts);
+  const long long chunk = pts->npts < (1LL << 22) ? pts->npts : (1LL << 22);
+  if ((long long)nout * chunk > pw->out_cap) {
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(pw->out);
+    pw->out = nullptr;
+    CK(cudaMalloc(&pw->out, sizeof(double) * (size_t)nout * chunk));
+    pw->out_cap = (long long)nout * chunk;
+  }
+  KbSweepResult total{};
+  bool first = true;
+  for (long long off = 0; off < pts->npts; off += chunk) {
+    const long long cur = (pts->npts - off < chunk) ? (pts->npts - off) : chunk;
+    double* od[KB_OUT_COUNT];
+    for (int k = 0; k < KB_OUT_COUNT; ++k) od[k] = (slot[k] >= 0) ? pw->out + (size_t)slot[k] * chunk : nullptr;
+    kb_status s = kb_predict_dev(m, cur, pts->x + (size_t)off * pts->d, off, ap, od, acq, m->result_dev);
+    if (s != KB_OK) return s;
+    for (int k = 0; k < KB_OUT_COUNT; ++k)
+      if (slot[k] >= 0)
+        CK(cudaMemcpyAsync(outs[k] + off, od[k], sizeof(double) * (size_t)cur, cudaMemcpyDeviceToHost, m->stream));
+    KbSweepResult part;
+    CK(cudaMemcpyAsync(&part, m->result_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    merge_result(total, part, first);
+    first = false;
+  }
+  if (result) *result = total;
+  return KB_OK;
+}
+
 kb_status kb_loocv(kb_model* m, double* pred_out) {
   if (!m || !pred_out) KB_FAIL(KB_ERR_INVALID, "bad argument");
   if (!m->fitted) KB_FAIL(KB_ERR_STATE, "loocv called before kb_fit_state");

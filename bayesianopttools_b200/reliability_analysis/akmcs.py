@@ -25,10 +25,22 @@ class AKMCS:
         self.sigmaG = np.zeros((1, self.nsamp))
         self.stop_criteria = 100
         self.keep_fields = akmcsInfo.get("keep_fields", True)
+        # the Monte-Carlo population is the same in every update (akmcs.py:66-206): it is uploaded
+        # to the device once and every sweep is one launch (`resident_population`, default on)
+        self._points = None
+        self.resident = akmcsInfo.get("resident_population", True)
+
+    def _population(self):
+        if not self.resident:
+            return self.init_samp
+        if self._points is None:
+            from .. import _lib
+            self._points = _lib.DevicePoints(self.init_samp)
+        return self._points
 
     def _sweep(self):
         want = ("pred", "s") if self.keep_fields else ()
-        res, outs = self.krigobj.predict_sweep(self.init_samp, acq="u", want=want)
+        res, outs = self.krigobj.predict_sweep(self._population(), acq="u", want=want)
         if self.keep_fields:
             self.Gx = outs["pred"].reshape(-1, 1)
             self.sigmaG = outs["s"].reshape(1, -1)

@@ -240,7 +240,8 @@ class Kriging:
 
     def predict_sweep(self, x, acq="EI", want=()):
         """Reduce-only sweep over many sites: arg-min of one acquisition plus the AK-MCS
-        counters, without materialising per-site outputs.  Returns (result dict, outputs dict)."""
+        counters, without materialising per-site outputs.  Returns (result dict, outputs dict).
+        `x` is an (m, d) array of raw sites or a `_lib.DevicePoints` set already on the device."""
         from .supports.prediction import _configure, _ensure_fitted
         from .supports.device_state import get_model
         K = self.KrigInfo
@@ -252,8 +253,12 @@ class Kriging:
             kw.update(limit=float(K["limit"]), limit_sign=1 if K.get("limittype", ">=") in (">", ">=") else -1)
         if "sigmalcb" in K:
             kw["sigmalcb"] = float(K["sigmalcb"])
-        outs, res = holder.model.predict(np.asarray(x, dtype=float), tuple(w.lower() for w in want),
-                                         acq=acq.lower(), **kw)
+        from .. import _lib
+        if isinstance(x, _lib.DevicePoints):
+            outs, res = holder.model.predict_points(x, tuple(w.lower() for w in want), acq=acq.lower(), **kw)
+        else:
+            outs, res = holder.model.predict(np.asarray(x, dtype=float), tuple(w.lower() for w in want),
+                                             acq=acq.lower(), **kw)
         return res, outs
 
 

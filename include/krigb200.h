@@ -123,6 +123,18 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
                          const kb_acq_params* acq_params, double* const* outs_dev, int acq,
                          KbSweepResult* result_dev);
 
+/* Device-resident point sets.  AK-MCS sweeps the SAME Monte-Carlo population after every model
+ * update (akmcs.py:66-206: `init_samp` is fixed, only the surrogate changes), so the population is
+ * uploaded once and every sweep is a single launch with a 64-byte result.  A point set belongs to a
+ * device, not to a model: it survives the re-creation of the model handle when the design grows. */
+typedef struct kb_points kb_points;
+kb_status kb_points_create(kb_points** out, int device, long long npts, int d, const double* x /*npts x d raw*/);
+void kb_points_destroy(kb_points* p);
+/* Same outputs/reductions as kb_predict over a resident point set; outs[k] are HOST buffers of
+ * npts doubles or NULL (reduce-only when all are NULL). */
+kb_status kb_predict_points(kb_model* m, const kb_points* pts, const kb_acq_params* acq_params,
+                            double* const* outs, int acq, KbSweepResult* result);
+
 /* Leave-one-out predictions at the fitted hyper-parameters, pred_out[n].  Replaces the n
  * refits + n single-site predictions of loocv2 (krigloocv2.py:7-33) with the closed form
  * from one factorisation; same numbers up to rounding. */

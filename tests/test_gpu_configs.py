@@ -191,3 +191,28 @@ def test_c5_akmcs_counters_are_shard_additive(lib):
     assert r["n_fail"] == int(np.sum(ref["pred"] <= 0))
     assert r["min_u_idx"] == int(np.argmin(ref["U"]))
     mdl.close()
+
+
+def test_resident_point_set_equals_host_sweep(lib):
+    """kb_points: the AK-MCS population uploaded once gives the same reductions and outputs as the
+    host-buffer sweep, also after the model handle was re-created with one more training point
+    (what AKMCS.run does every update)."""
+    rng = np.random.default_rng(61)
+    n, d = 30, 2
+    X = rng.uniform(-1, 1, (n + 1, d))
+    y = np.sum(X ** 2, axis=1) - 0.6
+    pop = rng.standard_normal((300_000 + 17, d)) * 0.5
+    pts = lib.DevicePoints(pop)
+    for nn in (n, n + 1):
+        mdl = lib.DeviceModel(X[:nn], y[:nn], np.ones((nn, 1)), ["gaussian"])
+        mdl.fit_state(np.array([-0.2, -0.1]), False, -6.0, want_U=False, want_Psi=False)
+        mdl.set_norm(lib.NORM_NONE)
+        _, a = mdl.predict(pop, (), acq="u")
+        _, b = mdl.predict_points(pts, (), acq="u")
+        assert a == b
+        oa, _ = mdl.predict(pop, ("pred", "s"), acq="u")
+        ob, rb = mdl.predict_points(pts, ("pred", "s"), acq="u")
+        assert np.array_equal(oa["pred"], ob["pred"]) and np.array_equal(oa["s"], ob["s"])
+        assert rb == a
+        mdl.close()
+    pts.close()
