@@ -71,6 +71,9 @@ _SIGNATURES = [
                                  C.POINTER(AcqParams), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     ("kb_points_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, c_double_p]),
     ("kb_points_destroy", None, [C.c_void_p]),
+    ("kb_points_generate", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_double,
+                                     C.c_double, c_double_p, c_double_p, C.c_ulonglong, C.c_longlong]),
+    ("kb_points_get_rows", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     ("kb_predict_points", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AcqParams), C.POINTER(c_double_p), C.c_int,
                                     C.POINTER(SweepResult)]),
     ("kb_loocv", C.c_int, [C.c_void_p, c_double_p]),
@@ -286,6 +289,8 @@ class DevicePoints:
     """A point set resident on the device (kb_points): uploaded once, swept many times -- the fixed
     Monte-Carlo population of AK-MCS (akmcs.py:66-206)."""
 
+    DISTS = {"normal": 0, "gaussian": 0, "lognormal": 1, "gumbel": 2, "random": 3, "uniform": 3}
+
     def __init__(self, x, device=None):
         require_gpu()
         self._lib = load()
@@ -295,6 +300,38 @@ class DevicePoints:
         h = C.c_void_p()
         check(self._lib.kb_points_create(C.byref(h), self.device, self.n, self.d, _dp(x)))
         self._h = h
+
+    @classmethod
+    def generate(cls, n, d, dist="gaussian", mean=0.0, stddev=1.0, lb=None, ub=None, seed=0, first_index=0,
+                 device=None):
+        """Population generated on the device (Philox4x32-10, reproducible per site index)."""
+        require_gpu()
+        self = cls.__new__(cls)
+        self._lib = load()
+        self.n, self.d = int(n), int(d)
+        self.device = default_device() if device is None else int(device)
+        kind = cls.DISTS[dist.lower()]
+        lbp = ubp = None
+        if kind == 3:
+            if lb is None or ub is None:
+                raise ValueError("type 'random' is selected, please input lower bound and upper bound value")
+            lb_, ub_ = _f64(np.asarray(lb).reshape(-1)), _f64(np.asarray(ub).reshape(-1))
+            lbp, ubp = _dp(lb_), _dp(ub_)
+        h = C.c_void_p()
+        check(self._lib.kb_points_generate(C.byref(h), self.device, self.n, self.d, kind, float(mean), float(stddev),
+                                           lbp, ubp, int(seed), int(first_index)))
+        self._h = h
+        return self
+
+    def rows(self, row0, nrows=1):
+        out = np.empty((int(nrows), self.d))
+        check(self._lib.kb_points_get_rows(self._h, int(row0), int(nrows), _dp(out)))
+        return out
+
+    def __getitem__(self, key):
+        """pts[i, :] -> one site as a (d,) array (what AKMCS needs for the next infill point)."""
+        i = key[0] if isinstance(key, tuple) else key
+        return self.rows(int(i), 1)[0]
 
     def close(self):
         if getattr(self, "_h", None):

@@ -674,6 +674,46 @@ kb_status kb_points_create(kb_points** out, int device, long long npts, int d, c
   return KB_OK;
 }
 
+kb_status kb_points_generate(kb_points** out, int device, long long npts, int d, int dist, double p0, double p1,
+                             const double* lb, const double* ub, unsigned long long seed, long long first_index) {
+  if (!out || npts < 1 || d < 1 || dist < 0 || dist > 3) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (dist == KB_DIST_UNIFORM && (!lb || !ub))
+    KB_FAIL(KB_ERR_INVALID, "type 'random' is selected, please input lower bound and upper bound value");
+  if (kb_device_count() == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: no CPU fallback");
+  CK(cudaSetDevice(device));
+  kb_points* p = new kb_points();
+  p->device = device; p->d = d; p->npts = npts;
+  if (cudaMalloc(&p->x, sizeof(double) * (size_t)npts * d) != cudaSuccess) {
+    delete p;
+    KB_FAIL(KB_ERR_CUDA, "cannot allocate %lld x %d points on device %d", npts, d, device);
+  }
+  double* bounds = nullptr;
+  if (dist == KB_DIST_UNIFORM) {
+    CK(cudaMalloc(&bounds, sizeof(double) * 2 * d));
+    CK(cudaMemcpy(bounds, lb, sizeof(double) * d, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(bounds + d, ub, sizeof(double) * d, cudaMemcpyHostToDevice));
+  }
+  cudaError_t e = kb_launch_points_generate(nullptr, p->x, npts, d, dist, p0, p1, bounds, bounds ? bounds + d : nullptr,
+                                            seed, first_index);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(bounds);
+  g_launches += 1;
+  if (e != cudaSuccess) {
+    cudaFree(p->x);
+    delete p;
+    KB_FAIL(KB_ERR_CUDA, "population generator: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return KB_OK;
+}
+
+kb_status kb_points_get_rows(const kb_points* p, long long row0, long long nrows, double* x_out) {
+  if (!p || !x_out || row0 < 0 || nrows < 1 || row0 + nrows > p->npts) KB_FAIL(KB_ERR_INVALID, "bad row range");
+  CK(cudaSetDevice(p->device));
+  CK(cudaMemcpy(x_out, p->x + (size_t)row0 * p->d, sizeof(double) * (size_t)nrows * p->d, cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
 void kb_points_destroy(kb_points* p) {
   if (!p) return;
   cudaSetDevice(p->device);

@@ -137,5 +137,10 @@ size_t kb_predict_warp_smem_bytes(int d, int n8, int qx);
 int kb_predict_warp_ctas_per_sm(int d, int n, int qx);
 int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx);
 
+// --- kb_rng.cu ---------------------------------------------------------------
+cudaError_t kb_launch_points_generate(cudaStream_t st, double* x, long long npts, int d, int dist, double p0, double p1,
+                                      const double* lb_dev, const double* ub_dev, unsigned long long seed,
+                                      long long first_index);
+
 // --- kb_peak.cu --------------------------------------------------------------
 cudaError_t kb_launch_peak(cudaStream_t st, int which, int iters, int grid, double* sink);

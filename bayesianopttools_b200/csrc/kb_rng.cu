@@ -1,0 +1,77 @@
+// krig-b200: Monte-Carlo population generator on the device (mcpopgen, reliability_analysis/akmcs.py:241-260).
+// Counter-based Philox4x32-10 (Salmon et al. 2011): no state, site i / dimension pair j -> one block of
+// four 32-bit words -> two 53-bit uniforms -> two variates; reproducible on the host (oracle/philox.py).
+#include "kb_common.cuh"
+#include "kb_internal.h"
+
+__device__ __forceinline__ void kb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1, uint32_t (&out)[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 52-bit uniform strictly inside (0, 1): (((hi << 20) | (lo >> 12)) + 0.5) * 2^-52  (exact in FP64)
+__device__ __forceinline__ double kb_u53(uint32_t hi, uint32_t lo) {
+  const unsigned long long v = ((unsigned long long)hi << 20) | (unsigned long long)(lo >> 12);
+  return ((double)v + 0.5) * 2.220446049250313e-16;
+}
+
+__global__ void kb_points_generate_kernel(double* __restrict__ x, long long npts, int d, int dist, double p0, double p1,
+                                          const double* __restrict__ lb, const double* __restrict__ ub,
+                                          unsigned long long seed, long long first_index) {
+  const int npair = (d + 1) / 2;
+  const long long total = npts * npair;
+  double lmu = 0.0, lsig = 0.0, gscale = 0.0;
+  if (dist == KB_DIST_LOGNORMAL) {          // akmcs.py:246-250
+    const double var = p1 * p1;
+    lsig = sqrt(log(var / (p0 * p0) + 1.0));
+    lmu = log((p0 * p0) / sqrt(var + p0 * p0));
+  } else if (dist == KB_DIST_GUMBEL) {      // akmcs.py:251-253
+    gscale = (p1 / 3.14159265358979323846) * sqrt(6.0);
+  }
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / npair;
+    const int j = (int)(e - i * npair);
+    const unsigned long long gi = (unsigned long long)(i + first_index);
+    uint32_t r[4];
+    kb_philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)j, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = kb_u53(r[0], r[1]), u2 = kb_u53(r[2], r[3]);
+    double v0, v1;
+    if (dist == KB_DIST_UNIFORM) {
+      v0 = u1; v1 = u2;
+    } else if (dist == KB_DIST_GUMBEL) {
+      v0 = p0 - gscale * log(-log(u1));
+      v1 = p0 - gscale * log(-log(u2));
+    } else {                                // Box-Muller
+      const double rad = sqrt(-2.0 * log(u1));
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      v0 = rad * cs; v1 = rad * sn;
+      if (dist == KB_DIST_NORMAL) { v0 = p1 * v0 + p0; v1 = p1 * v1 + p0; }
+      else { v0 = exp(lsig * v0 + lmu); v1 = exp(lsig * v1 + lmu); }
+    }
+    const int d0 = 2 * j, d1 = 2 * j + 1;
+    if (dist == KB_DIST_UNIFORM) {
+      v0 = lb[d0] + (ub[d0] - lb[d0]) * v0;
+      if (d1 < d) v1 = lb[d1] + (ub[d1] - lb[d1]) * v1;
+    }
+    x[(size_t)i * d + d0] = v0;
+    if (d1 < d) x[(size_t)i * d + d1] = v1;
+  }
+}
+
+cudaError_t kb_launch_points_generate(cudaStream_t st, double* x, long long npts, int d, int dist, double p0, double p1,
+                                      const double* lb_dev, const double* ub_dev, unsigned long long seed,
+                                      long long first_index) {
+  kb_points_generate_kernel<<<148 * 8, 256, 0, st>>>(x, npts, d, dist, p0, p1, lb_dev, ub_dev, seed, first_index);
+  return cudaGetLastError();
+}

@@ -18,9 +18,9 @@ class AKMCS:
         akmcsInfo = akmcsInfocheck(akmcsInfo)
         self.krigobj = krigobj
         self.akmcsInfo = akmcsInfo
-        self.init_samp = akmcsInfo["init_samp"]
+        self.init_samp = akmcsInfo["init_samp"]         # (N, d) array, or a _lib.DevicePoints set
         self.maxupdate = akmcsInfo["maxupdate"]
-        self.nsamp = np.size(self.init_samp, axis=0)
+        self.nsamp = self.init_samp.n if hasattr(self.init_samp, "_h") else np.size(self.init_samp, axis=0)
         self.Gx = np.zeros((self.nsamp, 1))
         self.sigmaG = np.zeros((1, self.nsamp))
         self.stop_criteria = 100
@@ -31,6 +31,8 @@ class AKMCS:
         self.resident = akmcsInfo.get("resident_population", True)
 
     def _population(self):
+        if hasattr(self.init_samp, "_h"):            # already a device-resident point set
+            return self.init_samp
         if not self.resident:
             return self.init_samp
         if self._points is None:
@@ -53,6 +55,7 @@ class AKMCS:
         self.stop_criteria = 100 if pf0 == 0 else (res["n_fail_minus"] / N - res["n_fail_plus"] / N) / pf0
         if self.keep_fields:
             self.U = np.abs(self.Gx) / self.sigmaG.reshape(-1, 1)
+        self.xnew = np.asarray(self.xnew, dtype=float).reshape(-1)
 
     def covpf(self):
         """akmcs.py:214-220"""
@@ -94,6 +97,24 @@ class AKMCS:
             if disp:
                 print(f"COV: {self.cov}")
             break          # akmcs.py:206 ("temporary break")
+
+
+def mcpopgen_device(lb=None, ub=None, n_order=6, n_coeff=1, type="random", ndim=2, stddev=1, mean=0, seed=0,
+                    first_index=0):
+    """mcpopgen (akmcs.py:241-260) with the population generated and kept on the device: same arguments
+    and distributions, counter-based Philox stream instead of numpy's global Mersenne Twister (so the
+    sample differs from numpy's, like any re-seeding would); returns a `_lib.DevicePoints` set that AKMCS
+    accepts as `init_samp`."""
+    from .. import _lib
+    nmc = int(n_coeff * 10 ** n_order)
+    if type.lower() == "random":
+        if lb is None or ub is None:
+            raise ValueError("type 'random' is selected, please input lower bound and upper bound value")
+        ndim = len(lb)
+    if type.lower() not in _lib.DevicePoints.DISTS:
+        raise ValueError("Monte Carlo sampling type not supported")
+    return _lib.DevicePoints.generate(nmc, ndim, dist=type, mean=mean, stddev=stddev, lb=lb, ub=ub, seed=seed,
+                                      first_index=first_index)
 
 
 def mcpopgen(lb=None, ub=None, n_order=6, n_coeff=1, type="random", ndim=2, stddev=1, mean=0):

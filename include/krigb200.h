@@ -130,6 +130,17 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
 typedef struct kb_points kb_points;
 kb_status kb_points_create(kb_points** out, int device, long long npts, int d, const double* x /*npts x d raw*/);
 void kb_points_destroy(kb_points* p);
+/* Monte-Carlo population generated ON the device (mcpopgen, akmcs.py:241-260) with the counter-based
+ * Philox4x32-10 generator: the two uniforms of site i, dimension pair j are Philox(counter = (i, j),
+ * key = seed), so any subset can be reproduced on the host (oracle/philox.py) and shards of a
+ * multi-GPU population are generated independently (first_index = global index of site 0).
+ * dist: KB_DIST_NORMAL (p0 = mean, p1 = stddev), KB_DIST_LOGNORMAL (mean, stddev of the variable),
+ * KB_DIST_GUMBEL (mean, stddev), KB_DIST_UNIFORM (per-dimension lb, ub). */
+enum { KB_DIST_NORMAL = 0, KB_DIST_LOGNORMAL = 1, KB_DIST_GUMBEL = 2, KB_DIST_UNIFORM = 3 };
+kb_status kb_points_generate(kb_points** out, int device, long long npts, int d, int dist, double p0, double p1,
+                             const double* lb, const double* ub, unsigned long long seed, long long first_index);
+/* Copy rows [row0, row0 + nrows) of a point set to the host (e.g. the site picked by the arg-min). */
+kb_status kb_points_get_rows(const kb_points* p, long long row0, long long nrows, double* x_out);
 /* Same outputs/reductions as kb_predict over a resident point set; outs[k] are HOST buffers of
  * npts doubles or NULL (reduce-only when all are NULL). */
 kb_status kb_predict_points(kb_model* m, const kb_points* pts, const kb_acq_params* acq_params,

@@ -216,3 +216,57 @@ def test_resident_point_set_equals_host_sweep(lib):
         assert rb == a
         mdl.close()
     pts.close()
+
+
+@pytest.mark.parametrize("dist,kw", [("gaussian", dict(mean=0.3, stddev=1.7)), ("lognormal", dict(mean=2.0, stddev=0.5)),
+                                     ("gumbel", dict(mean=1.0, stddev=2.0)),
+                                     ("random", dict(lb=[-5.0, 0.0, 1.0], ub=[5.0, 1.0, 4.0]))])
+def test_device_population_generator_matches_host_restatement(lib, dist, kw):
+    """the Monte-Carlo population is generated on the device with a counter-based RNG
+    that the host reproduces for any subset of site indices (oracle/philox.py); shards generated with
+    `first_index` are identical to the corresponding rows of the whole population (multi-GPU rule)."""
+    from oracle import philox
+    n, d, seed = 1_000_003, 3, 12345
+    pts = lib.DevicePoints.generate(n, d, dist=dist, seed=seed, **kw)
+    idx = np.array([0, 1, 2, 77, 4096, 65535, 65536, 999_999, n - 1])
+    host_kw = dict(p0=kw.get("mean", 0.0), p1=kw.get("stddev", 1.0), lb=kw.get("lb"), ub=kw.get("ub"))
+    name = {"gaussian": "normal", "random": "uniform"}.get(dist, dist)
+    ref = philox.population(idx, d, dist=name, seed=seed, **host_kw)
+    got = np.vstack([pts.rows(int(i), 1) for i in idx])
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 1e-13
+    head = pts.rows(0, 200_000)
+    if dist == "gaussian":
+        assert abs(head.mean() - 0.3) < 0.02 and abs(head.std() - 1.7) < 0.02
+    shard = lib.DevicePoints.generate(1000, d, dist=dist, seed=seed, first_index=500_000, **kw)
+    assert np.array_equal(shard.rows(0, 1000), pts.rows(500_000, 1000))
+    pts.close()
+    shard.close()
+
+
+def test_akmcs_runs_on_a_device_generated_population(lib):
+    """AKMCS with `init_samp` = a device-generated point set: one update, reductions equal those of
+    the same population pulled to the host."""
+    from bayesianopttools_b200.misc.sampling.samplingplan import sampling
+    from bayesianopttools_b200.reliability_analysis.akmcs import AKMCS, mcpopgen_device
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    from bayesianopttools_b200.testcase.RA.testcase import evaluate
+    lb, ub = -5.0 * np.ones(2), 5.0 * np.ones(2)
+    _, X = sampling("halton", 2, 12, result="real", upbound=ub, lobound=lb)
+    y = evaluate(X, type="fourbranches")
+
+    def fresh():
+        K = initkriginfo("single")
+        K.update(X=X.copy(), y=y.copy(), nvar=2, problem="fourbranches", nsamp=12, nrestart=3, ub=ub, lb=lb,
+                 optimizer="lbfgsb", kernel=["gaussian"], nugget=-6)
+        k = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+        k.train(disp=False)
+        return k
+    pop = mcpopgen_device(type="gaussian", ndim=2, n_order=5, n_coeff=3, stddev=1, mean=0, seed=7)
+    a = AKMCS(fresh(), dict(init_samp=pop, maxupdate=1, problem="fourbranches", keep_fields=False))
+    a.run(disp=False)
+    b = AKMCS(fresh(), dict(init_samp=pop.rows(0, pop.n), maxupdate=1, problem="fourbranches", keep_fields=False,
+                            resident_population=False))
+    b.run(disp=False)
+    assert a.Pf == b.Pf and a.minU == b.minU and np.array_equal(a.xnew, b.xnew)
+    assert a.stop_criteria == b.stop_criteria and a.updateX.shape == (2, 2)
