@@ -76,6 +76,10 @@ _SIGNATURES = [
     ("kb_points_get_rows", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     ("kb_predict_points", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AcqParams), C.POINTER(c_double_p), C.c_int,
                                     C.POINTER(SweepResult)]),
+    ("kb_exi2d", C.c_int, [C.c_int, C.c_longlong, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p,
+                           c_double_p]),
+    ("kb_ehvi2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, c_double_p, C.c_int, c_double_p, c_double_p,
+                            C.c_int, c_double_p, C.POINTER(C.c_longlong), c_double_p]),
     ("kb_loocv", C.c_int, [C.c_void_p, c_double_p]),
     ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  C.c_int, C.c_int, c_double_p, c_double_p]),
@@ -371,3 +375,35 @@ def measure_peak(which, device=None):
 
 def launch_count():
     return int(load().kb_launch_count())
+
+
+def exi2d_batch(front, ref, mu, s, device=None):
+    """`exi2d(P, r, mu, s)` (optim_tools/ehvi/exi2d.py:6-83) for an (m, 2) batch of candidates."""
+    require_gpu()
+    lib = load()
+    front = _f64(np.atleast_2d(front))
+    ref = _f64(np.asarray(ref).reshape(-1))
+    mu = _f64(np.atleast_2d(mu))
+    s = _f64(np.atleast_2d(s))
+    if front.shape[1] != 2 or ref.size != 2 or mu.shape[1] != 2 or s.shape != mu.shape:
+        raise ValueError("exi2d handles two objectives: P (k, 2), r (2,), mu and s (m, 2)")
+    out = np.empty(mu.shape[0])
+    check(lib.kb_exi2d(default_device() if device is None else int(device), mu.shape[0], _dp(mu), _dp(s),
+                       front.shape[0], _dp(front), _dp(ref), _dp(out)))
+    return out
+
+
+def ehvi2d_models(model1, model2, x, front, ref, spread="ssqr", want_values=True):
+    """Batched `ehvicalc` (optim_tools/ehvi/EHVIcomputation.py:10-42): both fitted DeviceModels predict
+    the raw candidates x (m, d); returns (improvement per candidate or None, argmax index, max value)."""
+    x = _f64(np.atleast_2d(x))
+    front = _f64(np.atleast_2d(front))
+    ref = _f64(np.asarray(ref).reshape(-1))
+    if front.shape[1] != 2 or ref.size != 2:
+        raise ValueError("ehvi2d handles two objectives: P (k, 2), r (2,)")
+    out = np.empty(x.shape[0]) if want_values else None
+    bi, bv = C.c_longlong(-1), C.c_double(0.0)
+    check(model1._lib.kb_ehvi2d(model1._h, model2._h, x.shape[0], _dp(x), front.shape[0], _dp(front), _dp(ref),
+                                0 if spread.lower() == "ssqr" else 1, _dp(out) if out is not None else None,
+                                C.byref(bi), C.cast(C.byref(bv), c_double_p)))
+    return out, int(bi.value), float(bv.value)

@@ -772,6 +772,113 @@ kb_status kb_predict_points(kb_model* m, const kb_points* pts, const kb_acq_para
   return KB_OK;
 }
 
+// ---- 2-objective expected hypervolume improvement -------------------------------------------------
+struct KbEhviBestHost { double val; long long idx; };
+
+static kb_status ehvi_table_to_device(int k, const double* front, const double* ref, double** table_dev) {
+  if (k < 1 || !front || !ref) KB_FAIL(KB_ERR_INVALID, "bad Pareto front");
+  std::vector<double> table(kb_ehvi_table_doubles(k));
+  kb_ehvi_build_table(k, front, ref, table.data());
+  CK(cudaMalloc(table_dev, sizeof(double) * table.size()));
+  CK(cudaMemcpy(*table_dev, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+  return KB_OK;
+}
+
+kb_status kb_exi2d(int device, long long npts, const double* mu, const double* s, int k, const double* front,
+                   const double* ref, double* out) {
+  if (!mu || !s || !out || npts < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (kb_device_count() == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: no CPU fallback");
+  CK(cudaSetDevice(device));
+  int num_sms = 0;
+  CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  double* table_dev = nullptr;
+  kb_status st = ehvi_table_to_device(k, front, ref, &table_dev);
+  if (st != KB_OK) return st;
+  // de-interleave on the host: the kernel reads one array per quantity
+  std::vector<double> cols((size_t)4 * npts);
+  for (long long i = 0; i < npts; ++i) {
+    cols[(size_t)i] = mu[2 * i]; cols[(size_t)(npts + i)] = s[2 * i];
+    cols[(size_t)(2 * npts + i)] = mu[2 * i + 1]; cols[(size_t)(3 * npts + i)] = s[2 * i + 1];
+  }
+  double* buf = nullptr;
+  void* red = nullptr;
+  const int grid = kb_ehvi_grid(npts, num_sms);
+  cudaError_t e = cudaMalloc(&buf, sizeof(double) * (size_t)5 * npts);
+  if (e == cudaSuccess) e = cudaMalloc(&red, sizeof(KbEhviBestHost) * (size_t)(grid + 1));
+  if (e == cudaSuccess) e = cudaMemcpy(buf, cols.data(), sizeof(double) * cols.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = kb_launch_ehvi2d(nullptr, npts, buf, buf + npts, buf + 2 * npts, buf + 3 * npts, table_dev, k, 0, buf + 4 * npts,
+                         (KbEhviBestHost*)red + 1, red, 0, num_sms);
+  if (e == cudaSuccess) e = cudaMemcpy(out, buf + 4 * npts, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost);
+  g_launches += 2;
+  cudaFree(buf); cudaFree(red); cudaFree(table_dev);
+  if (e != cudaSuccess) KB_FAIL(KB_ERR_CUDA, "exi2d: %s", cudaGetErrorString(e));
+  return KB_OK;
+}
+
+kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x, int k, const double* front,
+                    const double* ref, int spread, double* out, long long* best_idx, double* best_val) {
+  if (!m1 || !m2 || !x || npts < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (m1->device != m2->device || m1->d != m2->d)
+    KB_FAIL(KB_ERR_INVALID, "the two objective models must share the device and the input dimension");
+  if (!m1->fitted || !m2->fitted) KB_FAIL(KB_ERR_STATE, "ehvi called before kb_fit_state");
+  CK(cudaSetDevice(m1->device));
+  double* table_dev = nullptr;
+  kb_status st = ehvi_table_to_device(k, front, ref, &table_dev);
+  if (st != KB_OK) return st;
+  const long long chunk = npts < (1LL << 20) ? npts : (1LL << 20);
+  const int d = m1->d;
+  const int grid = kb_ehvi_grid(chunk, m1->num_sms);
+  double *xd = nullptr, *buf = nullptr;
+  void* red = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_p2 = nullptr;
+  cudaError_t e = cudaMalloc(&xd, sizeof(double) * (size_t)chunk * d);
+  if (e == cudaSuccess) e = cudaMalloc(&buf, sizeof(double) * (size_t)5 * chunk);
+  if (e == cudaSuccess) e = cudaMalloc(&red, sizeof(KbEhviBestHost) * (size_t)(grid + 1));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_p2, cudaEventDisableTiming);
+  const int sid = spread ? KB_OUT_S : KB_OUT_SSQR;
+  for (long long off = 0; off < npts && e == cudaSuccess && st == KB_OK; off += chunk) {
+    const long long cur = (npts - off < chunk) ? (npts - off) : chunk;
+    // the second model's sweep of the previous chunk must be done with xd before it is overwritten
+    e = cudaStreamWaitEvent(m1->stream, ev_p2, 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(xd, x + (size_t)off * d, sizeof(double) * (size_t)cur * d, cudaMemcpyHostToDevice, m1->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_x, m1->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(m2->stream, ev_x, 0);
+    if (e != cudaSuccess) break;
+    double* o1[KB_OUT_COUNT] = {nullptr};
+    double* o2[KB_OUT_COUNT] = {nullptr};
+    o1[KB_OUT_PRED] = buf; o1[sid] = buf + chunk;
+    o2[KB_OUT_PRED] = buf + 2 * chunk; o2[sid] = buf + 3 * chunk;
+    // the two objective models sweep the chunk concurrently on their own streams
+    st = kb_predict_dev(m1, cur, xd, off, nullptr, o1, KB_OUT_PRED, nullptr);
+    if (st == KB_OK) st = kb_predict_dev(m2, cur, xd, off, nullptr, o2, KB_OUT_PRED, nullptr);
+    if (st != KB_OK) break;
+    e = cudaEventRecord(ev_p2, m2->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(m1->stream, ev_p2, 0);
+    if (e == cudaSuccess)
+      e = kb_launch_ehvi2d(m1->stream, cur, buf, buf + chunk, buf + 2 * chunk, buf + 3 * chunk, table_dev, k, off,
+                           buf + 4 * chunk, (KbEhviBestHost*)red + 1, red, off > 0 ? 1 : 0, m1->num_sms);
+    g_launches += 2;
+    if (e == cudaSuccess && out)
+      e = cudaMemcpyAsync(out + off, buf + 4 * chunk, sizeof(double) * (size_t)cur, cudaMemcpyDeviceToHost, m1->stream);
+  }
+  KbEhviBestHost best{0.0, -1};
+  if (e == cudaSuccess && st == KB_OK)
+    e = cudaMemcpyAsync(&best, red, sizeof(best), cudaMemcpyDeviceToHost, m1->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m1->stream);
+  cudaStreamSynchronize(m2->stream);
+  cudaFree(xd); cudaFree(buf); cudaFree(red); cudaFree(table_dev);
+  if (ev_x) cudaEventDestroy(ev_x);
+  if (ev_p2) cudaEventDestroy(ev_p2);
+  if (st != KB_OK) return st;
+  if (e != cudaSuccess) KB_FAIL(KB_ERR_CUDA, "ehvi2d: %s", cudaGetErrorString(e));
+  if (best_idx) *best_idx = best.idx;
+  if (best_val) *best_val = best.val;
+  return KB_OK;
+}
+
 kb_status kb_loocv(kb_model* m, double* pred_out) {
   if (!m || !pred_out) KB_FAIL(KB_ERR_INVALID, "bad argument");
   if (!m->fitted) KB_FAIL(KB_ERR_STATE, "loocv called before kb_fit_state");

@@ -142,5 +142,13 @@ cudaError_t kb_launch_points_generate(cudaStream_t st, double* x, long long npts
                                       const double* lb_dev, const double* ub_dev, unsigned long long seed,
                                       long long first_index);
 
+// kb_ehvi.cu: 2-objective expected hypervolume improvement (exi2d.py:6-83)
+size_t kb_ehvi_table_doubles(int k);
+void kb_ehvi_build_table(int k, const double* front, const double* ref, double* table);
+int kb_ehvi_grid(long long m, int num_sms);
+cudaError_t kb_launch_ehvi2d(cudaStream_t st, long long m, const double* mu1, const double* s1, const double* mu2,
+                             const double* s2, const double* table_dev, int k, long long idx_offset, double* out,
+                             void* partials, void* result, int accumulate, int num_sms);
+
 // --- kb_peak.cu --------------------------------------------------------------
 cudaError_t kb_launch_peak(cudaStream_t st, int which, int iters, int grid, double* sink);

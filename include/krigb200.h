@@ -146,6 +146,22 @@ kb_status kb_points_get_rows(const kb_points* p, long long row0, long long nrows
 kb_status kb_predict_points(kb_model* m, const kb_points* pts, const kb_acq_params* acq_params,
                             double* const* outs, int acq, KbSweepResult* result);
 
+/* 2-objective expected hypervolume improvement (multi-objective acquisition).
+ * kb_exi2d is `exi2d(P, r, mu, s)` (optim_tools/ehvi/exi2d.py:6-83) over npts candidates at once:
+ * front is the k x 2 row-major set of non-dominated objective values P, ref the reference point r,
+ * mu and s are (npts x 2) row-major HOST arrays, out[npts] the improvement of each candidate.
+ * kb_ehvi2d is the batched `ehvicalc` (optim_tools/ehvi/EHVIcomputation.py:10-42): both fitted models
+ * predict the npts raw candidates x (npts x d, HOST) and the improvements are computed from the
+ * predictions without leaving the device.  spread = 0 hands the predictive VARIANCE to exi2d as its
+ * `s` argument, which is what ehvicalc does (EHVIcomputation.py:30-35 fills `s` from 'SSqr');
+ * spread = 1 hands the standard deviation.  out (npts, HOST) may be NULL; best_idx/best_val receive
+ * the candidate with the LARGEST improvement (ties: lowest index).  The two models must live on the
+ * same device and share d. */
+kb_status kb_exi2d(int device, long long npts, const double* mu, const double* s, int k, const double* front,
+                   const double* ref, double* out);
+kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x, int k, const double* front,
+                    const double* ref, int spread, double* out, long long* best_idx, double* best_val);
+
 /* Leave-one-out predictions at the fitted hyper-parameters, pred_out[n].  Replaces the n
  * refits + n single-site predictions of loocv2 (krigloocv2.py:7-33) with the closed form
  * from one factorisation; same numbers up to rounding. */

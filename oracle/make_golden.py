@@ -218,6 +218,53 @@ def akmcs_case():
          xnew=ak.xnew, stop=ak.stop_criteria, n_fail=int(np.sum(ak.Gx <= 0)),
          n_fail_minus=int(np.sum(temp1 <= 0)), n_fail_plus=int(np.sum(temp2 <= 0)))
 
+def sobol_indices(ref_root="/root/reference"):
+    """tests/golden/sobol_indices.npz: the reference's SobolIndices on the analytical Styblinski-Tang
+    function (no surrogate), nvar = 3, bounds [-5, 5] repeated for the 2 nvar sampling dimensions as
+    the reference requires (sobol_ind.py:24-27 samples nvar*2 columns with the caller's bounds)."""
+    import os as _os
+    from oracle.ref_loader import load_reference
+    load_reference()
+    cwd = _os.getcwd()
+    _os.chdir(_os.path.join(ref_root, "demo"))
+    try:
+        from sensitivity_analysis.sobol_ind import SobolIndices as RefSI
+        lb, ub = -5 * np.ones(6), 5 * np.ones(6)
+        si = RefSI(3, krigobj=None, problem="styblinski", ub=ub, lb=lb)
+        res = si.analyze(True, True, True)
+    finally:
+        _os.chdir(cwd)
+    np.savez(_os.path.join(OUT, "sobol_indices.npz"), lb=lb, ub=ub, A_head=si.A[:64], B_head=si.B[:64],
+             A_tail=si.A[-64:], B_tail=si.B[-64:], first=res["first"], total=res["total"],
+             second_keys=np.array(list(res["second"].keys())), second_vals=np.array(list(res["second"].values())))
+
+
+def ehvi2d(ref_root="/root/reference"):
+    """tests/golden/ehvi2d.npz: the reference's exi2d (optim_tools/ehvi/exi2d.py) on random 2-objective
+    fronts of 1, 2, 5 and 9 points, 12 candidates each."""
+    import os as _os
+    from oracle.ref_loader import load_reference
+    load_reference()
+    cwd = _os.getcwd()
+    _os.chdir(_os.path.join(ref_root, "demo"))
+    try:
+        from optim_tools.ehvi.exi2d import exi2d as ref_exi2d
+        rng = np.random.default_rng(0)
+        out = {}
+        for c, k in enumerate((1, 2, 5, 9)):
+            f1 = np.sort(rng.uniform(0, 1, k))
+            f2 = np.sort(rng.uniform(0, 1, k))[::-1]
+            P = np.column_stack([f1, f2])[rng.permutation(k)]
+            r = np.array([1.3, 1.2])
+            mu = rng.uniform(-0.2, 1.4, (12, 2))
+            s = rng.uniform(0.01, 0.5, (12, 2))
+            ref = np.array([ref_exi2d(P, r, mu[i], s[i]) for i in range(12)])
+            for nm, v in zip(("P", "r", "mu", "s", "ref"), (P, r, mu, s, ref)):
+                out["%s%d" % (nm, c)] = v
+    finally:
+        _os.chdir(cwd)
+    np.savez(_os.path.join(OUT, "ehvi2d.npz"), **out)
+
 
 if __name__ == "__main__":
     notebook_case("krigdemo_nb", 50, [-0.06768278, -0.06558988, 121.47648552358743,
@@ -241,24 +288,5 @@ if __name__ == "__main__":
     random_case("ok_gaussian_n200_d10", 200, 10, ["gaussian"], seed=13, npop=4, theta_lo=0.0,
                 theta_hi=0.6)
     akmcs_case()
-
-
-def sobol_indices(ref_root="/root/reference"):
-    """tests/golden/sobol_indices.npz: the reference's SobolIndices on the analytical Styblinski-Tang
-    function (no surrogate), nvar = 3, bounds [-5, 5] repeated for the 2 nvar sampling dimensions as
-    the reference requires (sobol_ind.py:24-27 samples nvar*2 columns with the caller's bounds)."""
-    import os as _os
-    from oracle.ref_loader import load_reference
-    load_reference()
-    cwd = _os.getcwd()
-    _os.chdir(_os.path.join(ref_root, "demo"))
-    try:
-        from sensitivity_analysis.sobol_ind import SobolIndices as RefSI
-        lb, ub = -5 * np.ones(6), 5 * np.ones(6)
-        si = RefSI(3, krigobj=None, problem="styblinski", ub=ub, lb=lb)
-        res = si.analyze(True, True, True)
-    finally:
-        _os.chdir(cwd)
-    np.savez(_os.path.join(GOLDEN, "sobol_indices.npz"), lb=lb, ub=ub, A_head=si.A[:64], B_head=si.B[:64],
-             A_tail=si.A[-64:], B_tail=si.B[-64:], first=res["first"], total=res["total"],
-             second_keys=np.array(list(res["second"].keys())), second_vals=np.array(list(res["second"].values())))
+    sobol_indices()
+    ehvi2d()

@@ -1,5 +1,7 @@
 """GPU: the reference-facing Python surface (Kriging / KPLS / likelihood / prediction / SOBO /
 AKMCS) reproduces the reference's stored outputs end to end."""
+import os
+
 import numpy as np
 import pytest
 
@@ -183,3 +185,79 @@ def test_sobol_indices_on_surrogate_match_the_oracle_and_the_function():
     ana = SobolIndices(nvar, problem="styblinski", ub=np.hstack([ub, ub]), lb=np.hstack([lb, lb])).analyze(True, True)
     assert np.max(np.abs(res["first"] - ana["first"])) < 0.08
     assert set(res["second"].keys()) == {"x1-x2", "x1-x3", "x2-x3"}
+
+
+def _random_front(rng, k):
+    f1 = np.sort(rng.uniform(0, 1, k))
+    f2 = np.sort(rng.uniform(0, 1, k))[::-1]
+    return np.column_stack([f1, f2])[rng.permutation(k)]
+
+
+def test_exi2d_kernel_matches_reference_fixture_and_oracle():
+    """SURVEY section 8(f) row 3 (EHVI part): the device cell sum against the reference's own exi2d
+    outputs (tests/golden/ehvi2d.npz) and, on larger fronts and batches, against the oracle.
+    Tolerance: rel 1e-9 of the largest improvement in the batch (cells are sums of clipped differences,
+    so a candidate with a vanishing improvement carries the absolute error of the big cells)."""
+    from oracle import ehvi_oracle as eo
+    from bayesianopttools_b200.optim_tools.ehvi.exi2d import exi2d
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ehvi2d.npz"))
+    for c in range(4):
+        P, r, mu, s, ref = (g["%s%d" % (nm, c)] for nm in ("P", "r", "mu", "s", "ref"))
+        got = exi2d(P, r, mu, s)
+        assert np.max(np.abs(got - ref)) < 1e-9 * np.max(ref)
+        assert abs(exi2d(P, r, mu[3], s[3]) - ref[3]) < 1e-9 * np.max(ref)      # the reference's scalar call shape
+    rng = np.random.default_rng(11)
+    for k, m in ((1, 5), (17, 3000), (40, 1000), (120, 300)):                     # k = 120: table read from global memory
+        P = _random_front(rng, k)
+        r = np.array([1.2, 1.1])
+        mu = rng.uniform(-0.3, 1.3, (m, 2))
+        s = rng.uniform(1e-3, 0.6, (m, 2))
+        got, want = exi2d(P, r, mu, s), eo.exi2d(P, r, mu, s)
+        assert np.max(np.abs(got - want)) < 1e-9 * np.max(want), (k, m)
+        assert np.all(got >= 0)
+
+
+def test_ehvicalc_batch_matches_oracle_predictions_and_argmax():
+    """`ehvicalc` on two fitted objective models: per-candidate values equal exi2d of the ORACLE's
+    predictions (variance handed over as the spread, as the reference does), the scalar call shape
+    returns the same number, and the device argmax is the candidate numpy picks."""
+    from oracle import ehvi_oracle as eo
+    from oracle import kriging_oracle as ko
+    from bayesianopttools_b200.optim_tools.ehvi.EHVIcomputation import ehvicalc, ehvi_best
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    rng = np.random.default_rng(3)
+    n, d = 60, 2
+    lb, ub = np.zeros(d), np.ones(d)
+    X = rng.uniform(0, 1, (n, d))
+    # a ZDT-like pair of conflicting objectives
+    y1 = X[:, 0] + 0.1 * np.sin(6 * X[:, 1])
+    y2 = 1.0 - np.sqrt(np.clip(X[:, 0], 0, 1)) + 0.5 * (X[:, 1] - 0.3) ** 2
+    objs = []
+    for y in (y1, y2):
+        K = initkriginfo("single")
+        K.update(X=X, y=y.reshape(-1, 1), lb=lb, ub=ub, nrestart=3, kernel=["gaussian"], nugget=-6, TrendOrder=0,
+                 optimizer="lbfgsb")
+        o = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+        o.train(disp=False)
+        objs.append(o)
+    Y = np.column_stack([y1, y2])
+    nd = np.array([not np.any(np.all(Y <= Y[i], axis=1) & np.any(Y < Y[i], axis=1)) for i in range(n)])
+    ypar = Y[nd]
+    mobo = {"refpoint": np.array([1.3, 1.3])}
+    xc = rng.uniform(0, 1, (5000, d))
+    hv = ehvicalc(xc, ypar, mobo, objs)
+    mu = np.zeros((len(xc), 2))
+    var = np.zeros((len(xc), 2))
+    for j, o in enumerate(objs):
+        KI = o.KrigInfo
+        fit = ko.nll(np.asarray(KI["Theta"]).ravel(), KI["X_norm"], KI["y"], KI["F"], full=True)
+        p = ko.predict(ko.standardize_x(xc, lb, ub), KI["X_norm"], KI["y"], KI["F"], np.zeros((1, d), int), fit)
+        mu[:, j], var[:, j] = p["pred"].ravel(), p["ssqr"].ravel()
+    want = eo.exi2d(ypar, mobo["refpoint"], mu, var)
+    assert np.max(want) > 0
+    assert np.max(np.abs(-hv - want)) < 1e-8 * np.max(want)
+    assert np.all((hv < 0) | (hv == np.finfo(float).tiny))          # exact zeros get the reference's penalty sign
+    assert abs(ehvicalc(xc[17], ypar, mobo, objs) - hv[17]) <= 1e-12 * abs(hv[17])
+    idx, val = ehvi_best(xc, ypar, mobo, objs)
+    assert idx == int(np.argmin(hv)) and abs(val + hv[idx]) <= 1e-14 * abs(val)

@@ -1,4 +1,5 @@
 """CPU: the oracle restatement agrees with the reference's own outputs (tests/golden)."""
+import os
 import numpy as np
 import pytest
 
@@ -110,3 +111,15 @@ def test_pls_rotations_match_sklearn_fixture():
     g = load_golden("kpls")
     W = ko.pls1_rotations(g["X_norm"], g["y"], int(g["n_princomp"]))
     assert relerr(W ** 2, g["plscoeff"] ** 2) < 1e-9
+
+
+def test_exi2d_restatement_matches_the_reference_fixture():
+    """oracle/ehvi_oracle.py against exi2d outputs of the unmodified reference (fronts of 1, 2, 5, 9
+    points, shuffled rows, candidates inside and outside the dominated region)."""
+    from oracle import ehvi_oracle as eo
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ehvi2d.npz"))
+    for c in range(4):
+        got = eo.exi2d(g["P%d" % c], g["r%d" % c], g["mu%d" % c], g["s%d" % c])
+        ref = g["ref%d" % c]
+        assert np.all(ref >= 0) and np.any(ref > 0)
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-12
