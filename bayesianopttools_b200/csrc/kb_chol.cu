@@ -713,7 +713,10 @@ cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* a
   P.tasks = tasks; P.ntasks = ntasks; P.B = B; P.info = info;
   // chain SMs: up to 16; one worker per SM while that covers the population, else two; a
   // worker serves at most 8 candidates
-  int csm = B < 16 ? B : 16;
+  // (measured, B = 64: 16 SMs are best at 16 tile columns, 8 at 32 -- the bulk work per chain step
+  // grows with the column count, so fewer chain SMs keep up)
+  const int csm_cap = g.nb >= 24 ? 8 : (g.nb > 16 ? 12 : 16);
+  int csm = B < csm_cap ? B : csm_cap;
   int wps = (B > csm) ? 2 : 1;
   while (csm * wps * 8 < B && csm < num_sms / 2) ++csm;
   static const char* csm_env = getenv("KB_CHOL_CHAIN_SMS");     // debug aids
