@@ -12,6 +12,8 @@ from scipy.optimize import fmin_cobyla, minimize
 
 from bayesianopttools_b200.misc.sampling.samplingplan import realval
 from .cmaes import fmin_batched
+from .ehvi.EHVIcomputation import ehvi_best, ehvicalc
+from .ga.uncGA import uncGA
 
 
 def sweep_candidates(krigobj, ncand, rng=None):
@@ -22,7 +24,7 @@ def sweep_candidates(krigobj, ncand, rng=None):
 
 def run_single_opt(krigobj, soboInfo, krigconstlist=None, cheapconstlist=None):
     if krigconstlist is not None or cheapconstlist is not None:
-        raise NotImplementedError("constrained acquisition is outside the Kriging hot path")
+        raise NotImplementedError("constrained single-objective acquisition is outside the Kriging hot path")
     acquifuncopt = soboInfo["acquifuncopt"].lower()
     acquifunc = soboInfo["acquifunc"]
     if acquifunc.lower() == "parego":
@@ -65,5 +67,82 @@ def run_single_opt(krigobj, soboInfo, krigconstlist=None, cheapconstlist=None):
             xnextcand[im], fnextcand[im] = r, krigobj.predict(r, acquifunc)
         else:
             raise ValueError(soboInfo["acquifuncopt"], " is not a valid acquisition function optimizer.")
+    I = int(np.argmin(fnextcand))
+    return xnextcand[I, :], fnextcand[I]
+
+
+def _as_list(v):
+    return v if isinstance(v, list) else [v]
+
+
+def multiconstfun(x, ypar, kriglist, moboInfo, krigconstlist=None, cheapconstlist=None):
+    """acquifunc_opt.py:283-334: EHVI scaled by the product of the constraint models' probabilities
+    of feasibility and of the cheap constraints' 0/1 verdicts.  x may be one design or a batch."""
+    x = np.asarray(x, dtype=float)
+    xs = x.reshape(1, -1) if x.ndim == 1 else x
+    fx = np.atleast_1d(ehvicalc(xs, ypar, moboInfo, kriglist)).astype(float)
+    if krigconstlist is not None:
+        for kc in _as_list(krigconstlist):
+            fx = fx * np.asarray(kc.predict(xs, ["PoF"]), dtype=float).ravel()
+    if cheapconstlist is not None:
+        for fn in _as_list(cheapconstlist):
+            fx = fx * np.array([float(fn(row)) for row in xs])
+    return float(fx[0]) if x.ndim == 1 else fx
+
+
+def run_multi_opt(kriglist, moboInfo, ypar, krigconstlist=None, cheapconstlist=None):
+    """Next design by minimising the (negated) expected hypervolume improvement
+    (reference: acquifunc_opt.py:105-211).  `lbfgsb` and `cobyla` are the reference's multi-start local
+    searches on the one-design call; `cmaes` and `ga` evaluate each generation as one batch; `sweep`
+    scores `ncandidates` random designs in one pass (both objective models + the cell sum on the device,
+    only the argmax comes back) and polishes the winner with L-BFGS-B."""
+    opt = moboInfo["acquifuncopt"].lower()
+    if moboInfo["acquifunc"].lower() != "ehvi":
+        raise ValueError("Acquisition function handle is not available")
+    K = kriglist[0].KrigInfo
+    nres, nvar = moboInfo["nrestart"], K["nvar"]
+    lbv, ubv = np.asarray(K["lb"], dtype=float), np.asarray(K["ub"], dtype=float)
+    constrained = krigconstlist is not None or cheapconstlist is not None
+    if constrained:
+        fun, args = multiconstfun, (ypar, kriglist, moboInfo, krigconstlist, cheapconstlist)
+    else:
+        fun, args = ehvicalc, (ypar, moboInfo, kriglist)
+    batch = lambda P: np.asarray(fun(np.atleast_2d(P), *args), dtype=float).ravel()
+
+    if opt == "sweep":
+        cand = sweep_candidates(kriglist[0], moboInfo.get("ncandidates", 1_000_000), moboInfo.get("rng"))
+        if constrained:
+            f = batch(cand)
+            I = int(np.argmin(f))
+            xnext, fnext = cand[I].copy(), float(f[I])
+        else:
+            I, val = ehvi_best(cand, ypar, moboInfo, kriglist)
+            xnext, fnext = cand[I].copy(), -val
+        if moboInfo.get("sweep_polish", True):
+            r = minimize(fun, xnext, method="L-BFGS-B", bounds=np.column_stack((lbv, ubv)), args=args)
+            if r.fun < fnext:
+                xnext, fnext = r.x, float(r.fun)
+        return xnext, fnext
+    if opt == "ga":
+        xnext, fnext, _ = uncGA(batch, lb=lbv, ub=ubv, seed=moboInfo.get("seed"))
+        return xnext, fnext
+
+    Xrand = realval(lbv, ubv, np.random.rand(nres, nvar))
+    xnextcand, fnextcand = np.zeros((nres, nvar)), np.zeros(nres)
+    for im in range(nres):
+        if opt == "cmaes":
+            xnextcand[im], fnextcand[im], _ = fmin_batched(batch, Xrand[im], 1.0)
+        elif opt == "lbfgsb":
+            r = minimize(fun, Xrand[im], method="L-BFGS-B", bounds=np.column_stack((lbv, ubv)), args=args)
+            xnextcand[im], fnextcand[im] = r.x, r.fun
+        elif opt == "cobyla":
+            cons = []
+            for i in range(nvar):
+                cons.append(lambda x, *a, i=i: x[i] - lbv[i])
+                cons.append(lambda x, *a, i=i: ubv[i] - x[i])
+            r = fmin_cobyla(fun, Xrand[im], cons, rhobeg=0.5, rhoend=1e-4, args=args)
+            xnextcand[im], fnextcand[im] = r, fun(r, *args)
+        else:
+            raise ValueError(moboInfo["acquifuncopt"], " is not a valid acquisition function optimizer.")
     I = int(np.argmin(fnextcand))
     return xnextcand[I, :], fnextcand[I]

@@ -266,6 +266,41 @@ def ehvi2d(ref_root="/root/reference"):
     np.savez(_os.path.join(OUT, "ehvi2d.npz"), **out)
 
 
+def mobo_host(ref_root="/root/reference"):
+    """tests/golden/mobo_host.npz: host-side pieces of the reference's multi-objective loop --
+    `paretopoint` (optim_tools/searchpareto.py) on random and duplicated rows, and the two-objective test
+    problems (testcase/analyticalfcn/cases.py).  (`paregopre` cannot be recorded: the reference's `scale`
+    raises under numpy 2.x, samplingplan.py:141.)"""
+    import os as _os
+    from oracle.ref_loader import load_reference
+    load_reference()
+    cwd = _os.getcwd()
+    _os.chdir(_os.path.join(ref_root, "demo"))
+    try:
+        from optim_tools.searchpareto import paretopoint as ref_pp
+        from testcase.analyticalfcn.cases import evaluate as ref_eval
+        rng = np.random.default_rng(21)
+        out = {}
+        for c, m in enumerate((1, 2, 9, 40)):
+            B = rng.uniform(0, 1, (m, 2))
+            if m == 9:
+                B[5] = B[2]                      # duplicated row: the reference drops both copies
+                B[7, 0] = B[1, 0]                # tie in one objective
+            A, idx = ref_pp(B)
+            out["B%d" % c], out["A%d" % c], out["I%d" % c] = B, np.asarray(A), np.asarray(idx)
+        B3 = rng.uniform(0, 1, (25, 3))
+        A, idx = ref_pp(B3)
+        out["B4"], out["A4"], out["I4"] = B3, np.asarray(A), np.asarray(idx)
+        X = rng.uniform(-1, 1, (7, 2))
+        out["X"] = X
+        for t in ("schaffer", "fonseca", "schaffer1"):
+            out["y_" + t] = np.asarray(ref_eval(X, t))
+            out["y1_" + t] = np.asarray(ref_eval(X[0], t))
+    finally:
+        _os.chdir(cwd)
+    np.savez(_os.path.join(OUT, "mobo_host.npz"), **out)
+
+
 if __name__ == "__main__":
     notebook_case("krigdemo_nb", 50, [-0.06768278, -0.06558988, 121.47648552358743,
                                       4.379695408530209, 4.298317119160842])
@@ -290,3 +325,4 @@ if __name__ == "__main__":
     akmcs_case()
     sobol_indices()
     ehvi2d()
+    mobo_host()

@@ -261,3 +261,95 @@ def test_ehvicalc_batch_matches_oracle_predictions_and_argmax():
     assert abs(ehvicalc(xc[17], ypar, mobo, objs) - hv[17]) <= 1e-12 * abs(hv[17])
     idx, val = ehvi_best(xc, ypar, mobo, objs)
     assert idx == int(np.argmin(hv)) and abs(val + hv[idx]) <= 1e-14 * abs(val)
+
+
+def _hv2d(front, ref):
+    f = front[np.argsort(front[:, 0])]
+    h, prev = 0.0, ref[1]
+    for a, b in f:
+        if b < prev:
+            h += (ref[0] - a) * (prev - b)
+            prev = b
+    return h
+
+
+def test_mobo_ehvi_loop_with_believer_and_sweep():
+    """the multi-objective loop end to end on the reference's demo problem
+    (demo/MOBOdemo.py: Schaffer, 2 variables, 20 Halton samples): EHVI maximised by the device sweep,
+    Kriging-believer multi-update (refits at fixed theta), enrichment and retraining.  Checks the
+    bookkeeping the reference returns, that a believer refit equals the ORACLE's likelihood 'all' state on
+    the augmented design, and that the dominated hypervolume grows."""
+    from oracle import kriging_oracle as ko
+    from bayesianopttools_b200.misc.sampling.samplingplan import sampling
+    from bayesianopttools_b200.optim_tools.MOBO import MOBO
+    from bayesianopttools_b200.optim_tools.searchpareto import paretopoint
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    from bayesianopttools_b200.testcase.analyticalfcn.cases import evaluate
+    nvar, n = 2, 20
+    lb, ub = -np.ones(nvar), np.ones(nvar)
+    _, X = sampling("halton", nvar, n, result="real", upbound=ub, lobound=lb)
+    Y = evaluate(X, "schaffer")
+    objs = []
+    for j in range(2):
+        K = initkriginfo("single")
+        K.update(X=X, y=Y[:, j].reshape(-1, 1), problem="schaffer", nrestart=3, ub=ub, lb=lb, optimizer="lbfgsb",
+                 kernel=["gaussian"], nugget=-6, TrendOrder=0)
+        o = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+        o.train(disp=False)
+        objs.append(o)
+    ref = np.array([1.5, 1.5])
+    hv0 = _hv2d(paretopoint(Y)[0], ref)
+    info = {"nup": 2, "nrestart": 2, "acquifunc": "ehvi", "acquifuncopt": "sweep", "ncandidates": 20000,
+            "rng": np.random.default_rng(0), "refpoint": ref, "filename": "/tmp/krigb200_mobo_test.mat"}
+    opt = MOBO(info, objs, autoupdate=True, multiupdate=2, savedata=True)
+    # one believer round on its own first: the refit state must equal the oracle on the augmented design
+    opt.nup, opt.Xall, opt.yall = 0, X, Y.copy()
+    opt.ypar, _ = paretopoint(opt.yall)
+    xs, ys, ss, ms = opt.simultpredehvi()
+    assert xs.shape == (2, nvar) and ys.shape == (2, 2) and ss.shape == (2, 2) and np.all(ms < 0)
+    assert objs[0].KrigInfo["X"].shape[0] == n                       # the believers are copies
+    # full loop
+    xup, yup, sup, metric = opt.run(disp=False)
+    assert xup.shape == (4, nvar) and yup.shape == (4, 2) and sup.shape == (4, 2) and len(metric) == 4
+    assert np.max(np.abs(yup - evaluate(xup, "schaffer"))) < 1e-14    # enrichment stores true evaluations
+    assert objs[0].KrigInfo["X"].shape[0] == n + 4 and objs[1].KrigInfo["y"].shape == (n + 4, 1)
+    assert np.all(xup >= lb - 1e-12) and np.all(xup <= ub + 1e-12)
+    hv1 = _hv2d(opt.ypar, ref)
+    assert hv1 > hv0
+    # retrained models reproduce the oracle's likelihood at their own hyper-parameters
+    for o in objs:
+        KI = o.KrigInfo
+        fit = ko.nll(np.asarray(KI["Theta"]).ravel(), KI["X_norm"], KI["y"], KI["F"], full=True)
+        assert abs(fit["NegLnLike"] - float(np.ravel(KI["NegLnLike"])[0])) <= 1e-9 * abs(fit["NegLnLike"])
+
+
+def test_mobo_parego_loop_runs():
+    """ParEGO branch of the multi-objective loop (MOBO.py:193-240): scalarised model + single-objective
+    acquisition sweep, one and several (different weights) designs per iteration."""
+    from bayesianopttools_b200.misc.sampling.samplingplan import sampling
+    from bayesianopttools_b200.optim_tools.MOBO import MOBO
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    from bayesianopttools_b200.testcase.analyticalfcn.cases import evaluate
+    nvar, n = 2, 16
+    lb, ub = -np.ones(nvar), np.ones(nvar)
+    _, X = sampling("halton", nvar, n, result="real", upbound=ub, lobound=lb)
+    Y = evaluate(X, "schaffer")
+    for multi in (0, 2):
+        objs = []
+        for j in range(2):
+            K = initkriginfo("single")
+            K.update(X=X, y=Y[:, j].reshape(-1, 1), problem="schaffer", nrestart=2, ub=ub, lb=lb,
+                     optimizer="lbfgsb", kernel=["gaussian"], nugget=-6, TrendOrder=0)
+            o = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+            o.train(disp=False)
+            objs.append(o)
+        info = {"nup": 2, "nrestart": 2, "acquifunc": "parego", "acquifuncopt": "sweep", "ncandidates": 5000,
+                "rng": np.random.default_rng(1)}
+        opt = MOBO(info, objs, autoupdate=True, multiupdate=multi, savedata=False)
+        xup, yup, sup, metric = opt.run(disp=False)
+        nnew = 2 * max(1, multi)
+        assert xup.shape == (nnew, nvar) and yup.shape == (nnew, 2) and sup is None
+        assert objs[0].KrigInfo["X"].shape[0] == n + nnew
+        assert np.max(np.abs(yup - evaluate(xup, "schaffer"))) < 1e-14

@@ -119,3 +119,40 @@ def test_sobolnew_sampler_and_sobol_indices_match_reference(golden):
     assert np.allclose(res["total"], g["total"], rtol=1e-12, atol=1e-14)
     assert list(res["second"].keys()) == [str(k) for k in g["second_keys"]]
     assert np.allclose(list(res["second"].values()), g["second_vals"], rtol=1e-9, atol=1e-13)
+
+
+def test_mobo_host_pieces_match_the_reference_fixture():
+    """paretopoint (incl. duplicated rows, ties, 3 objectives, a single row) and the two-objective test
+    problems against outputs of the unmodified reference (tests/golden/mobo_host.npz)."""
+    from bayesianopttools_b200.optim_tools.searchpareto import paretopoint
+    from bayesianopttools_b200.testcase.analyticalfcn.cases import evaluate
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mobo_host.npz"))
+    for c in range(5):
+        A, idx = paretopoint(g["B%d" % c])
+        assert np.array_equal(np.asarray(A), g["A%d" % c]) and np.array_equal(np.asarray(idx), g["I%d" % c])
+    for t in ("schaffer", "fonseca", "schaffer1"):
+        assert np.max(np.abs(evaluate(g["X"], t) - g["y_" + t])) < 1e-15
+        y1 = evaluate(g["X"][0], t)
+        assert y1.shape == g["y1_" + t].shape and np.max(np.abs(y1 - g["y1_" + t])) < 1e-15
+
+
+def test_paregopre_and_moboinfocheck_defaults():
+    from bayesianopttools_b200.optim_tools.MOBO import moboinfocheck
+    from bayesianopttools_b200.optim_tools.parego import paregopre
+    Y = np.array([[0.0, 4.0], [1.0, 2.0], [2.0, 0.0]])
+    # weights (0.3, 0.7) on objectives scaled to [0, 1]: max(w f) + 0.05 sum(w f)   (parego.py:14-29)
+    F = np.array([[0.0, 1.0], [0.5, 0.5], [1.0, 0.0]])
+    want = np.max(F * [0.3, 0.7], axis=1) + 0.05 * np.sum(F * [0.3, 0.7], axis=1)
+    assert np.allclose(paregopre(Y, 3).ravel(), want, rtol=0, atol=1e-15)
+    assert paregopre(Y).shape == (3, 1)
+    info = moboinfocheck({"nup": 3}, True)
+    assert info["acquifunc"] == "EHVI" and info["refpointtype"] == "dynamic" and info["acquifuncopt"] == "lbfgsb"
+    assert info["nrestart"] == 1 and info["filename"] == "temporarydata.mat"
+    assert moboinfocheck({"nup": 3, "refpoint": np.array([1.0, 1.0])}, True)["refpointtype"] == "static"
+    assert moboinfocheck({"nup": 5}, False)["nup"] == 1
+    with pytest.raises(ValueError):
+        moboinfocheck({}, True)
+    with pytest.raises(ValueError):
+        moboinfocheck({"nup": 1, "acquifunc": "nsga"}, True)
+    p = moboinfocheck({"nup": 1, "acquifunc": "parego"}, True)
+    assert p["paregoacquifunc"] == "EI" and p["krignum"] == 1
