@@ -73,6 +73,8 @@ _SIGNATURES = [
     ("kb_points_destroy", None, [C.c_void_p]),
     ("kb_points_generate", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_double,
                                      C.c_double, c_double_p, c_double_p, C.c_ulonglong, C.c_longlong]),
+    ("kb_points_generate_lowdisc", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_int,
+                                             C.POINTER(C.c_uint), c_double_p, c_double_p, C.c_longlong]),
     ("kb_points_get_rows", C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     ("kb_predict_points", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AcqParams), C.POINTER(c_double_p), C.c_int,
                                     C.POINTER(SweepResult)]),
@@ -80,6 +82,8 @@ _SIGNATURES = [
                            c_double_p]),
     ("kb_ehvi2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, c_double_p, C.c_int, c_double_p, c_double_p,
                             C.c_int, c_double_p, C.POINTER(C.c_longlong), c_double_p]),
+    ("kb_ehvi2d_points", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int,
+                                   c_double_p, C.POINTER(C.c_longlong), c_double_p]),
     ("kb_loocv", C.c_int, [C.c_void_p, c_double_p]),
     ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  C.c_int, C.c_int, c_double_p, c_double_p]),
@@ -293,7 +297,8 @@ class DevicePoints:
     """A point set resident on the device (kb_points): uploaded once, swept many times -- the fixed
     Monte-Carlo population of AK-MCS (akmcs.py:66-206)."""
 
-    DISTS = {"normal": 0, "gaussian": 0, "lognormal": 1, "gumbel": 2, "random": 3, "uniform": 3}
+    DISTS = {"normal": 0, "gaussian": 0, "lognormal": 1, "gumbel": 2, "random": 3, "uniform": 3, "halton": 4,
+             "sobol": 5, "sobolnew": 5}
 
     def __init__(self, x, device=None):
         require_gpu()
@@ -308,7 +313,10 @@ class DevicePoints:
     @classmethod
     def generate(cls, n, d, dist="gaussian", mean=0.0, stddev=1.0, lb=None, ub=None, seed=0, first_index=0,
                  device=None):
-        """Population generated on the device (Philox4x32-10, reproducible per site index)."""
+        """Point set generated on the device: random variates from the counter-based Philox4x32-10
+        generator (reproducible per site index), or the 'halton' / 'sobol' designs of misc/sampling
+        (bit-identical to the host samplers; site i is the sequence's point first_index + i), mapped to
+        [lb, ub] when bounds are given."""
         require_gpu()
         self = cls.__new__(cls)
         self._lib = load()
@@ -316,6 +324,22 @@ class DevicePoints:
         self.device = default_device() if device is None else int(device)
         kind = cls.DISTS[dist.lower()]
         lbp = ubp = None
+        if kind >= 4:
+            if (lb is None) != (ub is None):
+                raise ValueError("give both bounds or neither")
+            if lb is not None:
+                lb_, ub_ = _f64(np.asarray(lb).reshape(-1)), _f64(np.asarray(ub).reshape(-1))
+                lbp, ubp = _dp(lb_), _dp(ub_)
+            dirs = None
+            if kind == 5:
+                from .misc.sampling.samplingplan import sobol_direction_numbers
+                dirs_ = np.ascontiguousarray(sobol_direction_numbers(self.d, 32), dtype=np.uint32)
+                dirs = dirs_.ctypes.data_as(C.POINTER(C.c_uint))
+            h = C.c_void_p()
+            check(self._lib.kb_points_generate_lowdisc(C.byref(h), self.device, self.n, self.d, kind, dirs, lbp, ubp,
+                                                       int(first_index)))
+            self._h = h
+            return self
         if kind == 3:
             if lb is None or ub is None:
                 raise ValueError("type 'random' is selected, please input lower bound and upper bound value")
@@ -395,15 +419,22 @@ def exi2d_batch(front, ref, mu, s, device=None):
 
 def ehvi2d_models(model1, model2, x, front, ref, spread="ssqr", want_values=True):
     """Batched `ehvicalc` (optim_tools/ehvi/EHVIcomputation.py:10-42): both fitted DeviceModels predict
-    the raw candidates x (m, d); returns (improvement per candidate or None, argmax index, max value)."""
-    x = _f64(np.atleast_2d(x))
+    the raw candidates x ((m, d) host array or a DevicePoints set); returns (improvement per candidate or None, argmax index, max value)."""
     front = _f64(np.atleast_2d(front))
     ref = _f64(np.asarray(ref).reshape(-1))
     if front.shape[1] != 2 or ref.size != 2:
         raise ValueError("ehvi2d handles two objectives: P (k, 2), r (2,)")
-    out = np.empty(x.shape[0]) if want_values else None
     bi, bv = C.c_longlong(-1), C.c_double(0.0)
+    sp = 0 if spread.lower() == "ssqr" else 1
+    if isinstance(x, DevicePoints):
+        out = np.empty(x.n) if want_values else None
+        check(model1._lib.kb_ehvi2d_points(model1._h, model2._h, x._h, front.shape[0], _dp(front), _dp(ref), sp,
+                                           _dp(out) if out is not None else None, C.byref(bi),
+                                           C.cast(C.byref(bv), c_double_p)))
+        return out, int(bi.value), float(bv.value)
+    x = _f64(np.atleast_2d(x))
+    out = np.empty(x.shape[0]) if want_values else None
     check(model1._lib.kb_ehvi2d(model1._h, model2._h, x.shape[0], _dp(x), front.shape[0], _dp(front), _dp(ref),
-                                0 if spread.lower() == "ssqr" else 1, _dp(out) if out is not None else None,
+                                sp, _dp(out) if out is not None else None,
                                 C.byref(bi), C.cast(C.byref(bv), c_double_p)))
     return out, int(bi.value), float(bv.value)

@@ -707,6 +707,58 @@ kb_status kb_points_generate(kb_points** out, int device, long long npts, int d,
   return KB_OK;
 }
 
+kb_status kb_points_generate_lowdisc(kb_points** out, int device, long long npts, int d, int kind,
+                                     const unsigned int* dirs, const double* lb, const double* ub,
+                                     long long first_index) {
+  if (!out || npts < 1 || d < 1 || first_index < 0 || (kind != KB_DIST_HALTON && kind != KB_DIST_SOBOL))
+    KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (kind == KB_DIST_SOBOL && !dirs) KB_FAIL(KB_ERR_INVALID, "the Sobol generator needs the direction numbers");
+  if ((lb == nullptr) != (ub == nullptr)) KB_FAIL(KB_ERR_INVALID, "give both bounds or neither");
+  if (kind == KB_DIST_SOBOL && first_index + npts > (1LL << 32))
+    KB_FAIL(KB_ERR_INVALID, "32-bit direction numbers cover 2^32 Sobol points");
+  if (kb_device_count() == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: no CPU fallback");
+  CK(cudaSetDevice(device));
+  std::vector<int> primes;
+  if (kind == KB_DIST_HALTON)
+    for (int c = 2; (int)primes.size() < d; ++c) {
+      bool is_prime = true;
+      for (int p : primes) if (c % p == 0) { is_prime = false; break; }
+      if (is_prime) primes.push_back(c);
+    }
+  kb_points* p = new kb_points();
+  p->device = device; p->d = d; p->npts = npts;
+  unsigned int* dirs_dev = nullptr;
+  int* primes_dev = nullptr;
+  double* bounds = nullptr;
+  cudaError_t e = cudaMalloc(&p->x, sizeof(double) * (size_t)npts * d);
+  if (e == cudaSuccess && kind == KB_DIST_SOBOL) {
+    e = cudaMalloc(&dirs_dev, sizeof(unsigned int) * 32 * d);
+    if (e == cudaSuccess) e = cudaMemcpy(dirs_dev, dirs, sizeof(unsigned int) * 32 * d, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && kind == KB_DIST_HALTON) {
+    e = cudaMalloc(&primes_dev, sizeof(int) * d);
+    if (e == cudaSuccess) e = cudaMemcpy(primes_dev, primes.data(), sizeof(int) * d, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && lb) {
+    e = cudaMalloc(&bounds, sizeof(double) * 2 * d);
+    if (e == cudaSuccess) e = cudaMemcpy(bounds, lb, sizeof(double) * d, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(bounds + d, ub, sizeof(double) * d, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess)
+    e = kb_launch_points_lowdisc(nullptr, p->x, npts, d, kind, dirs_dev, primes_dev, bounds, bounds ? bounds + d : nullptr,
+                                 first_index);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(dirs_dev); cudaFree(primes_dev); cudaFree(bounds);
+  g_launches += 1;
+  if (e != cudaSuccess) {
+    cudaFree(p->x);
+    delete p;
+    KB_FAIL(KB_ERR_CUDA, "low-discrepancy generator: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return KB_OK;
+}
+
 kb_status kb_points_get_rows(const kb_points* p, long long row0, long long nrows, double* x_out) {
   if (!p || !x_out || row0 < 0 || nrows < 1 || row0 + nrows > p->npts) KB_FAIL(KB_ERR_INVALID, "bad row range");
   CK(cudaSetDevice(p->device));
@@ -816,8 +868,9 @@ kb_status kb_exi2d(int device, long long npts, const double* mu, const double* s
   return KB_OK;
 }
 
-kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x, int k, const double* front,
-                    const double* ref, int spread, double* out, long long* best_idx, double* best_val) {
+static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const double* x, bool x_on_device, int k,
+                             const double* front, const double* ref, int spread, double* out, long long* best_idx,
+                             double* best_val) {
   if (!m1 || !m2 || !x || npts < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
   if (m1->device != m2->device || m1->d != m2->d)
     KB_FAIL(KB_ERR_INVALID, "the two objective models must share the device and the input dimension");
@@ -832,7 +885,7 @@ kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x,
   double *xd = nullptr, *buf = nullptr;
   void* red = nullptr;
   cudaEvent_t ev_x = nullptr, ev_p2 = nullptr;
-  cudaError_t e = cudaMalloc(&xd, sizeof(double) * (size_t)chunk * d);
+  cudaError_t e = x_on_device ? cudaSuccess : cudaMalloc(&xd, sizeof(double) * (size_t)chunk * d);
   if (e == cudaSuccess) e = cudaMalloc(&buf, sizeof(double) * (size_t)5 * chunk);
   if (e == cudaSuccess) e = cudaMalloc(&red, sizeof(KbEhviBestHost) * (size_t)(grid + 1));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming);
@@ -842,8 +895,12 @@ kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x,
     const long long cur = (npts - off < chunk) ? (npts - off) : chunk;
     // the second model's sweep of the previous chunk must be done with xd before it is overwritten
     e = cudaStreamWaitEvent(m1->stream, ev_p2, 0);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(xd, x + (size_t)off * d, sizeof(double) * (size_t)cur * d, cudaMemcpyHostToDevice, m1->stream);
+    const double* xc = x + (size_t)off * d;
+    if (!x_on_device) {
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(xd, xc, sizeof(double) * (size_t)cur * d, cudaMemcpyHostToDevice, m1->stream);
+      xc = xd;
+    }
     if (e == cudaSuccess) e = cudaEventRecord(ev_x, m1->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(m2->stream, ev_x, 0);
     if (e != cudaSuccess) break;
@@ -852,8 +909,8 @@ kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x,
     o1[KB_OUT_PRED] = buf; o1[sid] = buf + chunk;
     o2[KB_OUT_PRED] = buf + 2 * chunk; o2[sid] = buf + 3 * chunk;
     // the two objective models sweep the chunk concurrently on their own streams
-    st = kb_predict_dev(m1, cur, xd, off, nullptr, o1, KB_OUT_PRED, nullptr);
-    if (st == KB_OK) st = kb_predict_dev(m2, cur, xd, off, nullptr, o2, KB_OUT_PRED, nullptr);
+    st = kb_predict_dev(m1, cur, xc, off, nullptr, o1, KB_OUT_PRED, nullptr);
+    if (st == KB_OK) st = kb_predict_dev(m2, cur, xc, off, nullptr, o2, KB_OUT_PRED, nullptr);
     if (st != KB_OK) break;
     e = cudaEventRecord(ev_p2, m2->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(m1->stream, ev_p2, 0);
@@ -877,6 +934,20 @@ kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x,
   if (best_idx) *best_idx = best.idx;
   if (best_val) *best_val = best.val;
   return KB_OK;
+}
+
+kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x, int k, const double* front,
+                    const double* ref, int spread, double* out, long long* best_idx, double* best_val) {
+  return ehvi2d_core(m1, m2, npts, x, false, k, front, ref, spread, out, best_idx, best_val);
+}
+
+kb_status kb_ehvi2d_points(kb_model* m1, kb_model* m2, const kb_points* pts, int k, const double* front,
+                           const double* ref, int spread, double* out, long long* best_idx, double* best_val) {
+  if (!m1 || !pts) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if (pts->device != m1->device || pts->d != m1->d)
+    KB_FAIL(KB_ERR_INVALID, "point set (device %d, d=%d) does not match the model (device %d, d=%d)", pts->device,
+            pts->d, m1->device, m1->d);
+  return ehvi2d_core(m1, m2, pts->npts, pts->x, true, k, front, ref, spread, out, best_idx, best_val);
 }
 
 kb_status kb_loocv(kb_model* m, double* pred_out) {

@@ -142,6 +142,10 @@ cudaError_t kb_launch_points_generate(cudaStream_t st, double* x, long long npts
                                       const double* lb_dev, const double* ub_dev, unsigned long long seed,
                                       long long first_index);
 
+cudaError_t kb_launch_points_lowdisc(cudaStream_t st, double* x, long long npts, int d, int kind,
+                                     const unsigned int* dirs_dev, const int* primes_dev, const double* lb_dev,
+                                     const double* ub_dev, long long first_index);
+
 // kb_ehvi.cu: 2-objective expected hypervolume improvement (exi2d.py:6-83)
 size_t kb_ehvi_table_doubles(int k);
 void kb_ehvi_build_table(int k, const double* front, const double* ref, double* table);

@@ -75,3 +75,59 @@ cudaError_t kb_launch_points_generate(cudaStream_t st, double* x, long long npts
   kb_points_generate_kernel<<<148 * 8, 256, 0, st>>>(x, npts, d, dist, p0, p1, lb_dev, ub_dev, seed, first_index);
   return cudaGetLastError();
 }
+
+
+// ---- low-discrepancy designs on the device (misc/sampling: halton, sobolnew) -------------------------
+// Site i of either sequence is a pure function of i, so shards are generated independently
+// (first_index) and any subset is reproducible on the host bit for bit:
+//  * Halton (haltonsampling.py:30-40): radical inverse of i in the k-th prime base, accumulated in the
+//    reference's order (f /= base; r += f * digit) with IEEE division;
+//  * Sobol (sobol_new.py:5-98, Joe & Kuo direction numbers): x_i = XOR of v[b + 1] over the set bits b of
+//    the Gray code i ^ (i >> 1), the closed form of the reference's cumulative XOR; the 32 direction
+//    numbers per dimension come from the host (they depend on the Joe-Kuo table, which the library does
+//    not embed).
+// Both are mapped to [lb, ub] as realval does: u * (ub - lb) + lb with separate roundings (no FMA).
+__global__ void kb_points_lowdisc_kernel(double* __restrict__ x, long long npts, int d, int kind,
+                                         const unsigned int* __restrict__ dirs, const int* __restrict__ primes,
+                                         const double* __restrict__ lb, const double* __restrict__ ub,
+                                         long long first_index) {
+  const long long total = npts * d;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / d;
+    const int j = (int)(e - i * d);
+    const unsigned long long gi = (unsigned long long)(i + first_index);
+    double u;
+    if (kind == KB_DIST_HALTON) {
+      const unsigned long long base = (unsigned long long)primes[j];
+      const double fb = (double)base;
+      double f = 1.0, r = 0.0;
+      unsigned long long k = gi;
+      while (k > 0) {
+        const unsigned long long q = k / base, rem = k - q * base;
+        k = q;
+        f = __ddiv_rn(f, fb);
+        r = __dadd_rn(r, __dmul_rn(f, (double)rem));
+      }
+      u = r;
+    } else {
+      unsigned long long g = gi ^ (gi >> 1);
+      unsigned int acc = 0;
+      const unsigned int* v = dirs + (size_t)j * 32;
+      while (g) {
+        const int b = __ffsll((long long)g) - 1;
+        acc ^= v[b];
+        g &= g - 1;
+      }
+      u = (double)acc * 2.3283064365386963e-10;          // / 2^32, exact
+    }
+    x[e] = lb ? __dadd_rn(__dmul_rn(u, __dsub_rn(ub[j], lb[j])), lb[j]) : u;
+  }
+}
+
+cudaError_t kb_launch_points_lowdisc(cudaStream_t st, double* x, long long npts, int d, int kind,
+                                     const unsigned int* dirs_dev, const int* primes_dev, const double* lb_dev,
+                                     const double* ub_dev, long long first_index) {
+  kb_points_lowdisc_kernel<<<148 * 8, 256, 0, st>>>(x, npts, d, kind, dirs_dev, primes_dev, lb_dev, ub_dev, first_index);
+  return cudaGetLastError();
+}

@@ -38,6 +38,39 @@ def sobol(nvar, nsamp):
 _JK = None
 
 
+def _joekuo():
+    global _JK
+    if _JK is None:
+        _JK = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sobol_joekuo_256.npy"))
+    return _JK
+
+
+def sobol_direction_numbers(d, L=32):
+    """The first L 32-bit direction numbers v_1..v_L (v_k = m_k << (32 - k)) of the first d Joe & Kuo
+    dimensions, shape (d, L) uint64 (sobol_new.py:44-80).  Also the table handed to the device generator
+    (`_lib.DevicePoints.generate(dist='sobol')`)."""
+    JK = _joekuo()
+    if d - 1 > len(JK):
+        raise ValueError("sobolnew supports up to %d dimensions" % (len(JK) + 1))
+    V = np.zeros((d, L), dtype=np.uint64)
+    for j in range(d):
+        v = [0] * (L + 1)
+        if j == 0:
+            for i in range(1, L + 1):
+                v[i] = 1 << (32 - i)
+        else:
+            s_, a_ = int(JK[j - 1, 0]), int(JK[j - 1, 1])
+            m = [0] + [int(x) for x in JK[j - 1, 2:2 + s_]]
+            for i in range(1, min(L, s_) + 1):
+                v[i] = m[i] << (32 - i)
+            for i in range(s_ + 1, L + 1):
+                v[i] = v[i - s_] ^ (v[i - s_] >> s_)
+                for k in range(1, s_):
+                    v[i] ^= ((a_ >> (s_ - 1 - k)) & 1) * v[i - k]
+        V[j] = v[1:]
+    return V
+
+
 def sobol_points(n, d):
     """Joe & Kuo Sobol points in Gray-code order, first point 0 (reference: misc/sampling/sobol_new.py:5-98,
     the `sobolnew` option; direction numbers new-joe-kuo-6.21201, first 257 dimensions packed in
@@ -46,12 +79,7 @@ def sobol_points(n, d):
     x_0 = 0, x_i = x_{i-1} XOR v[c_{i-1}] with c_i = 1 + index of the lowest zero bit of i and the
     32-bit direction numbers v_k = m_k << (32 - k), m_k from the primitive-polynomial recurrence
     m_k = m_{k-s} XOR (m_{k-s} << s ... ) (Joe & Kuo 2008)."""
-    global _JK
     n, d = int(n), int(d)
-    if _JK is None:
-        _JK = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sobol_joekuo_256.npy"))
-    if d - 1 > len(_JK):
-        raise ValueError("sobolnew supports up to %d dimensions" % (len(_JK) + 1))
     L = max(int(np.ceil(np.log(n) / np.log(2.0))), 1)
     idx = np.arange(n, dtype=np.int64)
     c = np.ones(n, dtype=np.int64)              # 1 + number of trailing one bits of i
@@ -63,20 +91,9 @@ def sobol_points(n, d):
         c[odd] += 1
         t[odd] >>= 1
     pts = np.zeros((n, d))
+    V = sobol_direction_numbers(d, L)
     for j in range(d):
-        v = np.zeros(L + 2, dtype=np.int64)
-        if j == 0:
-            for i in range(1, L + 1):
-                v[i] = 1 << (32 - i)
-        else:
-            s_, a_ = int(_JK[j - 1, 0]), int(_JK[j - 1, 1])
-            m = [0] + [int(x) for x in _JK[j - 1, 2:2 + s_]]
-            for i in range(1, min(L, s_) + 1):
-                v[i] = m[i] << (32 - i)
-            for i in range(s_ + 1, L + 1):
-                v[i] = v[i - s_] ^ (v[i - s_] >> s_)
-                for k in range(1, s_):
-                    v[i] ^= ((a_ >> (s_ - 1 - k)) & 1) * v[i - k]
+        v = np.concatenate(([0], V[j], [0])).astype(np.int64)
         # x_i = XOR of v[c_0..c_{i-1}]: cumulative XOR along the sequence
         steps = v[c[:-1]] if n > 1 else np.zeros(0, dtype=np.int64)
         x = np.zeros(n, dtype=np.int64)

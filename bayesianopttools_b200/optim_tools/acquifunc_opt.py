@@ -16,10 +16,26 @@ from .ehvi.EHVIcomputation import ehvi_best, ehvicalc
 from .ga.uncGA import uncGA
 
 
-def sweep_candidates(krigobj, ncand, rng=None):
-    rng = np.random.default_rng() if rng is None else rng
+_sweep_calls = 0
+
+
+def sweep_candidates(krigobj, ncand, rng=None, sampler="sobol", seed=None):
+    """Candidate designs of the `sweep` optimisers.  Default: a Sobol design generated ON the device
+    (no host->device copy of the candidates; a different stretch of the sequence on every call so that
+    successive updates do not re-score the same sites); `sampler='random'` draws device Philox uniforms;
+    a caller-supplied numpy `rng` keeps everything on the host (reproducible tests)."""
+    global _sweep_calls
     K = krigobj.KrigInfo
-    return realval(K["lb"], K["ub"], rng.random((int(ncand), K["nvar"])))
+    if rng is not None:
+        return realval(K["lb"], K["ub"], rng.random((int(ncand), K["nvar"])))
+    from .. import _lib
+    call = _sweep_calls
+    _sweep_calls += 1
+    if sampler.lower() == "random":
+        return _lib.DevicePoints.generate(int(ncand), K["nvar"], dist="random", lb=K["lb"], ub=K["ub"],
+                                          seed=call if seed is None else seed)
+    first = 1 + (call * int(ncand)) % max(1, (1 << 32) - 2 * int(ncand))
+    return _lib.DevicePoints.generate(int(ncand), K["nvar"], dist="sobol", lb=K["lb"], ub=K["ub"], first_index=first)
 
 
 def run_single_opt(krigobj, soboInfo, krigconstlist=None, cheapconstlist=None):
@@ -36,9 +52,10 @@ def run_single_opt(krigobj, soboInfo, krigconstlist=None, cheapconstlist=None):
     lbv, ubv = np.asarray(K["lb"], dtype=float), np.asarray(K["ub"], dtype=float)
 
     if acquifuncopt == "sweep":
-        cand = sweep_candidates(krigobj, soboInfo.get("ncandidates", 1_000_000), soboInfo.get("rng"))
+        cand = sweep_candidates(krigobj, soboInfo.get("ncandidates", 1_000_000), soboInfo.get("rng"),
+                                soboInfo.get("sweep_sampler", "sobol"), soboInfo.get("seed"))
         res, _ = krigobj.predict_sweep(cand, acq=acquifunc)
-        xnext, fnext = cand[res["best_idx"]].copy(), res["best_val"]
+        xnext, fnext = np.array(cand[res["best_idx"]], dtype=float), res["best_val"]
         if soboInfo.get("sweep_polish", True):
             r = minimize(krigobj.predict, xnext, method="L-BFGS-B", bounds=np.column_stack((lbv, ubv)),
                          args=(acquifunc,))
@@ -110,14 +127,17 @@ def run_multi_opt(kriglist, moboInfo, ypar, krigconstlist=None, cheapconstlist=N
     batch = lambda P: np.asarray(fun(np.atleast_2d(P), *args), dtype=float).ravel()
 
     if opt == "sweep":
-        cand = sweep_candidates(kriglist[0], moboInfo.get("ncandidates", 1_000_000), moboInfo.get("rng"))
-        if constrained:
+        if constrained:          # constraint callbacks need the candidates on the host
+            cand = sweep_candidates(kriglist[0], moboInfo.get("ncandidates", 100_000),
+                                    moboInfo.get("rng") or np.random.default_rng(moboInfo.get("seed")))
             f = batch(cand)
             I = int(np.argmin(f))
             xnext, fnext = cand[I].copy(), float(f[I])
         else:
+            cand = sweep_candidates(kriglist[0], moboInfo.get("ncandidates", 1_000_000), moboInfo.get("rng"),
+                                    moboInfo.get("sweep_sampler", "sobol"), moboInfo.get("seed"))
             I, val = ehvi_best(cand, ypar, moboInfo, kriglist)
-            xnext, fnext = cand[I].copy(), -val
+            xnext, fnext = np.array(cand[I], dtype=float), -val
         if moboInfo.get("sweep_polish", True):
             r = minimize(fun, xnext, method="L-BFGS-B", bounds=np.column_stack((lbv, ubv)), args=args)
             if r.fun < fnext:

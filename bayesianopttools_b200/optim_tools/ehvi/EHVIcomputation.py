@@ -43,9 +43,9 @@ def EHVI(x, ypar, moboInfo, kriglist):
 
 
 def ehvi_best(x, ypar, moboInfo, kriglist):
-    """Candidate of the batch x (m, d) with the largest expected improvement: (index, value); only the
+    """Candidate of the batch x ((m, d) array or a device-resident point set) with the largest expected improvement: (index, value); only the
     16-byte reduction leaves the device."""
     m1, m2 = _device_models(kriglist)
-    _, idx, val = _lib.ehvi2d_models(m1, m2, np.asarray(x, dtype=float), ypar, moboInfo["refpoint"], spread="ssqr",
-                                     want_values=False)
+    xs = x if isinstance(x, _lib.DevicePoints) else np.asarray(x, dtype=float)
+    _, idx, val = _lib.ehvi2d_models(m1, m2, xs, ypar, moboInfo["refpoint"], spread="ssqr", want_values=False)
     return idx, val

@@ -136,9 +136,19 @@ void kb_points_destroy(kb_points* p);
  * multi-GPU population are generated independently (first_index = global index of site 0).
  * dist: KB_DIST_NORMAL (p0 = mean, p1 = stddev), KB_DIST_LOGNORMAL (mean, stddev of the variable),
  * KB_DIST_GUMBEL (mean, stddev), KB_DIST_UNIFORM (per-dimension lb, ub). */
-enum { KB_DIST_NORMAL = 0, KB_DIST_LOGNORMAL = 1, KB_DIST_GUMBEL = 2, KB_DIST_UNIFORM = 3 };
+enum { KB_DIST_NORMAL = 0, KB_DIST_LOGNORMAL = 1, KB_DIST_GUMBEL = 2, KB_DIST_UNIFORM = 3, KB_DIST_HALTON = 4,
+       KB_DIST_SOBOL = 5 };
 kb_status kb_points_generate(kb_points** out, int device, long long npts, int d, int dist, double p0, double p1,
                              const double* lb, const double* ub, unsigned long long seed, long long first_index);
+/* Low-discrepancy designs generated on the device, bit-identical to the reference's host samplers
+ * (`sampling('halton' | 'sobolnew', ...)`, misc/sampling/haltonsampling.py:30-40, sobol_new.py:5-98) and
+ * mapped to [lb, ub] as `realval` does (lb = ub = NULL: unit cube).  kind = KB_DIST_HALTON (dirs unused)
+ * or KB_DIST_SOBOL with dirs = the 32 direction numbers v_1..v_32 (as 32-bit integers, v_k = m_k << (32-k))
+ * of each of the d dimensions, d x 32 row-major; site i is the sequence's point first_index + i
+ * (point 0 is the origin). */
+kb_status kb_points_generate_lowdisc(kb_points** out, int device, long long npts, int d, int kind,
+                                     const unsigned int* dirs, const double* lb, const double* ub,
+                                     long long first_index);
 /* Copy rows [row0, row0 + nrows) of a point set to the host (e.g. the site picked by the arg-min). */
 kb_status kb_points_get_rows(const kb_points* p, long long row0, long long nrows, double* x_out);
 /* Same outputs/reductions as kb_predict over a resident point set; outs[k] are HOST buffers of
@@ -161,6 +171,9 @@ kb_status kb_exi2d(int device, long long npts, const double* mu, const double* s
                    const double* ref, double* out);
 kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x, int k, const double* front,
                     const double* ref, int spread, double* out, long long* best_idx, double* best_val);
+/* kb_ehvi2d over a device-resident point set (no host->device copy of the candidates). */
+kb_status kb_ehvi2d_points(kb_model* m1, kb_model* m2, const kb_points* pts, int k, const double* front,
+                           const double* ref, int spread, double* out, long long* best_idx, double* best_val);
 
 /* Leave-one-out predictions at the fitted hyper-parameters, pred_out[n].  Replaces the n
  * refits + n single-site predictions of loocv2 (krigloocv2.py:7-33) with the closed form

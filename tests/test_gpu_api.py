@@ -301,7 +301,7 @@ def test_mobo_ehvi_loop_with_believer_and_sweep():
     ref = np.array([1.5, 1.5])
     hv0 = _hv2d(paretopoint(Y)[0], ref)
     info = {"nup": 2, "nrestart": 2, "acquifunc": "ehvi", "acquifuncopt": "sweep", "ncandidates": 20000,
-            "rng": np.random.default_rng(0), "refpoint": ref, "filename": "/tmp/krigb200_mobo_test.mat"}
+            "refpoint": ref, "filename": "/tmp/krigb200_mobo_test.mat"}       # candidates: device Sobol design
     opt = MOBO(info, objs, autoupdate=True, multiupdate=2, savedata=True)
     # one believer round on its own first: the refit state must equal the oracle on the augmented design
     opt.nup, opt.Xall, opt.yall = 0, X, Y.copy()

@@ -270,3 +270,46 @@ def test_akmcs_runs_on_a_device_generated_population(lib):
     b.run(disp=False)
     assert a.Pf == b.Pf and a.minU == b.minU and np.array_equal(a.xnew, b.xnew)
     assert a.stop_criteria == b.stop_criteria and a.updateX.shape == (2, 2)
+
+
+@pytest.mark.parametrize("kind,d,first", [("halton", 3, 0), ("halton", 7, 12345), ("sobol", 1, 0), ("sobol", 10, 0),
+                                           ("sobol", 40, 777)])
+def test_device_lowdiscrepancy_designs_are_bit_identical_to_host_samplers(lib, kind, d, first):
+    """SURVEY section 8(f) row 4 (device-side generators): the Halton / Joe-Kuo Sobol designs produced on
+    the device equal the host samplers of misc/sampling bit for bit (those are pinned to the reference by
+    the CPU fixtures), on the unit cube and mapped to a box, from any starting index."""
+    from bayesianopttools_b200.misc.sampling.samplingplan import halton, realval, sobol_points
+    n = 5000
+    host = (halton(d, first + n) if kind == "halton" else sobol_points(first + n, d))[first:]
+    pts = lib.DevicePoints.generate(n, d, dist=kind, first_index=first)
+    assert np.array_equal(pts.rows(0, n), host)
+    lb, ub = -np.arange(1.0, d + 1), 0.5 + np.arange(d)
+    box = lib.DevicePoints.generate(n, d, dist=kind, lb=lb, ub=ub, first_index=first)
+    assert np.array_equal(box.rows(0, n), realval(lb, ub, host))
+    pts.close(); box.close()
+
+
+def test_ehvi_over_resident_points_equals_host_buffer_call(lib):
+    """kb_ehvi2d_points (candidates generated and kept on the device) returns the same values and the
+    same argmax as kb_ehvi2d on the host copy of those candidates."""
+    rng = np.random.default_rng(6)
+    n, d = 50, 3
+    X = rng.uniform(-1, 1, (n, d))
+    mdls = []
+    for j in range(2):
+        y = np.sum((X - 0.3 * j) ** 2, axis=1) * (1 - 2 * j) + 2 * j
+        m = lib.DeviceModel(X, y, np.ones((n, 1)), ["gaussian"])
+        m.fit_state(np.full(d, -0.2), False, -6.0, want_U=False, want_Psi=False)
+        m.set_norm(lib.NORM_NONE)
+        mdls.append(m)
+    f1 = np.sort(rng.uniform(0, 1, 6))
+    P = np.column_stack([f1, np.sort(rng.uniform(-1, 1, 6))[::-1]])
+    r = np.array([1.5, 1.5])
+    pts = lib.DevicePoints.generate(30000, d, dist="sobol", lb=-np.ones(d), ub=np.ones(d), first_index=1)
+    vd, id_, bd = lib.ehvi2d_models(mdls[0], mdls[1], pts, P, r)
+    vh, ih, bh = lib.ehvi2d_models(mdls[0], mdls[1], pts.rows(0, pts.n), P, r)
+    assert np.array_equal(vd, vh) and id_ == ih and bd == bh
+    assert id_ == int(np.argmax(vd)) and bd == vd[id_] and bd > 0
+    pts.close()
+    for m in mdls:
+        m.close()
