@@ -28,6 +28,11 @@ class AcqParams(C.Structure):
                 ("sigmalcb", C.c_double)]
 
 
+class CmaesOpts(C.Structure):
+    _fields_ = [("popsize", C.c_int), ("maxiter", C.c_int), ("check_every", C.c_int), ("sigma0", C.c_double),
+                ("tolfun", C.c_double), ("tolx", C.c_double), ("seed", C.c_ulonglong)]
+
+
 class SweepResult(C.Structure):
     _fields_ = [("best_val", C.c_double), ("best_idx", C.c_longlong), ("min_u", C.c_double),
                 ("min_u_idx", C.c_longlong), ("n_fail", C.c_longlong), ("n_fail_minus", C.c_longlong),
@@ -84,6 +89,8 @@ _SIGNATURES = [
                             C.c_int, c_double_p, C.POINTER(C.c_longlong), c_double_p]),
     ("kb_ehvi2d_points", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int,
                                    c_double_p, C.POINTER(C.c_longlong), c_double_p]),
+    ("kb_train_cmaes", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p, c_double_p,
+                                 c_double_p, C.c_void_p, c_double_p, c_double_p, c_int_p, c_int_p, c_double_p]),
     ("kb_loocv", C.c_int, [C.c_void_p, c_double_p]),
     ("kb_corr_matrix", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  C.c_int, C.c_int, c_double_p, c_double_p]),
@@ -199,6 +206,26 @@ class DeviceModel:
         s2 = np.empty(B)
         check(self._lib.kb_nll_batch_extras(self._h, B, _dp(beta), _dp(s2)))
         return beta, s2
+
+    def train_cmaes(self, x0, sigma0, trainvar, fixed_nugget, lb=None, ub=None, scaling=None, popsize=0, maxiter=0,
+                    seed=0, tolfun=0.0, tolx=0.0, check_every=0):
+        """CMA-ES over the hyper-parameters with the generation loop on the device (kb_train_cmaes).
+        Returns (xbest, fbest, generations, stop_reason, history of the best objective per generation)."""
+        x0 = _f64(np.asarray(x0).reshape(-1))
+        N = x0.size
+        lam = int(popsize) if popsize else 4 + int(3 * np.log(N))
+        mi = int(maxiter) if maxiter else 100 + 150 * (N + 3) ** 2 // int(np.sqrt(lam))
+        arr = lambda v: None if v is None else _f64(np.broadcast_to(np.asarray(v, dtype=float), (N,)))
+        lb_, ub_, sc_ = arr(lb), arr(ub), arr(scaling)
+        opts = CmaesOpts(int(popsize), int(maxiter), int(check_every), float(sigma0), float(tolfun), float(tolx), int(seed))
+        xbest, hist = np.empty(N), np.zeros(mi)
+        fbest, gens, why = C.c_double(), C.c_int(), C.c_int()
+        check(self._lib.kb_train_cmaes(self._h, N, int(bool(trainvar)), float(fixed_nugget), _dp(x0),
+                                       _dp(lb_) if lb_ is not None else None, _dp(ub_) if ub_ is not None else None,
+                                       _dp(sc_) if sc_ is not None else None, C.byref(opts), _dp(xbest),
+                                       C.cast(C.byref(fbest), c_double_p), C.cast(C.byref(gens), c_int_p),
+                                       C.cast(C.byref(why), c_int_p), _dp(hist)))
+        return xbest, float(fbest.value), int(gens.value), int(why.value), hist[:gens.value].copy()
 
     def reserve_population(self, B):
         check(self._lib.kb_reserve_population(self._h, int(B)))

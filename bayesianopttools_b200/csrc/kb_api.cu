@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "kb_internal.h"
@@ -948,6 +950,93 @@ kb_status kb_ehvi2d_points(kb_model* m1, kb_model* m2, const kb_points* pts, int
     KB_FAIL(KB_ERR_INVALID, "point set (device %d, d=%d) does not match the model (device %d, d=%d)", pts->device,
             pts->d, m1->device, m1->d);
   return ehvi2d_core(m1, m2, pts->npts, pts->x, true, k, front, ref, spread, out, best_idx, best_val);
+}
+
+// ---- device-resident CMA-ES --------------------------------------------------------------------------
+kb_status kb_train_cmaes(kb_model* m, int nbhyp, int trainvar, double fixed_nugget_log10, const double* x0,
+                         const double* lb, const double* ub, const double* scaling, const kb_cmaes_opts* opts,
+                         double* xbest, double* fbest, int* generations, int* stop_reason, double* hist) {
+  if (!m || !x0 || !opts || !xbest || nbhyp < 1) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  if ((lb == nullptr) != (ub == nullptr)) KB_FAIL(KB_ERR_INVALID, "give both bounds or neither");
+  if (!(opts->sigma0 > 0.0)) KB_FAIL(KB_ERR_INVALID, "sigma0 must be positive");
+  const int N = nbhyp;
+  if (N > 64) KB_FAIL(KB_ERR_INVALID, "the device CMA-ES handles up to 64 hyper-parameters (got %d)", N);
+  KbCmaParams P{};
+  P.N = N; P.nbhyp = nbhyp;
+  P.lam = opts->popsize > 0 ? opts->popsize : 4 + (int)(3.0 * std::log((double)N));
+  if (P.lam < 4 || P.lam > 256) KB_FAIL(KB_ERR_INVALID, "population size %d outside [4, 256]", P.lam);
+  P.mu = P.lam / 2;
+  std::vector<double> w((size_t)P.mu);
+  double wsum = 0.0, w2 = 0.0;
+  for (int i = 0; i < P.mu; ++i) { w[i] = std::log(P.mu + 0.5) - std::log((double)(i + 1)); wsum += w[i]; }
+  for (int i = 0; i < P.mu; ++i) { w[i] /= wsum; w2 += w[i] * w[i]; }
+  P.mueff = 1.0 / w2;
+  P.cc = (4.0 + P.mueff / N) / (N + 4.0 + 2.0 * P.mueff / N);
+  P.cs = (P.mueff + 2.0) / (N + P.mueff + 5.0);
+  P.c1 = 2.0 / ((N + 1.3) * (N + 1.3) + P.mueff);
+  P.cmu = std::min(1.0 - P.c1, 2.0 * (P.mueff - 2.0 + 1.0 / P.mueff) / ((N + 2.0) * (N + 2.0) + P.mueff));
+  P.damps = 1.0 + 2.0 * std::max(0.0, std::sqrt((P.mueff - 1.0) / (N + 1.0)) - 1.0) + P.cs;
+  P.chiN = std::sqrt((double)N) * (1.0 - 1.0 / (4.0 * N) + 1.0 / (21.0 * N * N));
+  P.maxiter = opts->maxiter > 0 ? opts->maxiter : 100 + 150 * (N + 3) * (N + 3) / (int)std::sqrt((double)P.lam);
+  P.tolfun = opts->tolfun > 0.0 ? opts->tolfun : 1e-11;
+  P.tolx = opts->tolx > 0.0 ? opts->tolx : 1e-11;
+  P.window = 10 + (int)(30.0 * N / P.lam);
+  P.has_bounds = lb ? 1 : 0;
+  P.seed = opts->seed;
+  const int check_every = opts->check_every > 0 ? opts->check_every : 4;
+
+  CK(cudaSetDevice(m->device));
+  kb_status s = ensure_ws(m, m->pop, P.lam, false);
+  if (s != KB_OK) return s;
+  const size_t nstate = kb_cmaes_state_doubles(N, P.lam, P.mu, P.maxiter);
+  std::vector<double> init(nstate, 0.0);
+  KbCmaView V;
+  kb_cma_view(init.data(), N, P.lam, P.mu, P.maxiter, &V);
+  V.scal[0] = opts->sigma0;
+  V.scal[1] = INFINITY;
+  for (int a = 0; a < N; ++a) {
+    V.mean[a] = x0[a]; V.best_x[a] = x0[a]; V.D[a] = 1.0;
+    V.scale[a] = scaling ? scaling[a] : 1.0;
+    V.lb[a] = lb ? lb[a] : 0.0; V.ub[a] = ub ? ub[a] : 0.0;
+    V.C[(size_t)a * N + a] = 1.0; V.A[(size_t)a * N + a] = 1.0;
+  }
+  for (int i = 0; i < P.mu; ++i) V.w[i] = w[i];
+  double *state = nullptr, *xpop = nullptr, *fdev = nullptr;
+  cudaError_t e = cudaMalloc(&state, sizeof(double) * nstate);
+  if (e == cudaSuccess) e = cudaMalloc(&xpop, sizeof(double) * (size_t)P.lam * nbhyp);
+  if (e == cudaSuccess) e = cudaMalloc(&fdev, sizeof(double) * (size_t)P.lam);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(state, init.data(), sizeof(double) * nstate, cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess) e = kb_launch_cmaes_step(m->stream, P, state, fdev, xpop, 1);
+  g_launches += 1;
+  double scal[8] = {0};
+  while (e == cudaSuccess && s == KB_OK) {
+    for (int it = 0; it < check_every && e == cudaSuccess && s == KB_OK; ++it) {
+      s = run_pipeline(m, m->pop, P.lam, nbhyp, xpop, trainvar, fixed_nugget_log10, fdev, nullptr);
+      if (s == KB_OK) e = kb_launch_cmaes_step(m->stream, P, state, fdev, xpop, 0);
+      g_launches += 1;
+    }
+    if (e == cudaSuccess && s == KB_OK)
+      e = cudaMemcpyAsync(scal, state, sizeof(scal), cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (scal[3] != 0.0) break;
+  }
+  if (e == cudaSuccess && s == KB_OK) {
+    std::vector<double> fin(nstate);
+    e = cudaMemcpy(fin.data(), state, sizeof(double) * nstate, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+      kb_cma_view(fin.data(), N, P.lam, P.mu, P.maxiter, &V);
+      for (int a = 0; a < N; ++a) xbest[a] = V.best_x[a];
+      if (fbest) *fbest = V.scal[1];
+      if (generations) *generations = (int)V.scal[2];
+      if (stop_reason) *stop_reason = (int)V.scal[3];
+      if (hist) for (int g = 0; g < (int)V.scal[2]; ++g) hist[g] = V.hist[g];
+    }
+  }
+  cudaFree(state); cudaFree(xpop); cudaFree(fdev);
+  if (s != KB_OK) return s;
+  if (e != cudaSuccess) KB_FAIL(KB_ERR_CUDA, "cmaes: %s", cudaGetErrorString(e));
+  return KB_OK;
 }
 
 kb_status kb_loocv(kb_model* m, double* pred_out) {

@@ -156,3 +156,35 @@ cudaError_t kb_launch_ehvi2d(cudaStream_t st, long long m, const double* mu1, co
 
 // --- kb_peak.cu --------------------------------------------------------------
 cudaError_t kb_launch_peak(cudaStream_t st, int which, int iters, int grid, double* sink);
+
+// kb_cmaes.cu: device-resident CMA-ES generation loop
+// state layout (doubles) -- see kb_cmaes_state_doubles
+struct KbCmaView {
+  double *mean, *pc, *ps, *C, *A, *D, *scale, *lb, *ub, *w, *best_x, *z, *y, *x, *hist;
+  double* scal;   // [0] sigma [1] best_f [2] gen [3] stop [4] evals
+};
+
+__host__ __device__ inline size_t kb_cma_view(double* base, int N, int lam, int mu, int maxiter, KbCmaView* v) {
+  size_t o = 0;
+  auto take = [&](size_t n) { double* p = base ? base + o : nullptr; o += n; return p; };
+  KbCmaView t;
+  t.scal = take(8);
+  t.mean = take(N); t.pc = take(N); t.ps = take(N); t.D = take(N); t.scale = take(N); t.lb = take(N); t.ub = take(N);
+  t.best_x = take(N); t.w = take(mu);
+  t.C = take((size_t)N * N); t.A = take((size_t)N * N);
+  t.z = take((size_t)lam * N); t.y = take((size_t)lam * N); t.x = take((size_t)lam * N);
+  t.hist = take(maxiter + 1);
+  if (v) *v = t;
+  return o;
+}
+
+
+struct KbCmaParams {
+  int N, lam, mu, maxiter, nbhyp, has_bounds, window;
+  double cc, cs, c1, cmu, damps, chiN, mueff, tolfun, tolx;
+  unsigned long long seed;
+};
+
+size_t kb_cmaes_state_doubles(int N, int lam, int mu, int maxiter);
+cudaError_t kb_launch_cmaes_step(cudaStream_t st, const KbCmaParams& P, double* state, const double* f_in, double* xpop,
+                                 int first);

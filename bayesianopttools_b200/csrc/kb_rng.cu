@@ -3,26 +3,7 @@
 // four 32-bit words -> two 53-bit uniforms -> two variates; reproducible on the host (oracle/philox.py).
 #include "kb_common.cuh"
 #include "kb_internal.h"
-
-__device__ __forceinline__ void kb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                                 uint32_t k1, uint32_t (&out)[4]) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += W0; k1 += W1;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// 52-bit uniform strictly inside (0, 1): (((hi << 20) | (lo >> 12)) + 0.5) * 2^-52  (exact in FP64)
-__device__ __forceinline__ double kb_u53(uint32_t hi, uint32_t lo) {
-  const unsigned long long v = ((unsigned long long)hi << 20) | (unsigned long long)(lo >> 12);
-  return ((double)v + 0.5) * 2.220446049250313e-16;
-}
+#include "kb_philox.cuh"
 
 __global__ void kb_points_generate_kernel(double* __restrict__ x, long long npts, int d, int dist, double p0, double p1,
                                           const double* __restrict__ lb, const double* __restrict__ ub,

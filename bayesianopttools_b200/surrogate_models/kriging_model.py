@@ -195,6 +195,15 @@ class Kriging:
             f = self._batch_nll(np.asarray(x, dtype=float)[None, :])[0]
             return float(f) if np.isfinite(f) else PENALTY
 
+        if opt == "cmaes" and K.get("cmaes_device", True) and len(x0) <= 64:
+            # the whole generation loop runs on the device (kb_train_cmaes): no host round trip per generation
+            from .supports.device_state import fixed_nugget_of, get_model
+            seed = K.get("seed")
+            bx, bf, _, _, _ = get_model(K).model.train_cmaes(
+                x0, self.sigmacmaes, self.trainvar, fixed_nugget_of(K), lb=lbv, ub=ubv, scaling=self.scaling,
+                popsize=K.get("cmaes_popsize") or 0, maxiter=K.get("cmaes_maxiter") or 0,
+                seed=int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed))
+            return bx, bf
         if opt == "cmaes":
             bx, bf, _ = fmin_batched(lambda P: self._batch_nll(P), x0, self.sigmacmaes, bounds=[lbv, ubv],
                                      scaling=self.scaling, popsize=K.get("cmaes_popsize"),

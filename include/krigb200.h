@@ -175,6 +175,26 @@ kb_status kb_ehvi2d(kb_model* m1, kb_model* m2, long long npts, const double* x,
 kb_status kb_ehvi2d_points(kb_model* m1, kb_model* m2, const kb_points* pts, int k, const double* front,
                            const double* ref, int spread, double* out, long long* best_idx, double* best_val);
 
+/* Hyper-parameter search by CMA-ES with the whole generation loop on the device (replaces the host
+ * loop around `cma.fmin2(likelihood, xhyp, sigmacmaes, {'bounds': ..., 'scaling_of_variables': ...})`,
+ * kriging_model.py:420-424).  Per generation the device ranks the population, updates mean / evolution
+ * paths / covariance / step size, eigen-decomposes the covariance (parallel Jacobi), tests the stop
+ * criteria and samples the next population from the counter-based Philox stream; the likelihood pipeline
+ * then evaluates it.  The host enqueues `check_every` generations at a time and reads back a 40-byte
+ * status.  x0, lb, ub, scaling: nbhyp values each (lb = ub = NULL: unbounded; scaling NULL: ones).
+ * Zero-valued options take the defaults of optim_tools/cmaes.py (popsize 4 + floor(3 ln N), maxiter
+ * 100 + 150 (N+3)^2 / sqrt(popsize), tolfun = tolx = 1e-11, check_every 4).  Limits: nbhyp <= 64,
+ * popsize <= 256.  hist (optional, maxiter doubles) receives the best penalised objective of every
+ * generation; stop_reason: 1 maxiter, 2 tolx, 3 tolfun (flat history), 4 ill-conditioned covariance. */
+typedef struct {
+  int popsize, maxiter, check_every;
+  double sigma0, tolfun, tolx;
+  unsigned long long seed;
+} kb_cmaes_opts;
+kb_status kb_train_cmaes(kb_model* m, int nbhyp, int trainvar, double fixed_nugget_log10, const double* x0,
+                         const double* lb, const double* ub, const double* scaling, const kb_cmaes_opts* opts,
+                         double* xbest, double* fbest, int* generations, int* stop_reason, double* hist);
+
 /* Leave-one-out predictions at the fitted hyper-parameters, pred_out[n].  Replaces the n
  * refits + n single-site predictions of loocv2 (krigloocv2.py:7-33) with the closed form
  * from one factorisation; same numbers up to rounding. */

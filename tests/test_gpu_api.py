@@ -353,3 +353,25 @@ def test_mobo_parego_loop_runs():
         assert xup.shape == (nnew, nvar) and yup.shape == (nnew, 2) and sup is None
         assert objs[0].KrigInfo["X"].shape[0] == n + nnew
         assert np.max(np.abs(yup - evaluate(xup, "schaffer"))) < 1e-14
+
+
+def test_train_with_device_cmaes_reaches_the_multistart_optimum():
+    """`Kriging.train` with optimizer='cmaes' runs the generation loop on the device (kb_train_cmaes) and
+    ends at a likelihood as good as the multi-start L-BFGS-B search and the host-loop CMA-ES."""
+    from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
+    from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
+    rng = np.random.default_rng(8)
+    n, d = 80, 3
+    X = rng.uniform(-5, 5, (n, d))
+    y = 0.5 * np.sum(X ** 4 - 16 * X ** 2 + 5 * X, axis=1).reshape(-1, 1)
+    got = {}
+    for name, extra in (("lbfgsb", dict(optimizer="lbfgsb", nrestart=6)),
+                        ("cmaes_device", dict(optimizer="cmaes", nrestart=2, seed=4)),
+                        ("cmaes_host", dict(optimizer="cmaes", nrestart=2, seed=4, cmaes_device=False))):
+        K = initkriginfo("single")
+        K.update(X=X, y=y, lb=-5 * np.ones(d), ub=5 * np.ones(d), kernel=["gaussian"], nugget=-6, TrendOrder=0, **extra)
+        o = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+        o.train(disp=False)
+        got[name] = float(np.ravel(o.KrigInfo["NegLnLike"])[0])
+    assert got["cmaes_device"] <= got["lbfgsb"] + 1e-4 * abs(got["lbfgsb"])
+    assert abs(got["cmaes_device"] - got["cmaes_host"]) <= 1e-4 * abs(got["cmaes_host"])

@@ -313,3 +313,59 @@ def test_ehvi_over_resident_points_equals_host_buffer_call(lib):
     pts.close()
     for m in mdls:
         m.close()
+
+
+def _cma_model(lib, n=60, d=3, seed=31, dup=False):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, (n, d))
+    if dup:
+        X[5] = X[2]
+    y = np.sum(np.sin(2.5 * X) + X ** 2, axis=1)
+    if dup:
+        y[5] += 0.3          # conflicting observations at the duplicated site: the optimum nugget is interior
+    F = np.ones((n, 1))
+    return X, y, F, lib.DeviceModel(X, y, F, ["gaussian"])
+
+
+def test_device_cmaes_trajectory_matches_host_restatement(lib):
+    """SURVEY section 8(f) row 4 (on-GPU optimiser loop): 15 generations of the device CMA-ES -- ranking,
+    path / covariance / step-size updates, Jacobi eigen-decomposition, Philox sampling, all in one kernel per
+    generation -- follow the numpy restatement (LAPACK eigh, same Philox stream, oracle likelihood) to
+    1e-8 in the best objective of every generation and in the incumbent."""
+    from oracle import cmaes_oracle
+    X, y, F, mdl = _cma_model(lib)
+    d = X.shape[1]
+    kw = dict(popsize=0, maxiter=15, seed=7)
+    xb, fb, gens, why, hist = mdl.train_cmaes(np.zeros(d), 2.0, False, -6.0, lb=-5 * np.ones(d), ub=5 * np.ones(d),
+                                              scaling=np.ones(d), **kw)
+    ref = cmaes_oracle.run(lambda P: ko.nll_batch(P, X, y, F)[0], np.zeros(d), 2.0, lb=-5 * np.ones(d),
+                           ub=5 * np.ones(d), **kw)
+    assert gens == ref["gen"] == 15 and why == ref["stop"] == 1
+    assert np.max(np.abs(hist - ref["hist"]) / np.maximum(1.0, np.abs(ref["hist"]))) < 1e-8
+    assert abs(fb - ref["best_f"]) < 1e-8 * max(1.0, abs(fb)) and np.max(np.abs(xb - ref["best_x"])) < 1e-7
+    mdl.close()
+
+
+def test_device_cmaes_converges_and_survives_non_pd_candidates(lib):
+    """Full run with the default stop criteria: ends for a stated reason, at a likelihood no worse than a
+    dense grid over the box; with duplicated sites and a tunable nugget down to 1e-30 part of every
+    population is not positive definite (+inf objective) and must simply rank last."""
+    X, y, F, mdl = _cma_model(lib, n=50, d=2, seed=32)
+    lbv, ubv = -3 * np.ones(2), 3 * np.ones(2)
+    xb, fb, gens, why, hist = mdl.train_cmaes(np.zeros(2), 1.2, False, -6.0, lb=lbv, ub=ubv, seed=3)
+    assert why in (1, 2, 3, 4) and gens == len(hist) and np.all(xb >= lbv) and np.all(xb <= ubv)
+    g = np.linspace(-3, 3, 25)
+    grid = np.array([[a, b] for a in g for b in g])
+    fgrid = mdl.nll_batch(grid[:256], False, -6.0)
+    for s0 in range(256, len(grid), 256):
+        fgrid = np.concatenate([fgrid, mdl.nll_batch(grid[s0:s0 + 256], False, -6.0)])
+    assert fb <= np.min(fgrid) + 1e-6
+    assert abs(fb - ko.nll(xb, X, y, F)) <= 1e-9 * max(1.0, abs(fb))          # the incumbent is a real evaluation
+    mdl.close()
+    X, y, F, mdl = _cma_model(lib, n=40, d=2, seed=33, dup=True)
+    lbv, ubv = np.array([-3.0, -3.0, -30.0]), np.array([3.0, 3.0, 0.0])      # theta_1, theta_2, log10 nugget
+    xb, fb, gens, why, hist = mdl.train_cmaes(np.array([0.0, 0.0, -16.0]), 6.0, False, 0.0, lb=lbv, ub=ubv,
+                                              scaling=np.array([1.0, 1.0, 1.0]), maxiter=60, seed=5, popsize=16)
+    assert np.isfinite(fb) and why in (1, 2, 3, 4) and gens >= 1 and np.all(np.isfinite(hist))
+    assert abs(fb - ko.nll(xb, X, y, F)) <= 1e-7 * max(1.0, abs(fb))
+    mdl.close()
