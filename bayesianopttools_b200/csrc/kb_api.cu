@@ -78,6 +78,7 @@ struct kb_model {
   KbSweepResult* result_dev = nullptr;
   int pred_grid = 0;
   int pred_resident = 0;
+  int pred_stage_x = 1;
   // host-API staging
   double* stage_x[2] = {nullptr, nullptr};
   double* stage_out[2] = {nullptr, nullptr};
@@ -519,9 +520,20 @@ static kb_status ensure_predict_scratch(kb_model* m) {
   cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
   m->psi_scratch = m->ex_scratch = nullptr; m->partials = nullptr;
   m->pred_resident = resident;
-  m->pred_grid = (resident == 2) ? kb_predict_warp_ctas_per_sm(m->d, m->n, qx) * m->num_sms
-                                 : kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx);
-  if (m->pred_grid < 1) KB_FAIL(KB_ERR_CUDA, "predict kernel does not fit on this device (d=%d)", m->d);
+  m->pred_stage_x = 1;
+  if (resident == 2) {
+    m->pred_grid = kb_predict_warp_ctas_per_sm(m->d, m->n, qx) * m->num_sms;
+  } else {
+    // prefetching the next strip's raw sites costs 2 x 64 x d doubles of shared memory: keep it only
+    // while it does not cost a resident CTA
+    const int g1 = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx, 1);
+    const int g0 = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx, 0);
+    m->pred_stage_x = (g1 >= g0 && g1 > 0) ? 1 : 0;
+    m->pred_grid = m->pred_stage_x ? g1 : g0;
+  }
+  if (m->pred_grid < 1)
+    KB_FAIL(KB_ERR_CUDA, "the predictor keeps one 64-site strip and a 16-site training tile per dimension in shared "
+                         "memory: d = %d does not fit (limit about 180)", m->d);
   const size_t strip = kb_predict_strip(resident != 0);
   if (!resident) CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip));
   CK(cudaMalloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * strip));
@@ -554,6 +566,7 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   for (int k = 0; k < KB_OUT_COUNT; ++k) a.out[k] = outs_dev ? outs_dev[k] : nullptr;
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
   a.resident = m->pred_resident;
+  a.stage_x = m->pred_stage_x;
   const long long strip = (m->pred_resident == 2) ? 256 : kb_predict_strip(m->pred_resident != 0);
   const long long nstrips = (npts + strip - 1) / strip;
   const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);

@@ -123,19 +123,20 @@ struct KbPredictArgs {
   // scratch
   double* psi_scratch;     // [grid][n_pad][strip]   (streaming variant only; strip = 128)
   double* ex_scratch;      // [grid][qx][strip]
+  int stage_x;             // raw sites of the next strip prefetched into shared memory (narrow inputs)
   int qx;                  // extra rows (1 + nind)
   int resident;            // 1: inverse factor and psi strip stay in shared memory (n_pad <= 128);
                            // 2: warp-autonomous variant (n <= 64, d <= 8, ordinary Kriging)
   KbSweepResult* partials; // [grid]
 };
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev);
-size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx);
+size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx, int stage_x);
 bool kb_predict_can_reside(int d, int n_pad, int qx, int nind_trend);
 int kb_predict_strip(bool resident);
 bool kb_predict_can_warp(int d, int n, int qx, int nind_trend);
 size_t kb_predict_warp_smem_bytes(int d, int n8, int qx);
 int kb_predict_warp_ctas_per_sm(int d, int n, int qx);
-int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx);
+int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx, int stage_x);
 
 // --- kb_rng.cu ---------------------------------------------------------------
 cudaError_t kb_launch_points_generate(cudaStream_t st, double* x, long long npts, int d, int dist, double p0, double p1,

@@ -38,20 +38,24 @@ struct KbPredSmem {
 int kb_predict_strip(bool resident) { (void)resident; return 64; }
 int kb_predict_threads(bool resident) { (void)resident; return 256; }
 
-size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx) {
+// stage_x: raw sites of the next strip are prefetched into two shared buffers (2 x 64 x d doubles).
+// For wide inputs that staging costs a resident CTA (or does not fit at all), so the host turns it off
+// and the strip is read straight from global memory when it is standardised.
+size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx, int stage_x) {
   const size_t mt = kb_predict_strip(resident);
   size_t big;
   if (resident)
     big = sizeof(double) * ((size_t)n_pad * (n_pad + 4) + (size_t)n_pad * (mt + 4) + 4 * (size_t)(qx < PK_QIN ? qx : PK_QIN) * mt);
   else
     big = sizeof(double) * PK_STAGES * PK_KC * (PK_LDA + mt + 4);
-  return sizeof(KbPredSmem) + ((size_t)d * (mt + 2) + 2 * (size_t)d * PK_TK + 2 * PK_TK * PK_QIN + 2 * mt * (size_t)d) * sizeof(double) + big;
+  return sizeof(KbPredSmem) +
+         ((size_t)d * (mt + 2) + 2 * (size_t)d * PK_TK + 2 * PK_TK * PK_QIN + (stage_x ? 2 * mt * (size_t)d : 0)) * sizeof(double) + big;
 }
 
 // The resident variant needs the whole inverse factor in shared memory.
 bool kb_predict_can_reside(int d, int n_pad, int qx, int nind_trend) {
   return n_pad <= 128 && nind_trend == 0 && qx <= PK_QIN &&
-         kb_predict_smem_bytes(d, true, n_pad, qx) <= 220 * 1024;
+         kb_predict_smem_bytes(d, true, n_pad, qx, 1) <= 220 * 1024;
 }
 
 __device__ __forceinline__ double kb_legendre_on(int o, double x) {
@@ -173,7 +177,7 @@ kb_predict_kernel(KbPredictArgs P) {
   double* xtile = sith + P.d;                                             // [2][d][16] training-site tiles
   double* etile = xtile + 2 * P.d * PK_TK;                                // [2][16][PK_QIN] extra columns
   double* xraw = etile + 2 * PK_TK * PK_QIN;                                // [2][64 d] raw sites, prefetched
-  double* big = xraw + 2 * MT * P.d;
+  double* big = xraw + (P.stage_x ? 2 * MT * P.d : 0);
   double (*sa)[PK_KC][PK_LDA] = reinterpret_cast<double (*)[PK_KC][PK_LDA]>(big);
   double (*sb)[PK_KC][LDB] = reinterpret_cast<double (*)[PK_KC][LDB]>(big + PK_STAGES * PK_KC * PK_LDA);
   const int lda_r = P.n_pad + 4;
@@ -212,7 +216,7 @@ kb_predict_kernel(KbPredictArgs P) {
   // raw sites of the NEXT strip are prefetched (cp.async, two buffers) while this one is processed
   const bool x_aligned = ((reinterpret_cast<uintptr_t>(P.x) & 15) == 0);
   auto prefetch_x = [&](long long strip, int buf) {
-    if (x_aligned && strip < nstrips && (strip + 1) * MT <= P.m) {
+    if (P.stage_x && x_aligned && strip < nstrips && (strip + 1) * MT <= P.m) {
       const double* src = P.x + (size_t)strip * MT * d;
       double* dst = xraw + (size_t)buf * MT * d;
       for (int e = tid; e < MT * d / 2; e += NT) kb_cp_async16(dst + 2 * e, src + 2 * e);
@@ -228,7 +232,7 @@ kb_predict_kernel(KbPredictArgs P) {
     __syncthreads();
     prefetch_x(strip + gridDim.x, xbuf ^ 1);
     // ---- A1. standardise the strip ---------------------------------------
-    const bool staged = x_aligned && npt == MT;
+    const bool staged = P.stage_x && x_aligned && npt == MT;
     const double* xr = xraw + (size_t)xbuf * MT * d;
     for (int e = tid; e < MT * d; e += blockDim.x) {
       const int p = e / d, dim = e - p * d;
@@ -749,7 +753,7 @@ static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& 
 
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {
   const size_t smem = (a.resident == 2) ? kb_predict_warp_smem_bytes(a.d, (a.n + 7) & ~7, a.qx)
-                                        : kb_predict_smem_bytes(a.d, a.resident != 0, a.n_pad, a.qx);
+                                        : kb_predict_smem_bytes(a.d, a.resident != 0, a.n_pad, a.qx, a.stage_x);
   cudaError_t err = cudaSuccess;
   if (a.resident == 2) {
     KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_warp_launch<M_>(st, a, grid, smem)));
@@ -767,8 +771,9 @@ cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid,
 }
 
 // Largest persistent grid for the predict kernel: SMs x resident CTAs per SM.
-int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx) {
-  const size_t smem = kb_predict_smem_bytes(d, resident != 0, n_pad, qx);
+int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx, int stage_x) {
+  const size_t smem = kb_predict_smem_bytes(d, resident != 0, n_pad, qx, stage_x);
+  if (smem > 227 * 1024) return 0;
   int occ = 0;
   cudaError_t err = cudaSuccess;
   if (resident) {

@@ -369,3 +369,45 @@ def test_device_cmaes_converges_and_survives_non_pd_candidates(lib):
     assert np.isfinite(fb) and why in (1, 2, 3, 4) and gens >= 1 and np.all(np.isfinite(hist))
     assert abs(fb - ko.nll(xb, X, y, F)) <= 1e-7 * max(1.0, abs(fb))
     mdl.close()
+
+
+def test_wide_input_predictor_without_strip_staging(lib):
+    """d = 150 without KPLS: the predictor drops the shared-memory staging of the next strip's raw sites
+    (it would not fit) and reads them from global memory; outputs against the oracle."""
+    rng = np.random.default_rng(77)
+    n, d = 120, 150
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sum(np.sin(2 * X[:, :6]), axis=1)
+    F = np.ones((n, 1))
+    mdl = lib.DeviceModel(X, y, F, ["matern32"])
+    th = rng.uniform(0.5, 1.0, d)
+    mdl.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
+    mdl.set_norm(lib.NORM_NONE)
+    fit = ko.nll(th, X, y, F, kernels=("matern32",), full=True)
+    xq = rng.uniform(-1, 1, (333, d))
+    outs, res = mdl.predict(xq, ("pred", "ssqr", "ei"), acq="ei", ybest=float(y.min()))
+    p = ko.predict(xq, X, y, F, np.zeros((1, d), int), fit, kernels=("matern32",), ybest=float(y.min()))
+    for k in ("pred", "ssqr", "ei"):
+        assert relerr(outs[k], p[k]) < 2e-8, k
+    assert res["best_idx"] == int(np.argmin(p["ei"]))
+    mdl.close()
+    # d = 200 is the widest design a model accepts; wider ones are refused with a message, not a crash
+    with pytest.raises(lib.KrigB200Error, match="KB_MAX_D"):
+        lib.DeviceModel(rng.uniform(-1, 1, (40, 400)), np.zeros(40), np.ones((40, 1)), ["gaussian"])
+    Xw = rng.uniform(-1, 1, (40, 200))
+    yw = np.sum(Xw[:, :5], axis=1)
+    big = lib.DeviceModel(Xw, yw, np.ones((40, 1)), ["gaussian"])
+    thw = np.full(200, 0.8)
+    nll = big.nll_batch(thw[None, :], False, -6.0)
+    assert abs(nll[0] - ko.nll(thw, Xw, yw, np.ones((40, 1)))) < 1e-9 * max(1.0, abs(nll[0]))
+    big.fit_state(thw, False, -6.0, want_U=False, want_Psi=False)
+    big.set_norm(lib.NORM_NONE)
+    try:
+        outs, _ = big.predict(Xw[:7] + 0.01, ("pred",))
+    except lib.KrigB200Error as e:                       # allowed to refuse, with the reason
+        assert "does not fit" in str(e)
+    else:
+        fitw = ko.nll(thw, Xw, yw, np.ones((40, 1)), full=True)
+        pw = ko.predict(Xw[:7] + 0.01, Xw, yw, np.ones((40, 1)), np.zeros((1, 200), int), fitw)
+        assert relerr(outs["pred"], pw["pred"]) < 2e-8
+    big.close()
