@@ -529,6 +529,9 @@ static kb_status ensure_predict_scratch(kb_model* m) {
     const int g1 = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx, 1);
     const int g0 = kb_predict_max_grid(m->kmask, m->d, m->num_sms, resident, m->n_pad, qx, 0);
     m->pred_stage_x = (g1 >= g0 && g1 > 0) ? 1 : 0;
+    static const char* sx_env = getenv("KB_PRED_STAGE_X");            // debug aid: force 0 / 1 when it fits
+    if (sx_env && atoi(sx_env) == 1 && g1 > 0) m->pred_stage_x = 1;
+    if (sx_env && atoi(sx_env) == 0 && g0 > 0) m->pred_stage_x = 0;
     m->pred_grid = m->pred_stage_x ? g1 : g0;
   }
   if (m->pred_grid < 1)
