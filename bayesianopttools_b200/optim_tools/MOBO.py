@@ -1,12 +1,12 @@
 """Multi-objective Bayesian optimisation loop (reference: optim_tools/MOBO.py:14-467).
 
-Same call surface and bookkeeping as the reference's `MOBO` (run / ehviupdate / paregoupdate /
-simultpredehvi / simultpredparego / enrich, `moboinfocheck` defaults).  What changes is where the time
-goes: the acquisition is the device EHVI (optim_tools/ehvi/EHVIcomputation.py -> kb_ehvi2d), the
-Kriging-believer refits at fixed hyper-parameters (MOBO.py:258-267) are one `likelihood(mode='all')`
-= one kb_fit_state each, and `acquifuncopt='sweep'` replaces the multi-start local search by a
-one-launch scoring of a large candidate set.  `run` returns the reference's four values
-(xupdate, yupdate, supdate, metricall)."""
+Call surface of the reference's `MOBO` -- constructor arguments, `run(disp, infeasible)`, the attributes
+it leaves behind (Xall, yall, ypar, spredall, metricall, nup) and the `moboinfocheck` defaults -- with the
+loop written once for both acquisition modes.  Where the time goes is different: the EHVI acquisition is
+the device kernel behind optim_tools/ehvi/EHVIcomputation.py (kb_ehvi2d), a Kriging-believer refit at
+fixed hyper-parameters (MOBO.py:258-267) is one `likelihood(mode='all')` = one kb_fit_state, and
+`acquifuncopt='sweep'` scores a device-generated candidate design in one pass instead of running
+multi-start local searches.  `run` returns (xupdate, yupdate, supdate, metricall)."""
 import time
 from copy import deepcopy
 
@@ -17,238 +17,200 @@ from bayesianopttools_b200.surrogate_models.kriging_model import Kriging
 from bayesianopttools_b200.surrogate_models.supports.likelihood_func import likelihood
 from bayesianopttools_b200.surrogate_models.supports.trendfunction import compute_regression_mat
 from bayesianopttools_b200.testcase.analyticalfcn.cases import evaluate
-from . import searchpareto
 from .acquifunc_opt import run_multi_opt, run_single_opt
 from .parego import paregopre
+from .searchpareto import paretopoint
+
+_ACQUISITIONS = ("ehvi", "parego")
+_OPTIMISERS = ("lbfgsb", "cobyla", "cmaes", "ga", "sweep")
+
+
+def _scalar_predictions(kriglist, x, what):
+    """One row per requested output, one column per objective model, at the single design x."""
+    out = np.zeros((len(what), len(kriglist)))
+    for j, k in enumerate(kriglist):
+        vals = k.predict(x, list(what))
+        vals = vals if isinstance(vals, (list, tuple)) else [vals]
+        out[:, j] = [float(np.ravel(v)[0]) for v in vals]
+    return out
 
 
 class MOBO:
     def __init__(self, moboInfo, kriglist, autoupdate=True, multiupdate=0, savedata=True, expconst=None,
                  chpconst=None):
         self.moboInfo = moboinfocheck(moboInfo, autoupdate)
-        self.kriglist = kriglist
-        self.krignum = len(kriglist)
-        self.autoupdate = autoupdate
-        self.multiupdate = multiupdate
-        self.savedata = savedata
-        self.krigconstlist = expconst
-        self.cheapconstlist = chpconst
+        self.kriglist, self.krignum = kriglist, len(kriglist)
+        self.autoupdate, self.multiupdate, self.savedata = autoupdate, multiupdate, savedata
+        self.krigconstlist, self.cheapconstlist = expconst, chpconst
 
+    # -- public entry -----------------------------------------------------------------------------------
     def run(self, disp=True, infeasible=None):
-        """MOBO.py:56-135."""
-        K0 = self.kriglist[0].KrigInfo
+        """MOBO.py:56-135: collect the current designs, find the front, iterate, return the new designs."""
+        lead = self.kriglist[0].KrigInfo
         self.nup = 0
-        self.Xall = K0["X"]
+        self.Xall = lead["X"]
         self.yall = np.column_stack([np.asarray(k.KrigInfo["y"], dtype=float)[:, 0] for k in self.kriglist])
         if infeasible is not None:
-            self.yall = np.delete(self.yall.copy(), infeasible, 0)
             self.Xall = np.delete(self.Xall.copy(), infeasible, 0)
-        self.ypar, _ = searchpareto.paretopoint(self.yall)
+            self.yall = np.delete(self.yall.copy(), infeasible, 0)
+        self.ypar, _ = paretopoint(self.yall)
         print("Begin multi-objective Bayesian optimization process.")
-        if self.autoupdate and disp:
-            print(f"Update no.: {self.nup + 1}, F-count: {np.size(self.Xall, 0)}, "
-                  f"Maximum no. updates: {self.moboInfo['nup'] + 1}")
-        acq = self.moboInfo["acquifunc"].lower()
-        if acq == "parego":
-            self.KrigScalarizedInfo = deepcopy(K0)
-            self._train_scalarised(self.Xall, paregopre(self.yall))
+        self._progress(disp and self.autoupdate)
+        mode = self.moboInfo["acquifunc"].lower()
+        if mode == "parego":
+            self.KrigScalarizedInfo = deepcopy(lead)
+            self._fit_scalarised(self.Xall, paregopre(self.yall))
             self.paregoupdate(disp)
-        elif acq == "ehvi":
-            self.ehviupdate(disp)
         else:
-            raise ValueError(self.moboInfo["acquifunc"], " is not a valid acquisition function.")
+            self.ehviupdate(disp)
         if disp:
             print("Optimization finished, now creating the final outputs.")
-        ntail = self.moboInfo["nup"] * (self.multiupdate if self.multiupdate > 1 else 1)
-        xupdate, yupdate = self.Xall[-ntail:, :], self.yall[-ntail:, :]
-        supdate = self.spredall[-ntail:, :] if hasattr(self, "spredall") else None
-        return xupdate, yupdate, supdate, self.metricall
-
-    def _train_scalarised(self, X, y):
-        info = deepcopy(self.KrigScalarizedInfo)
-        info["X"], info["y"] = X, y
-        self.KrigScalarizedInfo = info
-        self.scalkrig = Kriging(info, standardization=True, standtype="default", normy=False, trainvar=False)
-        self.scalkrig.train(disp=False)
-        return self.scalkrig
-
-    def _record(self, metricnext):
-        self.metricall = metricnext if self.nup == 0 else np.vstack((self.metricall, metricnext))
+        tail = self.moboInfo["nup"] * max(1, self.multiupdate)
+        supdate = self.spredall[-tail:, :] if mode == "ehvi" else None
+        return self.Xall[-tail:, :], self.yall[-tail:, :], supdate, self.metricall
 
     def ehviupdate(self, disp):
         """MOBO.py:138-190."""
         self.spredall = np.zeros_like(self.yall)
-        while self.nup < self.moboInfo["nup"]:
-            if self.moboInfo["refpointtype"].lower() == "dynamic":
-                hi, lo = np.max(self.yall, 0), np.min(self.yall, 0)
-                self.moboInfo["refpoint"] = hi + (hi - lo) * 2
-            if self.multiupdate < 0:
-                raise ValueError("Number of multiple update must be greater or equal to 0")
-            if self.multiupdate in (0, 1):
-                xnext, metricnext = run_multi_opt(self.kriglist, self.moboInfo, self.ypar, self.krigconstlist,
-                                                  self.cheapconstlist)
-                yprednext, sprednext = np.zeros(self.krignum), np.zeros(self.krignum)
-                for ii, krigobj in enumerate(self.kriglist):
-                    yprednext[ii], sprednext[ii] = _pred_s(krigobj, xnext)
-            else:
-                xnext, yprednext, sprednext, metricnext = self.simultpredehvi(disp)
-            self._record(metricnext)
-            if self.autoupdate is False:
-                self.Xall = np.vstack((self.Xall, xnext))
-                self.yall = np.vstack((self.yall, yprednext))
-                self.spredall = np.vstack((self.spredall, sprednext))
-                break
-            self.spredall = np.vstack((self.spredall, sprednext))
-            self.enrich(xnext)
-            self.nup += 1
-            if disp:
-                print(f"Update no.: {self.nup + 1}, F-count: {np.size(self.Xall, 0)}, "
-                      f"Maximum no. updates: {self.moboInfo['nup'] + 1}")
+        self._iterate(disp, ehvi=True)
 
     def paregoupdate(self, disp):
         """MOBO.py:193-240."""
-        while self.nup < self.moboInfo["nup"]:
-            if self.multiupdate < 0:
-                raise ValueError("Number of multiple update must be greater or equal to 0")
-            if self.multiupdate in (0, 1):
-                xnext, metricnext = run_single_opt(self.scalkrig, self.moboInfo, self.krigconstlist,
-                                                   self.cheapconstlist)
-                yprednext = np.array([float(np.ravel(k.predict(xnext, ["pred"]))[0]) for k in self.kriglist])
-            else:
-                xnext, yprednext, metricnext = self.simultpredparego()
-            self._record(metricnext)
-            if self.autoupdate is False:
-                self.Xall = np.vstack((self.Xall, xnext))
-                self.yall = np.vstack((self.yall, yprednext))
-                break
-            self.enrich(xnext)
-            self.nup += 1
-            if disp:
-                print(f"Update no.: {self.nup + 1}, F-count: {np.size(self.Xall, 0)}, "
-                      f"Maximum no. updates: {self.moboInfo['nup'] + 1}")
+        self._iterate(disp, ehvi=False)
 
+    # -- the loop -----------------------------------------------------------------------------------------
+    def _progress(self, show):
+        if show:
+            print(f"Update no.: {self.nup + 1}, F-count: {np.size(self.Xall, 0)}, "
+                  f"Maximum no. updates: {self.moboInfo['nup'] + 1}")
+
+    def _suggest(self, ehvi, disp):
+        """Next design(s) with the objective models' predictions there: (x, ypred, spred or None, metric)."""
+        single = self.multiupdate in (0, 1)
+        if ehvi:
+            if not single:
+                return tuple(self.simultpredehvi(disp))
+            x, metric = run_multi_opt(self.kriglist, self.moboInfo, self.ypar, self.krigconstlist, self.cheapconstlist)
+            ps = _scalar_predictions(self.kriglist, x, ("pred", "s"))
+            return x, ps[0], ps[1], metric
+        if not single:
+            x, yp, metric = self.simultpredparego()
+            return x, yp, None, metric
+        x, metric = run_single_opt(self.scalkrig, self.moboInfo, self.krigconstlist, self.cheapconstlist)
+        return x, _scalar_predictions(self.kriglist, x, ("pred",))[0], None, metric
+
+    def _iterate(self, disp, ehvi):
+        info = self.moboInfo
+        if self.multiupdate < 0:
+            raise ValueError("Number of multiple update must be greater or equal to 0")
+        while self.nup < info["nup"]:
+            if ehvi and info["refpointtype"].lower() == "dynamic":       # MOBO.py:152-153
+                top, low = np.max(self.yall, 0), np.min(self.yall, 0)
+                info["refpoint"] = top + 2 * (top - low)
+            x, ypred, spred, metric = self._suggest(ehvi, disp)
+            self.metricall = metric if self.nup == 0 else np.vstack((self.metricall, metric))
+            if spred is not None:
+                self.spredall = np.vstack((self.spredall, spred))
+            if not self.autoupdate:                                      # manual mode: report and stop
+                self.Xall = np.vstack((self.Xall, x))
+                self.yall = np.vstack((self.yall, ypred))
+                return
+            self.enrich(x)
+            self.nup += 1
+            self._progress(disp)
+
+    # -- several designs per iteration ----------------------------------------------------------------------
     def simultpredehvi(self, disp=False):
-        """Kriging believer (MOBO.py:243-303): after each suggested design the objective models take their
-        own prediction there as if it were an observation and are re-fitted at FIXED hyper-parameters
-        (one device factorisation each), then the next design is sought against the updated front."""
-        krigtemp = [_clone(obj) for obj in self.kriglist]
-        nvar = krigtemp[0].KrigInfo["nvar"]
-        bound = np.vstack((-np.ones((1, nvar)), np.ones((1, nvar))))
-        ypartemp, yall = self.ypar, self.yall
-        xs, ys, ss, ms = [], [], [], []
-        for ii in range(self.multiupdate):
-            t1 = time.time()
+        """Kriging believer (MOBO.py:243-303): after each suggestion the objective models take their own
+        prediction there as an observation and are re-fitted at FIXED hyper-parameters (one device
+        factorisation each); the next suggestion is sought against the front updated the same way."""
+        believers = [deepcopy(k) for k in self.kriglist]          # the device handle copies to an empty holder
+        nvar = believers[0].KrigInfo["nvar"]
+        unit_box = np.vstack((-np.ones((1, nvar)), np.ones((1, nvar))))
+        front, yall = self.ypar, self.yall
+        rows = []
+        for it in range(self.multiupdate):
+            tic = time.time()
             if disp:
-                print(f"update number {ii + 1}")
-            xnext, metrictemp = run_multi_opt(krigtemp, self.moboInfo, ypartemp, self.krigconstlist,
-                                              self.cheapconstlist)
-            yprednext, sprednext = np.zeros(len(krigtemp)), np.zeros(len(krigtemp))
-            for jj, kt in enumerate(krigtemp):
-                yprednext[jj], sprednext[jj] = _pred_s(kt, xnext)
-                KI = kt.KrigInfo
-                KI["X"] = np.vstack((KI["X"], xnext))
-                KI["y"] = np.vstack((KI["y"], yprednext[jj]))
-                KI["nsamp"] = KI["X"].shape[0]
-                kt.standardize()
-                KI = kt.KrigInfo
-                KI["F"] = compute_regression_mat(KI["idx"], KI["X_norm"], bound, np.ones(nvar))
-                kt.KrigInfo = likelihood(KI["Theta"], KI, mode="all", trainvar=kt.trainvar)
-            xs.append(np.array(xnext, dtype=float)); ys.append(yprednext.copy()); ss.append(sprednext.copy())
-            ms.append(metrictemp)
-            yall = np.vstack((yall, yprednext))
-            ypartemp, _ = searchpareto.paretopoint(yall)
+                print(f"update number {it + 1}")
+            x, metric = run_multi_opt(believers, self.moboInfo, front, self.krigconstlist, self.cheapconstlist)
+            ps = _scalar_predictions(believers, x, ("pred", "s"))
+            for j, kb in enumerate(believers):
+                K = kb.KrigInfo
+                K["X"] = np.vstack((K["X"], x))
+                K["y"] = np.vstack((K["y"], ps[0, j]))
+                K["nsamp"] = K["X"].shape[0]
+                kb.standardize()
+                K = kb.KrigInfo
+                K["F"] = compute_regression_mat(K["idx"], K["X_norm"], unit_box, np.ones(nvar))
+                kb.KrigInfo = likelihood(K["Theta"], K, mode="all", trainvar=kb.trainvar)
+            rows.append((np.array(x, dtype=float), ps[0].copy(), ps[1].copy(), metric))
+            yall = np.vstack((yall, ps[0]))
+            front, _ = paretopoint(yall)
             if disp:
-                print("time: ", time.time() - t1, " s")
-        return [np.vstack(xs), np.vstack(ys), np.vstack(ss), np.vstack(ms)]
+                print("time: ", time.time() - tic, " s")
+        return [np.vstack([r[c] for r in rows]) for c in range(4)]
 
     def simultpredparego(self):
-        """MOBO.py:306-347: several designs per iteration from different scalarisation weights."""
-        idxs = np.random.choice(11, self.multiupdate)
-        xs, ys, ms = [], [], []
-        for ii, idx in enumerate(idxs):
-            print(f"update number {ii + 1}")
-            info = deepcopy(self.KrigScalarizedInfo)
-            info["X"], info["y"] = self.Xall, paregopre(self.yall, idx)
-            krigtemp = Kriging(info, standardization=True, standtype="default", normy=False, trainvar=False)
-            krigtemp.train(disp=False)
-            xnext, metricnext = run_single_opt(krigtemp, self.moboInfo, self.krigconstlist, self.cheapconstlist)
-            yprednext = np.array([float(np.ravel(k.predict(xnext, ["pred"]))[0]) for k in self.kriglist])
-            xs.append(np.array(xnext, dtype=float)); ys.append(yprednext); ms.append(metricnext)
-        return np.vstack(xs), np.vstack(ys), np.vstack(ms)
+        """MOBO.py:306-347: one design per randomly drawn scalarisation weight."""
+        rows = []
+        for it, widx in enumerate(np.random.choice(11, self.multiupdate)):
+            print(f"update number {it + 1}")
+            model = self._fit_scalarised(self.Xall, paregopre(self.yall, widx), keep=False)
+            x, metric = run_single_opt(model, self.moboInfo, self.krigconstlist, self.cheapconstlist)
+            rows.append((np.array(x, dtype=float), _scalar_predictions(self.kriglist, x, ("pred",))[0], metric))
+        return tuple(np.vstack([r[c] for r in rows]) for c in range(3))
+
+    # -- model upkeep -------------------------------------------------------------------------------------
+    def _fit_scalarised(self, X, y, keep=True):
+        info = deepcopy(self.KrigScalarizedInfo)
+        info["X"], info["y"] = X, y
+        model = Kriging(info, standardization=True, standtype="default", normy=False, trainvar=False)
+        model.train(disp=False)
+        if keep:
+            self.KrigScalarizedInfo, self.scalkrig = info, model
+        return model
 
     def enrich(self, xnext):
         """Evaluate the suggested design(s), append, recompute the front, retrain (MOBO.py:350-402)."""
-        K0 = self.kriglist[0].KrigInfo
-        evalfun = self.moboInfo.get("evaluate", lambda x: evaluate(x, K0["problem"]))
-        xn = np.atleast_2d(np.asarray(xnext, dtype=float))
-        ynext = np.vstack([np.asarray(evalfun(row), dtype=float).reshape(1, -1) for row in xn])
-        # failed evaluations are replaced by a pessimistic prediction (Forrester et al. 2006)
-        for r in np.flatnonzero(np.isnan(ynext).any(axis=1)):
-            for jj, k in enumerate(self.kriglist):
-                SSqr, y_hat = k.predict(xn[r], ["SSqr", "pred"])
-                ynext[r, jj] = float(np.ravel(y_hat)[0] + np.ravel(SSqr)[0])
-        self.yall = np.vstack((self.yall, ynext))
-        self.Xall = np.vstack((self.Xall, xn))
-        self.ypar, I = searchpareto.paretopoint(self.yall)
-        acq = self.moboInfo["acquifunc"].lower()
-        if acq not in ("ehvi", "parego"):
-            raise ValueError(self.moboInfo["acquifunc"], " is not a valid acquisition function.")
-        if acq == "parego":
-            self._train_scalarised(self.Xall, paregopre(self.yall))
-        for index, krigobj in enumerate(self.kriglist):
-            krigobj.KrigInfo["X"] = self.Xall
-            krigobj.KrigInfo["y"] = self.yall[:, index].reshape(-1, 1)
-            krigobj.KrigInfo["nsamp"] = self.Xall.shape[0]
-            krigobj.standardize()
-            krigobj.train(disp=False)
+        lead = self.kriglist[0].KrigInfo
+        fun = self.moboInfo.get("evaluate", lambda x: evaluate(x, lead["problem"]))
+        xs = np.atleast_2d(np.asarray(xnext, dtype=float))
+        ys = np.vstack([np.asarray(fun(row), dtype=float).reshape(1, -1) for row in xs])
+        # a failed evaluation is replaced by a pessimistic prediction (Forrester, Sobester & Keane 2006)
+        for r in np.flatnonzero(np.isnan(ys).any(axis=1)):
+            ps = _scalar_predictions(self.kriglist, xs[r], ("pred", "SSqr"))
+            ys[r] = ps[0] + ps[1]
+        self.Xall, self.yall = np.vstack((self.Xall, xs)), np.vstack((self.yall, ys))
+        self.ypar, members = paretopoint(self.yall)
+        if self.moboInfo["acquifunc"].lower() == "parego":
+            self._fit_scalarised(self.Xall, paregopre(self.yall))
+        for j, k in enumerate(self.kriglist):
+            k.KrigInfo.update(X=self.Xall, y=self.yall[:, j].reshape(-1, 1), nsamp=self.Xall.shape[0])
+            k.standardize()
+            k.train(disp=False)
         if self.savedata:
-            I = np.asarray(I).astype(int)
-            sio.savemat(self.moboInfo["filename"], {"xbest": self.Xall[I, :], "ybest": self.ypar})
-
-
-def _pred_s(krigobj, x):
-    pred, s = krigobj.predict(x, ["pred", "s"])
-    return float(np.ravel(pred)[0]), float(np.ravel(s)[0])
-
-
-def _clone(krigobj):
-    """Independent copy of a Kriging object; the device handle cached in KrigInfo deep-copies to an
-    empty holder (supports/device_state.py), so the copy builds its own on first use."""
-    return deepcopy(krigobj)
+            sio.savemat(self.moboInfo["filename"],
+                        {"xbest": self.Xall[np.asarray(members).astype(int), :], "ybest": self.ypar})
 
 
 def moboinfocheck(moboInfo, autoupdate):
-    """Defaults and validation of the MOBO settings (MOBO.py:405-467)."""
-    if "nup" not in moboInfo:
-        if autoupdate is True:
-            raise ValueError("Number of updates for Bayesian optimization, moboInfo['nup'], is not specified")
-        moboInfo["nup"] = 1
-        print("Number of updates for Bayesian optimization has been set to 1")
-    elif not autoupdate:
-        moboInfo["nup"] = 1
-        print("Manual mode is active, number of updates for Bayesian optimization is forced to 1")
-    if "acquifunc" not in moboInfo:
-        moboInfo["acquifunc"] = "EHVI"
-        print("The acquisition function is not specified, set to EHVI")
-    elif moboInfo["acquifunc"].lower() not in ("ehvi", "parego"):
+    """Validation and defaults of the settings dictionary (MOBO.py:405-467)."""
+    if autoupdate and "nup" not in moboInfo:
+        raise ValueError("Number of updates for Bayesian optimization, moboInfo['nup'], is not specified")
+    if not autoupdate:
+        moboInfo["nup"] = 1                     # manual mode always stops after one suggestion
+    acq = moboInfo.setdefault("acquifunc", "EHVI").lower()
+    if acq not in _ACQUISITIONS:
         raise ValueError(moboInfo["acquifunc"], " is not a valid acquisition function.")
-    if moboInfo["acquifunc"].lower() == "ehvi":
+    if acq == "ehvi":
         moboInfo["refpointtype"] = "static" if "refpoint" in moboInfo else "dynamic"
     else:
         moboInfo["krignum"] = 1
         moboInfo.setdefault("paregoacquifunc", "EI")
-    if "acquifuncopt" not in moboInfo:
-        moboInfo["acquifuncopt"] = "lbfgsb"
-        print("The acquisition function optimizer is not specified, set to L-BFGS-B.")
-    elif moboInfo["acquifuncopt"].lower() not in ("lbfgsb", "cobyla", "cmaes", "ga", "sweep"):
+    if moboInfo.setdefault("acquifuncopt", "lbfgsb").lower() not in _OPTIMISERS:
         raise ValueError(moboInfo["acquifuncopt"], " is not a valid acquisition function optimizer.")
-    if "nrestart" not in moboInfo:
-        moboInfo["nrestart"] = 1
-        print("The number of restart for acquisition function optimization is not specified, "
-              "setting BayesInfo.nrestart to 1.")
-    elif moboInfo["nrestart"] < 1:
+    if moboInfo.setdefault("nrestart", 1) < 1:
         raise ValueError("BayesInfo['nrestart'] should be at least one")
-    if "filename" not in moboInfo:
-        moboInfo["filename"] = "temporarydata.mat"
-        print("The file name for saving the results is not specified, set the name to temporarydata.mat")
+    moboInfo.setdefault("filename", "temporarydata.mat")
     return moboInfo
