@@ -49,6 +49,20 @@ struct KbPopWs {       // one augmented-matrix workspace (population or fit geom
   int xpop_cap = 0;
 };
 
+// Replayable capture of one host-buffer likelihood call (copy in -> decode -> build -> factor -> GLS ->
+// copy out) for a fixed (B, nbhyp, trainvar, nugget): at KrigDemo / AK-MCS sizes the call is launch-bound
+// (six launches and three copies for ~50 us of device work), and an optimiser repeats the same shape
+// hundreds of times.
+struct KbNllGraph {
+  cudaGraphExec_t exec = nullptr;
+  int B = 0, nbhyp = 0, trainvar = 0;
+  double nugget = 0.0;
+  double* h_x = nullptr;      // pinned staging
+  double* h_nll = nullptr;
+  int* h_info = nullptr;
+  int disabled = 0;           // capture failed once: use plain launches
+};
+
 struct kb_model {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -60,6 +74,7 @@ struct kb_model {
   double* kpls_dtiles = nullptr;   // KPLS: theta-independent per-component squared distances, tile-major
   int* kernel_ids_dev = nullptr;
   KbPopWs pop, fit;
+  KbNllGraph nll_graph;
   // predictor state
   bool fitted = false;
   double* AT = nullptr;
@@ -112,6 +127,14 @@ static KbAugGeom make_geom(int n, int nind, bool fit_mode) {
   g.ld = (g.nb + g.sb) * KB_TILE;
   g.stride = (size_t)g.NT * KB_TILE * g.ld;
   return g;
+}
+
+static void drop_nll_graph(KbNllGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  cudaFreeHost(g.h_x); cudaFreeHost(g.h_nll); cudaFreeHost(g.h_info);
+  const int disabled = g.disabled;
+  g = KbNllGraph{};
+  g.disabled = disabled;
 }
 
 static void free_ws(KbPopWs& w) {
@@ -190,22 +213,38 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
     KB_FAIL(KB_ERR_INVALID, "composite kernel needs %d weights in the hyper-parameter vector", m->nkernel);
   KbModelDev md{m->n, m->d, m->nind, m->n_pad, m->nb, m->kmask, m->XT, m->y, m->F};
   const bool prof = m->profile && (&w == &m->pop);
-  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][0], m->stream));
-  CK(kb_launch_decode(m->stream, B, nbhyp, xpop_dev, m->d, nth, trainvar, has_nugget, has_weights,
-                      fixed_nugget, m->nkernel, m->kernel_ids_dev,
-                      (m->model_type == KB_TYPE_KPLS) ? m->pls : nullptr, w.hp));
-  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][1], m->stream));
-  if (m->kpls_dtiles) CK(kb_launch_build_aug_kpls(m->stream, md, w.g, B, m->h, w.hp, m->kpls_dtiles, w.aug));
-  else CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug, 0));
-  CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
-  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
-  CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.sync_words, w.tasks, w.ntasks, w.info, m->num_sms));
-  if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][3], m->stream));
+  // One-tile designs (n <= 64): a single launch decodes, builds, factors and solves (kb_small.cu)
+  static const char* small_env = getenv("KB_SMALL_NLL");            // debug aid: 0 disables
+  const bool small = (&w == &m->pop) && kb_small_applies(w.g, m->d, m->model_type == KB_TYPE_KPLS) &&
+                     !(small_env && atoi(small_env) == 0);
+  if (small) {
+    if (prof) {
+      CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][0], m->stream));
+      CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][1], m->stream));
+      CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
+    }
+    CK(kb_launch_nll_small(m->stream, md, w.g, B, nbhyp, xpop_dev, nth, trainvar, has_nugget, has_weights,
+                           fixed_nugget, m->nkernel, m->kernel_ids_dev, w.hp, w.aug, w.info));
+    if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][3], m->stream));
+    g_launches += 2;
+  } else {
+    if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][0], m->stream));
+    CK(kb_launch_decode(m->stream, B, nbhyp, xpop_dev, m->d, nth, trainvar, has_nugget, has_weights,
+                        fixed_nugget, m->nkernel, m->kernel_ids_dev,
+                        (m->model_type == KB_TYPE_KPLS) ? m->pls : nullptr, w.hp));
+    if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][1], m->stream));
+    if (m->kpls_dtiles) CK(kb_launch_build_aug_kpls(m->stream, md, w.g, B, m->h, w.hp, m->kpls_dtiles, w.aug));
+    else CK(kb_launch_build_aug(m->stream, md, w.g, B, w.hp, w.aug, 0));
+    CK(cudaMemsetAsync(w.info, 0, sizeof(int) * B, m->stream));
+    if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][2], m->stream));
+    CK(kb_launch_chol(m->stream, w.g, B, w.aug, w.dinv, w.sync_words, w.tasks, w.ntasks, w.info, m->num_sms));
+    if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][3], m->stream));
+  }
   CK(kb_launch_gls(m->stream, w.g, B, w.aug, trainvar, w.hp.sigma2, w.Mbuf, w.beta, w.sigma2, nll_dev,
                    w.info, rt_out, w.lndet));
   if (prof) CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][4], m->stream));
   if (prof) m->pop_calls += 1;
-  g_launches += m->kpls_dtiles ? 5 : 4;
+  if (!small) g_launches += m->kpls_dtiles ? 5 : 4;
   return KB_OK;
 }
 
@@ -303,6 +342,7 @@ void kb_model_destroy(kb_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
+  drop_nll_graph(m->nll_graph);
   free_ws(m->pop);
   free_ws(m->fit);
   cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kpls_dtiles); cudaFree(m->kernel_ids_dev);
@@ -324,6 +364,7 @@ kb_status kb_model_set_stream(kb_model* m, void* cuda_stream) {
   CK(cudaSetDevice(m->device));
   CK(cudaStreamSynchronize(m->stream));
   // caller-owned stream (e.g. torch's current stream); NULL is the legacy default stream
+  drop_nll_graph(m->nll_graph);
   m->stream = (cudaStream_t)cuda_stream;
   return KB_OK;
 }
@@ -394,6 +435,48 @@ kb_status kb_nll_batch(kb_model* m, int B, int nbhyp, const double* xpop, int tr
   if (s != KB_OK) return s;
   s = ensure_xpop(m->pop, B * nbhyp);
   if (s != KB_OK) return s;
+  // Launch-bound shapes (a few tile columns, small populations): replay a captured graph of the whole call.
+  static const char* graph_env = getenv("KB_NLL_GRAPH");            // debug aid: 0 disables
+  KbNllGraph& G = m->nll_graph;
+  const bool want_graph = !m->profile && m->stream == m->own_stream && !G.disabled && m->pop.g.nb <= 4 &&
+                          (size_t)B * m->pop.g.nb <= 256 && !(graph_env && atoi(graph_env) == 0);
+  if (want_graph) {
+    if (!G.exec || G.B != B || G.nbhyp != nbhyp || G.trainvar != trainvar || G.nugget != fixed_nugget_log10) {
+      drop_nll_graph(G);
+      CK(cudaStreamSynchronize(m->stream));
+      cudaGraph_t graph = nullptr;
+      bool ok = cudaMallocHost(&G.h_x, sizeof(double) * B * nbhyp) == cudaSuccess &&
+                cudaMallocHost(&G.h_nll, sizeof(double) * B) == cudaSuccess &&
+                cudaMallocHost(&G.h_info, sizeof(int) * B) == cudaSuccess;
+      if (ok) ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        ok = cudaMemcpyAsync(m->pop.xpop, G.h_x, sizeof(double) * B * nbhyp, cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
+        if (ok) ok = run_pipeline(m, m->pop, B, nbhyp, m->pop.xpop, trainvar, fixed_nugget_log10, m->pop.nll, nullptr) == KB_OK;
+        if (ok) ok = cudaMemcpyAsync(G.h_nll, m->pop.nll, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+        if (ok) ok = cudaMemcpyAsync(G.h_info, m->pop.info, sizeof(int) * B, cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+        const cudaError_t ec = cudaStreamEndCapture(m->stream, &graph);
+        ok = ok && ec == cudaSuccess && graph != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) {
+        cudaGetLastError();
+        G.disabled = 1;                     // plain launches from now on (same kernels)
+        drop_nll_graph(G);
+      } else {
+        G.B = B; G.nbhyp = nbhyp; G.trainvar = trainvar; G.nugget = fixed_nugget_log10;
+      }
+    }
+    if (G.exec) {
+      std::memcpy(G.h_x, xpop, sizeof(double) * B * nbhyp);
+      CK(cudaGraphLaunch(G.exec, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+      std::memcpy(nll_out, G.h_nll, sizeof(double) * B);
+      if (info_out) std::memcpy(info_out, G.h_info, sizeof(int) * B);
+      g_launches += m->kpls_dtiles ? 5 : 4;
+      return KB_OK;
+    }
+  }
   CK(cudaMemcpyAsync(m->pop.xpop, xpop, sizeof(double) * B * nbhyp, cudaMemcpyHostToDevice, m->stream));
   s = run_pipeline(m, m->pop, B, nbhyp, m->pop.xpop, trainvar, fixed_nugget_log10, m->pop.nll, nullptr);
   if (s != KB_OK) return s;

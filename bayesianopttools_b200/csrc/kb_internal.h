@@ -147,6 +147,13 @@ cudaError_t kb_launch_points_lowdisc(cudaStream_t st, double* x, long long npts,
                                      const unsigned int* dirs_dev, const int* primes_dev, const double* lb_dev,
                                      const double* ub_dev, long long first_index);
 
+// kb_small.cu: one-tile designs (n <= 64, at most 16 right-hand-side rows) in a single launch
+bool kb_small_applies(const KbAugGeom& g, int d, bool kpls);
+cudaError_t kb_launch_nll_small(cudaStream_t st, const KbModelDev& m, const KbAugGeom& g, int B, int nbhyp,
+                                const double* xpop_dev, int nth, int trainvar, int has_nugget, int has_weights,
+                                double fixed_nugget, int nkernel, const int* kernel_ids_dev, KbHyper hp, double* aug,
+                                int* info);
+
 // kb_ehvi.cu: 2-objective expected hypervolume improvement (exi2d.py:6-83)
 size_t kb_ehvi_table_doubles(int k);
 void kb_ehvi_build_table(int k, const double* front, const double* ref, double* table);
