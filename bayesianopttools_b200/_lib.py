@@ -59,6 +59,7 @@ _SIGNATURES = [
                                   c_double_p, c_double_p, C.c_int, c_int_p, C.c_int, C.c_int, c_double_p]),
     ("kb_model_destroy", None, [C.c_void_p]),
     ("kb_model_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("kb_model_use_own_stream", C.c_int, [C.c_void_p]),
     ("kb_model_sync", C.c_int, [C.c_void_p]),
     ("kb_nll_batch", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_double, c_double_p,
                                c_int_p]),
@@ -240,7 +241,11 @@ class DeviceModel:
         return tuple(float(v) for v in buf)
 
     def set_stream(self, cuda_stream):
-        check(self._lib.kb_model_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+        """Run on a caller-owned CUDA stream (an integer handle); None returns to the handle's own stream."""
+        if cuda_stream is None:
+            check(self._lib.kb_model_use_own_stream(self._h))
+        else:
+            check(self._lib.kb_model_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def sync(self):
         check(self._lib.kb_model_sync(self._h))

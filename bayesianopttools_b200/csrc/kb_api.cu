@@ -369,6 +369,15 @@ kb_status kb_model_set_stream(kb_model* m, void* cuda_stream) {
   return KB_OK;
 }
 
+kb_status kb_model_use_own_stream(kb_model* m) {
+  if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  drop_nll_graph(m->nll_graph);
+  m->stream = m->own_stream;
+  return KB_OK;
+}
+
 kb_status kb_model_sync(kb_model* m) {
   if (!m) KB_FAIL(KB_ERR_INVALID, "null model");
   CK(cudaSetDevice(m->device));
@@ -435,11 +444,13 @@ kb_status kb_nll_batch(kb_model* m, int B, int nbhyp, const double* xpop, int tr
   if (s != KB_OK) return s;
   s = ensure_xpop(m->pop, B * nbhyp);
   if (s != KB_OK) return s;
-  // Launch-bound shapes (a few tile columns, small populations): replay a captured graph of the whole call.
+  // An optimiser repeats the same call shape hundreds of times: replay a captured graph of the whole call
+  // (most of the gain is at launch-bound sizes, a few tile columns and small populations).
   static const char* graph_env = getenv("KB_NLL_GRAPH");            // debug aid: 0 disables
   KbNllGraph& G = m->nll_graph;
-  const bool want_graph = !m->profile && m->stream == m->own_stream && !G.disabled && m->pop.g.nb <= 4 &&
-                          (size_t)B * m->pop.g.nb <= 256 && !(graph_env && atoi(graph_env) == 0);
+  // (measured: 82 -> 66 us at n=40, 216 -> 198 us at n=500 B=16, 1337 -> 1326 us at n=1000 B=64)
+  const bool want_graph = !m->profile && m->stream == m->own_stream && !G.disabled &&
+                          !(graph_env && atoi(graph_env) == 0);
   if (want_graph) {
     if (!G.exec || G.B != B || G.nbhyp != nbhyp || G.trainvar != trainvar || G.nugget != fixed_nugget_log10) {
       drop_nll_graph(G);

@@ -255,7 +255,7 @@ def run_gpu(args):
         _, r = mdl.predict(cand_pin.numpy(), (), acq="ei", ybest=ybest)
         return t1, r
 
-    mdl.set_stream(0)
+    mdl.set_stream(None)          # the handle's own stream: the host API path a user gets
     step_host()
     barrier()
     e_nll = e_swp = 0.0

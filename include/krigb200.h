@@ -79,6 +79,8 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
                           int model_type, int h, const double* plscoeff);
 void kb_model_destroy(kb_model* m);
 kb_status kb_model_set_stream(kb_model* m, void* cuda_stream);
+/* Back to the stream the handle created for itself (the default after kb_model_create). */
+kb_status kb_model_use_own_stream(kb_model* m);
 kb_status kb_model_sync(kb_model* m);
 
 /* Population-batched negative ln-likelihood.  Replaces `likelihood(x, KrigInfo,
