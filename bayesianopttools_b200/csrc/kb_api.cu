@@ -94,6 +94,7 @@ struct kb_model {
   int pred_grid = 0;
   int pred_resident = 0;
   int pred_stage_x = 1;
+  double* few_scratch = nullptr;   // few-sites predictor (kb_launch_predict_few)
   // host-API staging
   double* stage_x[2] = {nullptr, nullptr};
   double* stage_out[2] = {nullptr, nullptr};
@@ -348,7 +349,7 @@ void kb_model_destroy(kb_model* m) {
   cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kpls_dtiles); cudaFree(m->kernel_ids_dev);
   cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
   cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
-  cudaFree(m->result_dev); cudaFree(m->results_dev);
+  cudaFree(m->result_dev); cudaFree(m->results_dev); cudaFree(m->few_scratch);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->stage_x[i]); cudaFree(m->stage_out[i]);
     if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
@@ -664,6 +665,20 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
   a.resident = m->pred_resident;
   a.stage_x = m->pred_stage_x;
+  // a handful of sites on a large model: spread the single strip over n_pad / 64 CTAs
+  static const char* few_env = getenv("KB_PREDICT_FEW");            // debug aid: 0 disables
+  if (npts <= KB_FEW_MAX && m->pred_resident == 0 && !(few_env && atoi(few_env) == 0)) {
+    if (!m->few_scratch) {
+      const size_t nd = kb_predict_few_scratch_doubles(m->n_pad, a.qx);
+      CK(cudaMalloc(&m->few_scratch, sizeof(double) * nd));
+      CK(cudaMemsetAsync(m->few_scratch, 0, sizeof(double) * nd, m->stream));
+    }
+    if (m->profile) CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][0], m->stream));
+    CK(kb_launch_predict_few(m->stream, a, m->few_scratch, result_dev));
+    if (m->profile) { CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][1], m->stream)); m->pred_calls += 1; }
+    g_launches += 2;
+    return KB_OK;
+  }
   const long long strip = (m->pred_resident == 2) ? 256 : kb_predict_strip(m->pred_resident != 0);
   const long long nstrips = (npts + strip - 1) / strip;
   const int grid = (int)(nstrips < m->pred_grid ? nstrips : m->pred_grid);
@@ -725,6 +740,23 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
     m->results_dev = nullptr;
     CK(cudaMalloc(&m->results_dev, sizeof(KbSweepResult) * (size_t)nchunks));
     m->results_cap = nchunks;
+  }
+  if (nchunks == 1) {
+    // one chunk: nothing to overlap, so no second stream and no events (a local acquisition optimiser
+    // calls this path one design at a time -- every API call saved is latency)
+    CK(cudaMemcpyAsync(m->stage_x[0], x, sizeof(double) * (size_t)npts * m->d, cudaMemcpyHostToDevice, m->stream));
+    double* od[KB_OUT_COUNT];
+    for (int k = 0; k < KB_OUT_COUNT; ++k)
+      od[k] = (slot[k] >= 0) ? m->stage_out[0] + (size_t)slot[k] * m->stage_pts : nullptr;
+    kb_status s1 = kb_predict_dev(m, npts, m->stage_x[0], 0, ap, od, acq, result ? m->results_dev : nullptr);
+    if (s1 != KB_OK) return s1;
+    for (int k = 0; k < KB_OUT_COUNT; ++k)
+      if (slot[k] >= 0)
+        CK(cudaMemcpyAsync(outs[k], od[k], sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, m->stream));
+    if (result)
+      CK(cudaMemcpyAsync(result, m->results_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return KB_OK;
   }
   // the caller's stream may still be using the staging buffers of a previous call
   CK(cudaEventRecord(m->ev_swept[0], m->stream));

@@ -770,6 +770,206 @@ cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid,
   return err;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// A handful of sites (m <= KB_FEW_MAX) on a large model.  The reference's local acquisition optimisers call
+// `prediction` one design at a time (acquifunc_opt.py:45-76, EHVIcomputation.py:40-45); the strip kernel
+// above would push that single strip through ONE CTA (n^2 x 64 flops and the whole inverse factor through
+// one SM: 0.48 ms at n = 1000).  Here the work is spread over n_pad / 64 CTAs twice:
+//   F1  CTA c evaluates psi for training sites [64 c, 64 c + 64) x all m sites and its share of
+//       psi' alpha, psi' R^-1 F;
+//   F2  CTA c owns columns [64 c, 64 c + 64) of L^-1 psi (a tall-skinny product streamed once from L2/HBM)
+//       and their sum of squares; the last CTA to finish (atomic ticket) adds the partials in a fixed order
+//       and finishes the sites exactly as the strip kernel does.
+// ---------------------------------------------------------------------------------------------------
+template <int MASK>
+__global__ void __launch_bounds__(256) kb_predict_few_psi_kernel(KbPredictArgs P, KbFewScratch S) {
+  extern __shared__ __align__(16) double fsm[];
+  const int d = P.d, m = (int)P.m, n_pad = P.n_pad;
+  double* xs = fsm;                        // [KB_FEW_MAX][d] standardised sites
+  double* sgw = xs + KB_FEW_MAX * d;
+  double* sith = sgw + d;
+  double* swk = sith + d;                  // [4]
+  double* psis = swk + 4;                  // [64][KB_FEW_MAX]
+  const int tid = threadIdx.x, cb = blockIdx.x;
+  for (int e = tid; e < KB_FEW_MAX * d; e += 256) {
+    const int sidx = e / d, dim = e - sidx * d;
+    double v = 0.0;
+    if (sidx < m) {
+      v = P.x[(size_t)sidx * d + dim];
+      if (P.norm_type == KB_NORM_DEFAULT) {
+        const double lo = P.p0[dim], hi = P.p1[dim];
+        v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
+      } else if (P.norm_type == KB_NORM_STD) {
+        v = (v - P.p0[dim]) / P.p1[dim];
+      }
+    }
+    xs[e] = v;
+  }
+  for (int i = tid; i < d; i += 256) { sgw[i] = P.gw[i]; sith[i] = P.ith[i]; }
+  if (tid < 4) swk[tid] = P.wk[tid];
+  __syncthreads();
+  const int kl = tid & 63, sg = tid >> 6, k = cb * 64 + kl;
+  KbPairAcc acc[KB_FEW_MAX / 4];
+#pragma unroll
+  for (int t = 0; t < KB_FEW_MAX / 4; ++t) kb_pair_init(acc[t]);
+  for (int dim = 0; dim < d; ++dim) {
+    const double xk = __ldg(P.XT + (size_t)dim * n_pad + k), gw = sgw[dim], ith = sith[dim];
+#pragma unroll
+    for (int t = 0; t < KB_FEW_MAX / 4; ++t) kb_pair_dim(acc[t], xs[(sg + 4 * t) * d + dim] - xk, gw, ith, MASK);
+  }
+#pragma unroll
+  for (int t = 0; t < KB_FEW_MAX / 4; ++t) {
+    const int sidx = sg + 4 * t;
+    double val = kb_pair_finish(acc[t], swk, MASK);
+    if (k >= P.n || sidx >= m) val = 0.0;
+    psis[kl * KB_FEW_MAX + sidx] = val;
+    S.psi[(size_t)k * KB_FEW_MAX + sidx] = val;
+  }
+  __syncthreads();
+  // this block's share of the extra columns: ex[j][s] += sum_k psi[k][s] AT[k][n_pad + j]
+  for (int e = tid; e < P.qx * KB_FEW_MAX; e += 256) {
+    const int j = e / KB_FEW_MAX, sidx = e - j * KB_FEW_MAX;
+    const double* col = P.AT + (size_t)cb * 64 * P.ldat + n_pad + j;
+    double a0 = 0.0, a1 = 0.0;
+    for (int r = 0; r < 64; r += 2) {
+      a0 = fma(psis[r * KB_FEW_MAX + sidx], __ldg(col + (size_t)r * P.ldat), a0);
+      a1 = fma(psis[(r + 1) * KB_FEW_MAX + sidx], __ldg(col + (size_t)(r + 1) * P.ldat), a1);
+    }
+    S.ex[((size_t)cb * P.qx + j) * KB_FEW_MAX + sidx] = a0 + a1;
+  }
+}
+
+#define KB_FEW_CW 16      // columns of L^-1 psi per block of the second kernel
+#define KB_FEW_KG 16      // row groups (threads per column)
+__global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs P, KbFewScratch S,
+                                                                  KbSweepResult* __restrict__ result, int nexb) {
+  __shared__ double part[KB_FEW_KG][KB_FEW_CW][KB_FEW_MAX + 1];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, cb = blockIdx.x, ncb = gridDim.x;
+  const int il = tid & (KB_FEW_CW - 1), kg = tid / KB_FEW_CW, i = cb * KB_FEW_CW + il, m = (int)P.m;
+  double acc[KB_FEW_MAX];
+#pragma unroll
+  for (int t = 0; t < KB_FEW_MAX; ++t) acc[t] = 0.0;
+  const int kend = cb * KB_FEW_CW + KB_FEW_CW - 1;       // L^-1 is lower triangular: rows k <= i only
+  const double* col = P.AT + i;
+#pragma unroll 4
+  for (int k = kg; k <= kend; k += KB_FEW_KG) {
+    const double a = __ldg(col + (size_t)k * P.ldat);
+    const double2* pk = reinterpret_cast<const double2*>(S.psi + (size_t)k * KB_FEW_MAX);
+#pragma unroll
+    for (int t = 0; t < KB_FEW_MAX / 2; ++t) {
+      const double2 pv = __ldg(pk + t);                  // written by the previous kernel, read-only here
+      acc[2 * t] = fma(a, pv.x, acc[2 * t]);
+      acc[2 * t + 1] = fma(a, pv.y, acc[2 * t + 1]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < KB_FEW_MAX; ++t) part[kg][il][t] = acc[t];
+  __syncthreads();
+  if (tid < KB_FEW_MAX) {
+    double s2 = 0.0;
+    for (int c = 0; c < KB_FEW_CW; ++c) {
+      double v = 0.0;
+#pragma unroll
+      for (int g = 0; g < KB_FEW_KG; ++g) v += part[g][c][tid];
+      s2 = fma(v, v, s2);
+    }
+    S.vv[(size_t)cb * KB_FEW_MAX + tid] = s2;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(S.counter, 1) == ncb - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: fixed-order sums of the partials, then the per-site outputs (as section C above) ----
+  KbRunning run;
+  kb_run_init(run);
+  if (tid < m) {
+    const int sidx = tid, d = P.d, qx = P.qx;
+    double vv = 0.0;
+    for (int c = 0; c < ncb; ++c) vv += __ldcg(&S.vv[(size_t)c * KB_FEW_MAX + sidx]);
+    double* ex0 = S.ex + sidx;                       // block 0's slots hold the totals: ex0[j * KB_FEW_MAX]
+    for (int j = 0; j < qx; ++j) {
+      double t = 0.0;
+      for (int c = 0; c < nexb; ++c) t += __ldcg(&S.ex[((size_t)c * qx + j) * KB_FEW_MAX + sidx]);
+      ex0[(size_t)j * KB_FEW_MAX] = t;
+    }
+    double fpc, t2;
+    if (P.idx == nullptr) {
+      fpc = P.beta[0];
+      const double u = (ex0[KB_FEW_MAX] - 1.0) / P.LM[0];
+      t2 = u * u;
+    } else {
+      fpc = 0.0;
+      t2 = 0.0;
+      const int nind = P.nind;
+      for (int a = 0; a < nind; ++a) {
+        double pc = 1.0;
+        for (int dim = 0; dim < d; ++dim) {
+          const int o = P.idx[a * d + dim];
+          if (o) {
+            double v = P.x[(size_t)sidx * d + dim];
+            if (P.norm_type == KB_NORM_DEFAULT) {
+              const double lo = P.p0[dim], hi = P.p1[dim];
+              v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
+            } else if (P.norm_type == KB_NORM_STD) {
+              v = (v - P.p0[dim]) / P.p1[dim];
+            }
+            pc *= kb_legendre_on(o, v);
+          }
+        }
+        fpc = fma(pc, P.beta[a], fpc);
+        double u = ex0[(size_t)(1 + a) * KB_FEW_MAX] - pc;
+        for (int c = 0; c < a; ++c) u = fma(-P.LM[(size_t)a * nind + c], ex0[(size_t)(1 + c) * KB_FEW_MAX], u);
+        u /= P.LM[(size_t)a * nind + a];
+        ex0[(size_t)(1 + a) * KB_FEW_MAX] = u;
+        t2 = fma(u, u, t2);
+      }
+    }
+    kb_acq_site(P, fpc, ex0[0], vv, t2, sidx, run);
+  }
+  if (tid < 32) {
+    KbSweepResult r = kb_run_warp_reduce(run);
+    if (tid == 0) {
+      r.n_points = P.m;
+      if (result) *result = r;
+      *S.counter = 0;
+    }
+  }
+}
+
+template <int MASK>
+static cudaError_t kb_predict_few_psi_launch(cudaStream_t st, const KbPredictArgs& a, const KbFewScratch& S, int ncb,
+                                             size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_few_psi_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  kb_predict_few_psi_kernel<MASK><<<ncb, 256, smem, st>>>(a, S);
+  return cudaGetLastError();
+}
+
+size_t kb_predict_few_scratch_doubles(int n_pad, int qx) {
+  const size_t ncb = n_pad / 64, ncb2 = n_pad / KB_FEW_CW;
+  return (size_t)n_pad * KB_FEW_MAX + ncb * qx * KB_FEW_MAX + ncb2 * KB_FEW_MAX + 2;
+}
+
+cudaError_t kb_launch_predict_few(cudaStream_t st, const KbPredictArgs& a, double* scratch, KbSweepResult* result_dev) {
+  const int ncb = a.n_pad / 64;
+  KbFewScratch S;
+  S.psi = scratch;
+  S.ex = S.psi + (size_t)a.n_pad * KB_FEW_MAX;
+  S.vv = S.ex + (size_t)ncb * a.qx * KB_FEW_MAX;
+  const int ncb2 = a.n_pad / KB_FEW_CW;
+  S.counter = reinterpret_cast<int*>(S.vv + (size_t)ncb2 * KB_FEW_MAX);
+  const size_t smem = sizeof(double) * ((size_t)KB_FEW_MAX * a.d + 2 * a.d + 4 + 64 * KB_FEW_MAX);
+  cudaError_t err = cudaSuccess;
+  KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_few_psi_launch<M_>(st, a, S, ncb, smem)));
+  if (err != cudaSuccess) return err;
+  kb_predict_few_gemv_kernel<<<ncb2, 256, 0, st>>>(a, S, result_dev, ncb);
+  return cudaGetLastError();
+}
+
 // Largest persistent grid for the predict kernel: SMs x resident CTAs per SM.
 int kb_predict_max_grid(int kmask, int d, int num_sms, int resident, int n_pad, int qx, int stage_x) {
   const size_t smem = kb_predict_smem_bytes(d, resident != 0, n_pad, qx, stage_x);

@@ -411,3 +411,45 @@ def test_wide_input_predictor_without_strip_staging(lib):
         pw = ko.predict(Xw[:7] + 0.01, Xw, yw, np.ones((40, 1)), np.zeros((1, 200), int), fitw)
         assert relerr(outs["pred"], pw["pred"]) < 2e-8
     big.close()
+
+
+@pytest.mark.parametrize("n,d,order,kernel,kpls_h", [(1000, 10, 0, "gaussian", 0), (300, 4, 2, "matern52", 0),
+                                                     (200, 3, 1, "exponential", 0), (400, 30, 0, "gaussian", 3)])
+def test_few_sites_predictor_matches_strip_kernel_and_oracle(lib, n, d, order, kernel, kpls_h):
+    """One to sixteen sites on a model too large for the resident variants take the few-sites kernels
+    (the strip spread over n_pad / 64 CTAs): same outputs, arg-min and counters as the strip kernel on
+    the same sites (summation order differs: 1e-11) and as the oracle."""
+    rng = np.random.default_rng(n + d)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sum(np.sin(2 * X[:, :4]) + 0.2 * X[:, :4] ** 2, axis=1) - 0.3
+    idx = ko.total_order_index(order, d)
+    F = ko.legendre_basis(idx, X)
+    pls = rng.normal(size=(d, kpls_h)) / np.sqrt(d) if kpls_h else None
+    nth = kpls_h or d
+    th = rng.uniform(-0.2, 0.5, nth)
+    mdl = lib.DeviceModel(X, y, F, [kernel], model_type="kpls" if kpls_h else "kriging", plscoeff=pls)
+    mdl.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
+    mdl.set_trend(idx)
+    lbv, ubv = -1.5 * np.ones(d), 1.2 * np.ones(d)
+    mdl.set_norm(lib.NORM_DEFAULT, lbv, ubv)
+    kw = dict(kernels=(kernel,), plscoeff=pls, n_princomp=kpls_h or None) if kpls_h else dict(kernels=(kernel,))
+    fit = ko.nll(th, X, y, F, full=True, **kw)
+    xq = rng.uniform(-1.4, 1.1, (40, d))
+    want = ("pred", "ssqr", "s", "ei", "poi", "pof", "lcb", "u")
+    acq = dict(acq="ei", ybest=float(y.min()), limit=0.1, limit_sign=1, sigmalcb=2.0)
+    strip, rs = mdl.predict(xq, want, **acq)
+    p = ko.predict(ko.standardize_x(xq, lbv, ubv), X, y, F, idx, fit, kernels=(kernel,), plscoeff=pls,
+                   ybest=float(y.min()), limit=0.1, limittype=">=", sigmalcb=2.0)
+    for msites in (1, 7, 16):
+        few, rf = mdl.predict(xq[:msites], want, **acq)
+        for k in want:
+            assert relerr(few[k], strip[k][:msites]) < 1e-10, (k, msites)
+        assert relerr(few["pred"], p["pred"][:msites]) < 2e-8 and relerr(few["ssqr"], p["ssqr"][:msites]) < 2e-8
+        assert rf["best_idx"] == int(np.argmin(strip["ei"][:msites])) and rf["n_points"] == msites
+        assert rf["n_fail"] == int(np.sum(strip["pred"][:msites] <= 0))
+        assert rf["min_u_idx"] == int(np.argmin(strip["u"][:msites]))
+    # repeated calls reuse the block counter: same numbers every time
+    a, _ = mdl.predict(xq[:3], ("ei",), **acq)
+    b, _ = mdl.predict(xq[:3], ("ei",), **acq)
+    assert np.array_equal(a["ei"], b["ei"])
+    mdl.close()
