@@ -266,15 +266,29 @@ class DeviceModel:
                     nugget=nug.value, wgkf=wg)
 
     def set_trend(self, idx):
+        """Trend multi-index (nind x d).  The reference-facing layer calls this before every prediction;
+        an unchanged table is not uploaded again."""
         idx = np.ascontiguousarray(idx, dtype=np.int32)
+        key = (idx.shape, idx.tobytes())
+        if getattr(self, "_trend_key", None) == key:
+            return
         check(self._lib.kb_model_set_trend(self._h, idx.ctypes.data_as(c_int_p), idx.shape[0], idx.shape[1]))
+        self._trend_key = key
 
     def set_norm(self, norm_type, p0=None, p1=None):
+        """Input normalisation of the predictor (unchanged parameters are not uploaded again)."""
         if norm_type == NORM_NONE:
+            key = (NORM_NONE,)
+            if getattr(self, "_norm_key", None) == key:
+                return
             check(self._lib.kb_model_set_norm(self._h, NORM_NONE, None, None))
         else:
             p0, p1 = _f64(np.asarray(p0).reshape(-1)), _f64(np.asarray(p1).reshape(-1))
+            key = (norm_type, p0.tobytes(), p1.tobytes())
+            if getattr(self, "_norm_key", None) == key:
+                return
             check(self._lib.kb_model_set_norm(self._h, norm_type, _dp(p0), _dp(p1)))
+        self._norm_key = key
 
     def loocv(self):
         pred = np.empty(self.n)
