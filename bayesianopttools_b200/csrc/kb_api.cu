@@ -95,6 +95,7 @@ struct kb_model {
   int pred_resident = 0;
   int pred_stage_x = 1;
   double* few_scratch = nullptr;   // few-sites predictor (kb_launch_predict_few)
+  int few_slices = 0;              // slices of 16 sites the scratch is sized for
   // host-API staging
   double* stage_x[2] = {nullptr, nullptr};
   double* stage_out[2] = {nullptr, nullptr};
@@ -667,16 +668,27 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   a.stage_x = m->pred_stage_x;
   // a handful of sites on a large model: spread the single strip over n_pad / 64 CTAs
   static const char* few_env = getenv("KB_PREDICT_FEW");            // debug aid: 0 disables
-  if (npts <= KB_FEW_MAX && m->pred_resident == 0 && !(few_env && atoi(few_env) == 0)) {
-    if (!m->few_scratch) {
-      const size_t nd = kb_predict_few_scratch_doubles(m->n_pad, a.qx);
+  const int few_ny = npts <= (long long)KB_FEW_MAX * KB_FEW_MAX_SLICES ? kb_predict_few_slices(npts) : 0;
+  // the scratch grows with the slice count; cap it at 256 MB (many regressors on a large design)
+  const bool few_fits = few_ny > 0 &&
+                        kb_predict_few_scratch_doubles(m->n_pad, a.qx, few_ny) * sizeof(double) <= (256u << 20);
+  if (few_fits && m->pred_resident == 0 && !(few_env && atoi(few_env) == 0)) {
+    if (few_ny > m->few_slices) {
+      CK(cudaStreamSynchronize(m->stream));
+      cudaFree(m->few_scratch);
+      m->few_scratch = nullptr;
+      int cap = m->few_slices > 0 ? m->few_slices : 1;
+      while (cap < few_ny) cap *= 2;
+      while (cap > few_ny && kb_predict_few_scratch_doubles(m->n_pad, a.qx, cap) * sizeof(double) > (256u << 20)) --cap;
+      const size_t nd = kb_predict_few_scratch_doubles(m->n_pad, a.qx, cap);
       CK(cudaMalloc(&m->few_scratch, sizeof(double) * nd));
       CK(cudaMemsetAsync(m->few_scratch, 0, sizeof(double) * nd, m->stream));
+      m->few_slices = cap;
     }
     if (m->profile) CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][0], m->stream));
-    CK(kb_launch_predict_few(m->stream, a, m->few_scratch, result_dev));
+    CK(kb_launch_predict_few(m->stream, a, m->few_scratch, m->few_slices, result_dev));
     if (m->profile) { CK(cudaEventRecord(m->evp[m->pred_calls % KB_PROF_RING][1], m->stream)); m->pred_calls += 1; }
-    g_launches += 2;
+    g_launches += (result_dev && few_ny > 1) ? 3 : 2;
     return KB_OK;
   }
   const long long strip = (m->pred_resident == 2) ? 256 : kb_predict_strip(m->pred_resident != 0);

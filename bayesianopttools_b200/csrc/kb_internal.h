@@ -130,16 +130,20 @@ struct KbPredictArgs {
   KbSweepResult* partials; // [grid]
 };
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev);
-// few-sites path (m <= KB_FEW_MAX on a model that does not fit the resident variants)
+// few-sites path: slices of KB_FEW_MAX sites on a model that does not fit the resident variants
 #define KB_FEW_MAX 16
+#define KB_FEW_MAX_SLICES 96
 struct KbFewScratch {
-  double* psi;     // [n_pad][KB_FEW_MAX]
-  double* ex;      // [n_pad/64][qx][KB_FEW_MAX]  per-block partial sums of the extra columns
-  double* vv;      // [n_pad/16][KB_FEW_MAX]      per-block partial sums of squares
-  int* counter;    // finished blocks of the second kernel (reset by the last one)
+  double* psi;            // [slices][n_pad][KB_FEW_MAX]
+  double* ex;             // [slices][n_pad/64][qx][KB_FEW_MAX]  per-block partial sums of the extra columns
+  double* vv;             // [slices][n_pad/16][KB_FEW_MAX]      per-block partial sums of squares
+  KbSweepResult* slices;  // [slices] reductions of each slice
+  int* counter;           // [slices] finished blocks of the second kernel (reset by the last one)
 };
-size_t kb_predict_few_scratch_doubles(int n_pad, int qx);
-cudaError_t kb_launch_predict_few(cudaStream_t st, const KbPredictArgs& a, double* scratch, KbSweepResult* result_dev);
+int kb_predict_few_slices(long long m);
+size_t kb_predict_few_scratch_doubles(int n_pad, int qx, int ny);
+cudaError_t kb_launch_predict_few(cudaStream_t st, const KbPredictArgs& a, double* scratch, int ny_cap,
+                                  KbSweepResult* result_dev);
 size_t kb_predict_smem_bytes(int d, bool resident, int n_pad, int qx, int stage_x);
 bool kb_predict_can_reside(int d, int n_pad, int qx, int nind_trend);
 int kb_predict_strip(bool resident);

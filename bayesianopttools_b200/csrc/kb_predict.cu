@@ -784,7 +784,11 @@ cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid,
 template <int MASK>
 __global__ void __launch_bounds__(256) kb_predict_few_psi_kernel(KbPredictArgs P, KbFewScratch S) {
   extern __shared__ __align__(16) double fsm[];
-  const int d = P.d, m = (int)P.m, n_pad = P.n_pad;
+  const int d = P.d, n_pad = P.n_pad, slice = blockIdx.y;
+  const int m = (int)((P.m - (long long)slice * KB_FEW_MAX < KB_FEW_MAX) ? (P.m - (long long)slice * KB_FEW_MAX) : KB_FEW_MAX);
+  const double* xsl = P.x + (size_t)slice * KB_FEW_MAX * d;          // this slice's raw sites
+  double* Spsi = S.psi + (size_t)slice * n_pad * KB_FEW_MAX;
+  double* Sex = S.ex + (size_t)slice * gridDim.x * P.qx * KB_FEW_MAX;
   double* xs = fsm;                        // [KB_FEW_MAX][d] standardised sites
   double* sgw = xs + KB_FEW_MAX * d;
   double* sith = sgw + d;
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(256) kb_predict_few_psi_kernel(KbPredictArgs P
     const int sidx = e / d, dim = e - sidx * d;
     double v = 0.0;
     if (sidx < m) {
-      v = P.x[(size_t)sidx * d + dim];
+      v = xsl[(size_t)sidx * d + dim];
       if (P.norm_type == KB_NORM_DEFAULT) {
         const double lo = P.p0[dim], hi = P.p1[dim];
         v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
@@ -823,7 +827,7 @@ __global__ void __launch_bounds__(256) kb_predict_few_psi_kernel(KbPredictArgs P
     double val = kb_pair_finish(acc[t], swk, MASK);
     if (k >= P.n || sidx >= m) val = 0.0;
     psis[kl * KB_FEW_MAX + sidx] = val;
-    S.psi[(size_t)k * KB_FEW_MAX + sidx] = val;
+    Spsi[(size_t)k * KB_FEW_MAX + sidx] = val;
   }
   __syncthreads();
   // this block's share of the extra columns: ex[j][s] += sum_k psi[k][s] AT[k][n_pad + j]
@@ -835,7 +839,7 @@ __global__ void __launch_bounds__(256) kb_predict_few_psi_kernel(KbPredictArgs P
       a0 = fma(psis[r * KB_FEW_MAX + sidx], __ldg(col + (size_t)r * P.ldat), a0);
       a1 = fma(psis[(r + 1) * KB_FEW_MAX + sidx], __ldg(col + (size_t)(r + 1) * P.ldat), a1);
     }
-    S.ex[((size_t)cb * P.qx + j) * KB_FEW_MAX + sidx] = a0 + a1;
+    Sex[((size_t)cb * P.qx + j) * KB_FEW_MAX + sidx] = a0 + a1;
   }
 }
 
@@ -846,7 +850,12 @@ __global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs 
   __shared__ double part[KB_FEW_KG][KB_FEW_CW][KB_FEW_MAX + 1];
   __shared__ int s_last;
   const int tid = threadIdx.x, cb = blockIdx.x, ncb = gridDim.x;
-  const int il = tid & (KB_FEW_CW - 1), kg = tid / KB_FEW_CW, i = cb * KB_FEW_CW + il, m = (int)P.m;
+  const int il = tid & (KB_FEW_CW - 1), kg = tid / KB_FEW_CW, i = cb * KB_FEW_CW + il, slice = blockIdx.y;
+  const int m = (int)((P.m - (long long)slice * KB_FEW_MAX < KB_FEW_MAX) ? (P.m - (long long)slice * KB_FEW_MAX) : KB_FEW_MAX);
+  const double* Spsi = S.psi + (size_t)slice * P.n_pad * KB_FEW_MAX;
+  double* Sex = S.ex + (size_t)slice * nexb * P.qx * KB_FEW_MAX;
+  double* Svv = S.vv + (size_t)slice * ncb * KB_FEW_MAX;
+  const double* xsl = P.x + (size_t)slice * KB_FEW_MAX * P.d;
   double acc[KB_FEW_MAX];
 #pragma unroll
   for (int t = 0; t < KB_FEW_MAX; ++t) acc[t] = 0.0;
@@ -855,7 +864,7 @@ __global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs 
 #pragma unroll 4
   for (int k = kg; k <= kend; k += KB_FEW_KG) {
     const double a = __ldg(col + (size_t)k * P.ldat);
-    const double2* pk = reinterpret_cast<const double2*>(S.psi + (size_t)k * KB_FEW_MAX);
+    const double2* pk = reinterpret_cast<const double2*>(Spsi + (size_t)k * KB_FEW_MAX);
 #pragma unroll
     for (int t = 0; t < KB_FEW_MAX / 2; ++t) {
       const double2 pv = __ldg(pk + t);                  // written by the previous kernel, read-only here
@@ -874,11 +883,11 @@ __global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs 
       for (int g = 0; g < KB_FEW_KG; ++g) v += part[g][c][tid];
       s2 = fma(v, v, s2);
     }
-    S.vv[(size_t)cb * KB_FEW_MAX + tid] = s2;
+    Svv[(size_t)cb * KB_FEW_MAX + tid] = s2;
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(S.counter, 1) == ncb - 1) ? 1 : 0;
+  if (tid == 0) s_last = (atomicAdd(S.counter + slice, 1) == ncb - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -888,11 +897,11 @@ __global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs 
   if (tid < m) {
     const int sidx = tid, d = P.d, qx = P.qx;
     double vv = 0.0;
-    for (int c = 0; c < ncb; ++c) vv += __ldcg(&S.vv[(size_t)c * KB_FEW_MAX + sidx]);
-    double* ex0 = S.ex + sidx;                       // block 0's slots hold the totals: ex0[j * KB_FEW_MAX]
+    for (int c = 0; c < ncb; ++c) vv += __ldcg(&Svv[(size_t)c * KB_FEW_MAX + sidx]);
+    double* ex0 = Sex + sidx;                        // block 0's slots hold the totals: ex0[j * KB_FEW_MAX]
     for (int j = 0; j < qx; ++j) {
       double t = 0.0;
-      for (int c = 0; c < nexb; ++c) t += __ldcg(&S.ex[((size_t)c * qx + j) * KB_FEW_MAX + sidx]);
+      for (int c = 0; c < nexb; ++c) t += __ldcg(&Sex[((size_t)c * qx + j) * KB_FEW_MAX + sidx]);
       ex0[(size_t)j * KB_FEW_MAX] = t;
     }
     double fpc, t2;
@@ -909,7 +918,7 @@ __global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs 
         for (int dim = 0; dim < d; ++dim) {
           const int o = P.idx[a * d + dim];
           if (o) {
-            double v = P.x[(size_t)sidx * d + dim];
+            double v = xsl[(size_t)sidx * d + dim];
             if (P.norm_type == KB_NORM_DEFAULT) {
               const double lo = P.p0[dim], hi = P.p1[dim];
               v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
@@ -927,47 +936,59 @@ __global__ void __launch_bounds__(256) kb_predict_few_gemv_kernel(KbPredictArgs 
         t2 = fma(u, u, t2);
       }
     }
-    kb_acq_site(P, fpc, ex0[0], vv, t2, sidx, run);
+    kb_acq_site(P, fpc, ex0[0], vv, t2, (long long)slice * KB_FEW_MAX + sidx, run);
   }
   if (tid < 32) {
     KbSweepResult r = kb_run_warp_reduce(run);
     if (tid == 0) {
-      r.n_points = P.m;
-      if (result) *result = r;
-      *S.counter = 0;
+      r.n_points = m;
+      S.slices[slice] = r;                 // merged over the slices by kb_sweep_final_kernel
+      if (result && gridDim.y == 1) { r.n_points = P.m; *result = r; }
+      S.counter[slice] = 0;
     }
   }
 }
 
 template <int MASK>
 static cudaError_t kb_predict_few_psi_launch(cudaStream_t st, const KbPredictArgs& a, const KbFewScratch& S, int ncb,
-                                             size_t smem) {
+                                             int ny, size_t smem) {
   cudaError_t e = cudaFuncSetAttribute(kb_predict_few_psi_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_few_psi_kernel<MASK><<<ncb, 256, smem, st>>>(a, S);
+  kb_predict_few_psi_kernel<MASK><<<dim3(ncb, ny), 256, smem, st>>>(a, S);
   return cudaGetLastError();
 }
 
-size_t kb_predict_few_scratch_doubles(int n_pad, int qx) {
+int kb_predict_few_slices(long long m) { return (int)((m + KB_FEW_MAX - 1) / KB_FEW_MAX); }
+
+// doubles of scratch for ny slices of KB_FEW_MAX sites
+size_t kb_predict_few_scratch_doubles(int n_pad, int qx, int ny) {
   const size_t ncb = n_pad / 64, ncb2 = n_pad / KB_FEW_CW;
-  return (size_t)n_pad * KB_FEW_MAX + ncb * qx * KB_FEW_MAX + ncb2 * KB_FEW_MAX + 2;
+  const size_t per_slice = (size_t)n_pad * KB_FEW_MAX + ncb * qx * KB_FEW_MAX + ncb2 * KB_FEW_MAX;
+  return per_slice * ny + (size_t)ny * (sizeof(KbSweepResult) / sizeof(double)) + (size_t)(ny + 1) / 2 + 2;
 }
 
-cudaError_t kb_launch_predict_few(cudaStream_t st, const KbPredictArgs& a, double* scratch, KbSweepResult* result_dev) {
-  const int ncb = a.n_pad / 64;
+cudaError_t kb_launch_predict_few(cudaStream_t st, const KbPredictArgs& a, double* scratch, int ny_cap,
+                                  KbSweepResult* result_dev) {
+  const int ncb = a.n_pad / 64, ncb2 = a.n_pad / KB_FEW_CW, ny = kb_predict_few_slices(a.m);
+  if (ny > ny_cap) return cudaErrorInvalidValue;
   KbFewScratch S;
   S.psi = scratch;
-  S.ex = S.psi + (size_t)a.n_pad * KB_FEW_MAX;
-  S.vv = S.ex + (size_t)ncb * a.qx * KB_FEW_MAX;
-  const int ncb2 = a.n_pad / KB_FEW_CW;
-  S.counter = reinterpret_cast<int*>(S.vv + (size_t)ncb2 * KB_FEW_MAX);
+  S.ex = S.psi + (size_t)ny_cap * a.n_pad * KB_FEW_MAX;
+  S.vv = S.ex + (size_t)ny_cap * ncb * a.qx * KB_FEW_MAX;
+  S.slices = reinterpret_cast<KbSweepResult*>(S.vv + (size_t)ny_cap * ncb2 * KB_FEW_MAX);
+  S.counter = reinterpret_cast<int*>(S.slices + ny_cap);
   const size_t smem = sizeof(double) * ((size_t)KB_FEW_MAX * a.d + 2 * a.d + 4 + 64 * KB_FEW_MAX);
   cudaError_t err = cudaSuccess;
-  KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_few_psi_launch<M_>(st, a, S, ncb, smem)));
+  KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_few_psi_launch<M_>(st, a, S, ncb, ny, smem)));
   if (err != cudaSuccess) return err;
-  kb_predict_few_gemv_kernel<<<ncb2, 256, 0, st>>>(a, S, result_dev, ncb);
-  return cudaGetLastError();
+  kb_predict_few_gemv_kernel<<<dim3(ncb2, ny), 256, 0, st>>>(a, S, result_dev, ncb);
+  err = cudaGetLastError();
+  if (err == cudaSuccess && result_dev && ny > 1) {
+    kb_sweep_final_kernel<<<1, 32, 0, st>>>(S.slices, ny, a.m, result_dev);
+    err = cudaGetLastError();
+  }
+  return err;
 }
 
 // Largest persistent grid for the predict kernel: SMs x resident CTAs per SM.

@@ -416,9 +416,10 @@ def test_wide_input_predictor_without_strip_staging(lib):
 @pytest.mark.parametrize("n,d,order,kernel,kpls_h", [(1000, 10, 0, "gaussian", 0), (300, 4, 2, "matern52", 0),
                                                      (200, 3, 1, "exponential", 0), (400, 30, 0, "gaussian", 3)])
 def test_few_sites_predictor_matches_strip_kernel_and_oracle(lib, n, d, order, kernel, kpls_h):
-    """One to sixteen sites on a model too large for the resident variants take the few-sites kernels
-    (the strip spread over n_pad / 64 CTAs): same outputs, arg-min and counters as the strip kernel on
-    the same sites (summation order differs: 1e-11) and as the oracle."""
+    """Up to 1536 sites on a model too large for the resident variants take the few-sites kernels (slices of
+    16 sites, each spread over n_pad / 64 + n_pad / 16 CTAs) instead of one CTA per 64-site strip: same
+    outputs, arg-min and counters as the strip kernel on the same sites (summation order differs: 1e-9)
+    and as the oracle."""
     rng = np.random.default_rng(n + d)
     X = rng.uniform(-1, 1, (n, d))
     y = np.sum(np.sin(2 * X[:, :4]) + 0.2 * X[:, :4] ** 2, axis=1) - 0.3
@@ -434,16 +435,17 @@ def test_few_sites_predictor_matches_strip_kernel_and_oracle(lib, n, d, order, k
     mdl.set_norm(lib.NORM_DEFAULT, lbv, ubv)
     kw = dict(kernels=(kernel,), plscoeff=pls, n_princomp=kpls_h or None) if kpls_h else dict(kernels=(kernel,))
     fit = ko.nll(th, X, y, F, full=True, **kw)
-    xq = rng.uniform(-1.4, 1.1, (40, d))
+    xq = rng.uniform(-1.4, 1.1, (1700, d))             # 1700 > 1536: this call runs the strip kernel
     want = ("pred", "ssqr", "s", "ei", "poi", "pof", "lcb", "u")
     acq = dict(acq="ei", ybest=float(y.min()), limit=0.1, limit_sign=1, sigmalcb=2.0)
     strip, rs = mdl.predict(xq, want, **acq)
     p = ko.predict(ko.standardize_x(xq, lbv, ubv), X, y, F, idx, fit, kernels=(kernel,), plscoeff=pls,
                    ybest=float(y.min()), limit=0.1, limittype=">=", sigmalcb=2.0)
-    for msites in (1, 7, 16):
+    for msites in (1, 7, 16, 17, 100, 1536):
         few, rf = mdl.predict(xq[:msites], want, **acq)
         for k in want:
-            assert relerr(few[k], strip[k][:msites]) < 1e-10, (k, msites)
+            # tail probabilities and |f|/s near training sites amplify the 1e-13 differences of the summation order
+            assert relerr(few[k], strip[k][:msites]) < (1e-7 if k in ("ei", "poi", "pof", "u") else 1e-9), (k, msites)
         assert relerr(few["pred"], p["pred"][:msites]) < 2e-8 and relerr(few["ssqr"], p["ssqr"][:msites]) < 2e-8
         assert rf["best_idx"] == int(np.argmin(strip["ei"][:msites])) and rf["n_points"] == msites
         assert rf["n_fail"] == int(np.sum(strip["pred"][:msites] <= 0))
