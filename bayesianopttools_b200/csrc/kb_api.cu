@@ -94,6 +94,16 @@ struct kb_model {
   int pred_grid = 0;
   int pred_resident = 0;
   int pred_stage_x = 1;
+  // 2-objective EHVI workspace (kept on the first objective's handle: the acquisition is called in a loop)
+  struct {
+    double *xd = nullptr, *buf = nullptr, *table = nullptr;
+    void* red = nullptr;
+    long long cap_pts = 0;
+    int cap_grid = 0;
+    size_t cap_table = 0;
+    cudaEvent_t ev_x = nullptr, ev_p2 = nullptr;
+    std::vector<double> key;       // front | ref of the table currently on the device
+  } ehvi;
   double* few_scratch = nullptr;   // few-sites predictor (kb_launch_predict_few)
   int few_slices = 0;              // slices of 16 sites the scratch is sized for
   // host-API staging
@@ -351,6 +361,9 @@ void kb_model_destroy(kb_model* m) {
   cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
   cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
   cudaFree(m->result_dev); cudaFree(m->results_dev); cudaFree(m->few_scratch);
+  cudaFree(m->ehvi.xd); cudaFree(m->ehvi.buf); cudaFree(m->ehvi.table); cudaFree(m->ehvi.red);
+  if (m->ehvi.ev_x) cudaEventDestroy(m->ehvi.ev_x);
+  if (m->ehvi.ev_p2) cudaEventDestroy(m->ehvi.ev_p2);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->stage_x[i]); cudaFree(m->stage_out[i]);
     if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
@@ -1032,20 +1045,55 @@ static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const d
     KB_FAIL(KB_ERR_INVALID, "the two objective models must share the device and the input dimension");
   if (!m1->fitted || !m2->fitted) KB_FAIL(KB_ERR_STATE, "ehvi called before kb_fit_state");
   CK(cudaSetDevice(m1->device));
-  double* table_dev = nullptr;
-  kb_status st = ehvi_table_to_device(k, front, ref, &table_dev);
-  if (st != KB_OK) return st;
+  if (k < 1 || !front || !ref) KB_FAIL(KB_ERR_INVALID, "bad Pareto front");
+  auto& W = m1->ehvi;
   const long long chunk = npts < (1LL << 20) ? npts : (1LL << 20);
   const int d = m1->d;
   const int grid = kb_ehvi_grid(chunk, m1->num_sms);
-  double *xd = nullptr, *buf = nullptr;
-  void* red = nullptr;
-  cudaEvent_t ev_x = nullptr, ev_p2 = nullptr;
-  cudaError_t e = x_on_device ? cudaSuccess : cudaMalloc(&xd, sizeof(double) * (size_t)chunk * d);
-  if (e == cudaSuccess) e = cudaMalloc(&buf, sizeof(double) * (size_t)5 * chunk);
-  if (e == cudaSuccess) e = cudaMalloc(&red, sizeof(KbEhviBestHost) * (size_t)(grid + 1));
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_p2, cudaEventDisableTiming);
+  // persistent workspace: the acquisition is evaluated in a loop by the optimisers
+  if (!W.ev_x) {
+    CK(cudaEventCreateWithFlags(&W.ev_x, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&W.ev_p2, cudaEventDisableTiming));
+  }
+  if (chunk > W.cap_pts || grid > W.cap_grid) {
+    CK(cudaStreamSynchronize(m1->stream));
+    CK(cudaStreamSynchronize(m2->stream));
+    cudaFree(W.xd); cudaFree(W.buf); cudaFree(W.red);
+    W.xd = W.buf = nullptr; W.red = nullptr;
+    const long long cp = chunk > W.cap_pts ? chunk : W.cap_pts;
+    const int cg = kb_ehvi_grid(cp, m1->num_sms);
+    CK(cudaMalloc(&W.xd, sizeof(double) * (size_t)cp * d));
+    CK(cudaMalloc(&W.buf, sizeof(double) * (size_t)5 * cp));
+    CK(cudaMalloc(&W.red, sizeof(KbEhviBestHost) * (size_t)(cg + 1)));
+    W.cap_pts = cp; W.cap_grid = cg;
+  }
+  // the cell table depends on the front and the reference point only: rebuilt when they change
+  {
+    std::vector<double> key((size_t)2 * k + 2);
+    std::memcpy(key.data(), front, sizeof(double) * 2 * k);
+    key[2 * k] = ref[0]; key[2 * k + 1] = ref[1];
+    if (key != W.key) {
+      std::vector<double> table(kb_ehvi_table_doubles(k));
+      kb_ehvi_build_table(k, front, ref, table.data());
+      CK(cudaStreamSynchronize(m1->stream));
+      if (table.size() > W.cap_table) {
+        cudaFree(W.table);
+        W.table = nullptr;
+        CK(cudaMalloc(&W.table, sizeof(double) * table.size()));
+        W.cap_table = table.size();
+      }
+      CK(cudaMemcpy(W.table, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+      W.key.swap(key);
+    }
+  }
+  double* const table_dev = W.table;
+  double* const xd = W.xd;
+  double* const buf = W.buf;
+  void* const red = W.red;
+  const cudaEvent_t ev_x = W.ev_x, ev_p2 = W.ev_p2;
+  const long long bstride = W.cap_pts;          // the five result arrays are cap_pts apart
+  kb_status st = KB_OK;
+  cudaError_t e = cudaSuccess;
   const int sid = spread ? KB_OUT_S : KB_OUT_SSQR;
   for (long long off = 0; off < npts && e == cudaSuccess && st == KB_OK; off += chunk) {
     const long long cur = (npts - off < chunk) ? (npts - off) : chunk;
@@ -1062,8 +1110,8 @@ static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const d
     if (e != cudaSuccess) break;
     double* o1[KB_OUT_COUNT] = {nullptr};
     double* o2[KB_OUT_COUNT] = {nullptr};
-    o1[KB_OUT_PRED] = buf; o1[sid] = buf + chunk;
-    o2[KB_OUT_PRED] = buf + 2 * chunk; o2[sid] = buf + 3 * chunk;
+    o1[KB_OUT_PRED] = buf; o1[sid] = buf + bstride;
+    o2[KB_OUT_PRED] = buf + 2 * bstride; o2[sid] = buf + 3 * bstride;
     // the two objective models sweep the chunk concurrently on their own streams
     st = kb_predict_dev(m1, cur, xc, off, nullptr, o1, KB_OUT_PRED, nullptr);
     if (st == KB_OK) st = kb_predict_dev(m2, cur, xc, off, nullptr, o2, KB_OUT_PRED, nullptr);
@@ -1071,20 +1119,17 @@ static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const d
     e = cudaEventRecord(ev_p2, m2->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(m1->stream, ev_p2, 0);
     if (e == cudaSuccess)
-      e = kb_launch_ehvi2d(m1->stream, cur, buf, buf + chunk, buf + 2 * chunk, buf + 3 * chunk, table_dev, k, off,
-                           buf + 4 * chunk, (KbEhviBestHost*)red + 1, red, off > 0 ? 1 : 0, m1->num_sms);
+      e = kb_launch_ehvi2d(m1->stream, cur, buf, buf + bstride, buf + 2 * bstride, buf + 3 * bstride, table_dev, k, off,
+                           buf + 4 * bstride, (KbEhviBestHost*)red + 1, red, off > 0 ? 1 : 0, m1->num_sms);
     g_launches += 2;
     if (e == cudaSuccess && out)
-      e = cudaMemcpyAsync(out + off, buf + 4 * chunk, sizeof(double) * (size_t)cur, cudaMemcpyDeviceToHost, m1->stream);
+      e = cudaMemcpyAsync(out + off, buf + 4 * bstride, sizeof(double) * (size_t)cur, cudaMemcpyDeviceToHost, m1->stream);
   }
   KbEhviBestHost best{0.0, -1};
   if (e == cudaSuccess && st == KB_OK)
     e = cudaMemcpyAsync(&best, red, sizeof(best), cudaMemcpyDeviceToHost, m1->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m1->stream);
   cudaStreamSynchronize(m2->stream);
-  cudaFree(xd); cudaFree(buf); cudaFree(red); cudaFree(table_dev);
-  if (ev_x) cudaEventDestroy(ev_x);
-  if (ev_p2) cudaEventDestroy(ev_p2);
   if (st != KB_OK) return st;
   if (e != cudaSuccess) KB_FAIL(KB_ERR_CUDA, "ehvi2d: %s", cudaGetErrorString(e));
   if (best_idx) *best_idx = best.idx;
