@@ -81,10 +81,21 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms are meant to use the whole host, so the
+    BLAS pools are raised back to the core count (rank 0 is the only rank doing CPU work at that point)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     t_all = []
     sample_nll, sample_pred = 16, 4000          # ~2.5 s of host work per step
     for _ in range(args.warmup and 1):
@@ -285,6 +296,7 @@ def run_gpu(args):
             traffic = {}
         chol_flops = POP * (N_TRAIN ** 3) / 3.0
         pred_flops = float(SWEEP_PTS) * N_TRAIN * N_TRAIN           # n^2/2 FMA = n^2 flop per site
+        use_all_host_threads()
         cpu_v, cpu_p = cpu_sample(48, 16000)        # ~7 s of host work (48 of the 64 candidates, 16000 sites)
         cores = blas_threads()
         line = {
