@@ -63,16 +63,18 @@ kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
   double bb0 = 0.0;                                   // BE' b accumulates below (SMEM path)
 
   if (SMEM) {
-    // 3s. Cholesky on the packed triangle in 16-column panels.  A panel (all rows below its diagonal
-    //     block) is factored by ONE warp, column by column with warp barriers only; the trailing
-    //     triangle then takes the panel's 16 rank-1 updates in one pass by all warps (one row per warp,
-    //     the updates applied to each element in column order, so the result is bit-identical to the
-    //     column-by-column right-looking factorisation this replaces: 3 block barriers per COLUMN
-    //     became 2 per PANEL; GLS stage 0.90 -> 0.82 ms at n = 4000, nind = 231, B = 8).
+    // 3s. Cholesky on the packed triangle in 16-column panels: (a) ONE warp factors the 16 x 16 diagonal
+    //     block column by column (warp barriers only); (b) every row below solves its 16 panel entries
+    //     against that block independently, one row per thread; (c) the trailing triangle takes the
+    //     panel's 16 rank-1 updates in one pass, one row per warp.  Each element sees the same sequence of
+    //     fma updates and the same multiply by 1/pivot as in the column-by-column right-looking
+    //     factorisation this replaces (bit-identical), with 3 block barriers per PANEL instead of per COLUMN.
     const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     constexpr int PW = 16;
+    __shared__ double s_inv[PW];
     for (int j0 = 0; j0 < nind; j0 += PW) {
       const int pw = (nind - j0 < PW) ? (nind - j0) : PW;
+      const int t0 = j0 + pw;
       if (warp == 0) {
         for (int c = 0; c < pw; ++c) {
           const int j = j0 + c;
@@ -82,24 +84,41 @@ kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
             dj = 1.0;
           }
           const double piv = sqrt(dj), inv = 1.0 / piv;
+          if (lane == 0) s_inv[c] = inv;
           __syncwarp();
-          for (int r = j + lane; r < nind; r += 32) {
+          for (int r = j + lane; r < t0; r += 32) {
             double* row = Ms + (size_t)r * (r + 1) / 2;
             row[j] = (r == j) ? piv : row[j] * inv;
           }
           __syncwarp();
-          // the rest of the panel: columns j+1 .. j0+pw-1 of every row below
-          for (int r = j + 1 + lane; r < nind; r += 32) {
+          for (int r = j + 1 + lane; r < t0; r += 32) {
             double* row = Ms + (size_t)r * (r + 1) / 2;
             const double lr = row[j];
-            const int cend = (r < j0 + pw - 1) ? r : (j0 + pw - 1);
-            for (int c2 = j + 1; c2 <= cend; ++c2) row[c2] = fma(-lr, Ms[(size_t)c2 * (c2 + 1) / 2 + j], row[c2]);
+            for (int c2 = j + 1; c2 <= r; ++c2) row[c2] = fma(-lr, Ms[(size_t)c2 * (c2 + 1) / 2 + j], row[c2]);
           }
           __syncwarp();
         }
       }
       __syncthreads();
-      const int t0 = j0 + pw;
+      for (int r = t0 + tid; r < nind; r += blockDim.x) {
+        double* row = Ms + (size_t)r * (r + 1) / 2 + j0;
+        double v[PW];
+#pragma unroll
+        for (int c = 0; c < PW; ++c) {
+          if (c < pw) {
+            const double* dc = Ms + (size_t)(j0 + c) * (j0 + c + 1) / 2 + j0;     // row j0+c of the diagonal block
+            double a = row[c];
+#pragma unroll
+            for (int t = 0; t < PW; ++t)
+              if (t < c) a = fma(-v[t], dc[t], a);
+            v[c] = a * s_inv[c];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < PW; ++c)
+          if (c < pw) row[c] = v[c];
+      }
+      __syncthreads();
       for (int r = t0 + warp; r < nind; r += nw) {
         double* row = Ms + (size_t)r * (r + 1) / 2;
         double lr[PW];

@@ -94,6 +94,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 3 and sys.argv[1] == "pred":          # pred <n> <d> [log2 sites]
         predict_case(int(sys.argv[2]), int(sys.argv[3]), 1 << (int(sys.argv[4]) if len(sys.argv) > 4 else 19))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c3":
+        nll_case(4000, 20, 8, nind=231)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pred1000":
         predict_case(1000, 10, 1 << 20)
         sys.exit(0)
