@@ -116,6 +116,8 @@ struct kb_model {
     cudaEvent_t ev_x = nullptr, ev_p2 = nullptr;
     std::vector<double> key;       // front | ref of the table currently on the device
   } ehvi;
+  double* pin_small = nullptr;     // pinned staging for small predict calls: x | outputs | result
+  size_t pin_small_bytes = 0;
   double* few_scratch = nullptr;   // few-sites predictor (kb_launch_predict_few)
   int few_slices = 0;              // slices of 16 sites the scratch is sized for
   // host-API staging
@@ -375,6 +377,7 @@ void kb_model_destroy(kb_model* m) {
   cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
   cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
   cudaFree(m->result_dev); cudaFree(m->results_dev); cudaFree(m->few_scratch);
+  cudaFreeHost(m->pin_small);
   cudaFree(m->ehvi.xd); cudaFree(m->ehvi.buf); cudaFree(m->ehvi.table); cudaFree(m->ehvi.red);
   if (m->ehvi.ev_x) cudaEventDestroy(m->ehvi.ev_x);
   if (m->ehvi.ev_p2) cudaEventDestroy(m->ehvi.ev_p2);
@@ -802,8 +805,28 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
   }
   if (nchunks == 1) {
     // one chunk: nothing to overlap, so no second stream and no events (a local acquisition optimiser
-    // calls this path one design at a time -- every API call saved is latency)
-    CK(cudaMemcpyAsync(m->stage_x[0], x, sizeof(double) * (size_t)npts * m->d, cudaMemcpyHostToDevice, m->stream));
+    // calls this path one design at a time -- every API call saved is latency).  Small calls go through
+    // pinned staging so that the copies back do not each serialise on pageable memory.
+    const bool pinned = npts <= 2048;
+    double* hx = nullptr;
+    if (pinned) {
+      const size_t need = sizeof(double) * ((size_t)npts * m->d + (size_t)nout * npts) + sizeof(KbSweepResult);
+      if (need > m->pin_small_bytes) {
+        CK(cudaStreamSynchronize(m->stream));
+        cudaFreeHost(m->pin_small);
+        m->pin_small = nullptr; m->pin_small_bytes = 0;
+        size_t cap = 1 << 16;
+        while (cap < need) cap *= 2;
+        CK(cudaMallocHost(&m->pin_small, cap));
+        m->pin_small_bytes = cap;
+      }
+      hx = m->pin_small;
+      std::memcpy(hx, x, sizeof(double) * (size_t)npts * m->d);
+    }
+    double* hout = pinned ? hx + (size_t)npts * m->d : nullptr;
+    KbSweepResult* hres = pinned ? reinterpret_cast<KbSweepResult*>(hout + (size_t)nout * npts) : result;
+    CK(cudaMemcpyAsync(m->stage_x[0], pinned ? hx : x, sizeof(double) * (size_t)npts * m->d, cudaMemcpyHostToDevice,
+                       m->stream));
     double* od[KB_OUT_COUNT];
     for (int k = 0; k < KB_OUT_COUNT; ++k)
       od[k] = (slot[k] >= 0) ? m->stage_out[0] + (size_t)slot[k] * m->stage_pts : nullptr;
@@ -811,10 +834,16 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
     if (s1 != KB_OK) return s1;
     for (int k = 0; k < KB_OUT_COUNT; ++k)
       if (slot[k] >= 0)
-        CK(cudaMemcpyAsync(outs[k], od[k], sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(pinned ? hout + (size_t)slot[k] * npts : outs[k], od[k], sizeof(double) * (size_t)npts,
+                           cudaMemcpyDeviceToHost, m->stream));
     if (result)
-      CK(cudaMemcpyAsync(result, m->results_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
+      CK(cudaMemcpyAsync(hres, m->results_dev, sizeof(KbSweepResult), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
+    if (pinned) {
+      for (int k = 0; k < KB_OUT_COUNT; ++k)
+        if (slot[k] >= 0) std::memcpy(outs[k], hout + (size_t)slot[k] * npts, sizeof(double) * (size_t)npts);
+      if (result) *result = *hres;
+    }
     return KB_OK;
   }
   // the caller's stream may still be using the staging buffers of a previous call
