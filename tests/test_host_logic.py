@@ -156,3 +156,36 @@ def test_paregopre_and_moboinfocheck_defaults():
         moboinfocheck({"nup": 1, "acquifunc": "nsga"}, True)
     p = moboinfocheck({"nup": 1, "acquifunc": "parego"}, True)
     assert p["paregoacquifunc"] == "EI" and p["krignum"] == 1
+
+
+def test_philox_restatement_known_answers():
+    """oracle/philox.py against the known-answer vectors of the Random123 distribution (Salmon et al. 2011,
+    kat_vectors: philox4x32-10) -- the generator the device population / CMA-ES sampling is checked against."""
+    from oracle import philox
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+    z = philox.population(np.arange(20000), 2, dist="normal", seed=11)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02 and np.all(np.isfinite(z))
+
+
+def test_cmaes_restatement_minimises_known_functions():
+    """oracle/cmaes_oracle.py (the checker of the device CMA-ES loop) finds the minimum of a shifted
+    ellipsoid inside a box and respects the bounds when the minimum lies outside."""
+    from oracle import cmaes_oracle
+    c = np.array([0.3, -1.2, 2.0, 0.7])
+    w = np.array([1.0, 10.0, 100.0, 3.0])
+    f = lambda X: np.sum(w * (X - c) ** 2, axis=1)
+    r = cmaes_oracle.run(f, np.zeros(4), 1.5, lb=-5 * np.ones(4), ub=5 * np.ones(4), seed=2)
+    assert r["stop"] in (2, 3) and r["best_f"] < 1e-12 and np.max(np.abs(r["best_x"] - c)) < 1e-5
+    r = cmaes_oracle.run(f, np.zeros(4), 1.5, lb=-np.ones(4), ub=np.ones(4), seed=2)
+    assert np.all(np.abs(r["best_x"]) <= 1.0)
+    assert np.max(np.abs(r["best_x"] - np.clip(c, -1, 1))) < 1e-4
+    # a non-finite objective (what a non-positive-definite candidate returns) ranks last and is never the incumbent
+    g = lambda X: np.where(X[:, 0] > 0.5, np.inf, np.sum((X + 0.2) ** 2, axis=1))
+    r = cmaes_oracle.run(g, np.zeros(3), 1.0, seed=4, maxiter=200)
+    assert np.isfinite(r["best_f"]) and r["best_x"][0] <= 0.5 and r["best_f"] < 1e-8
