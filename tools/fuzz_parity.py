@@ -73,10 +73,12 @@ for case in range(ncases):
         status = "ok" if (e_nll < 1e-7 and e_pred < 2e-8 and e_ssqr < 1e-6 and bad_flags == 0) else "FAIL"
         if status == "ok" and e_nll >= 1e-9:
             status = "ok(ill-conditioned)"
-        fails += status != "ok"
+        fails += status == "FAIL"
+        illc = globals().get("illc", 0) + (status == "ok(ill-conditioned)")
+        globals()["illc"] = illc
         print(f"{status} {tag}: nll {e_nll:.1e} pred {e_pred:.1e} ssqr {e_ssqr:.1e} flags {bad_flags} notpd {int(np.sum(info != 0))}", flush=True)
     except Exception as ex:                      # noqa: BLE001
         fails += 1
         print(f"EXC {tag}: {type(ex).__name__}: {ex}", flush=True)
-print("worst:", worst, "failures:", fails)
+print("worst:", worst, "ill-conditioned (1e-9 <= nll err < 1e-7):", globals().get("illc", 0), "failures:", fails)
 sys.exit(1 if fails else 0)
