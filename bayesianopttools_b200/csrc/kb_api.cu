@@ -140,7 +140,7 @@ struct kb_model {
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
-static KbAugGeom make_geom(int n, int nind, bool fit_mode) {
+static KbAugGeom make_geom(int n, int nind, bool fit_mode, bool allow_seated) {
   KbAugGeom g{};
   g.n = n;
   g.n_pad = round_up(n, KB_TILE);
@@ -148,6 +148,10 @@ static KbAugGeom make_geom(int n, int nind, bool fit_mode) {
   g.nind = nind;
   g.q = 1 + nind;
   g.sb = round_up(g.q, KB_TILE) / KB_TILE;
+  static const char* seated_env = getenv("KB_CHOL_SEATED");         // debug aid: 0 disables
+  g.seated = (!fit_mode && allow_seated && g.q <= 16 && g.nb >= 3 && (n % KB_TILE) != 0 &&
+              (n % KB_TILE) + g.q <= KB_TILE && !(seated_env && atoi(seated_env) == 0)) ? 1 : 0;
+  if (g.seated) g.sb = 0;
   g.ib = fit_mode ? g.nb : 0;
   g.NT = g.nb + g.sb + g.ib;
   g.ld = (g.nb + g.sb) * KB_TILE;
@@ -187,7 +191,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   }
   CK(cudaStreamSynchronize(m->stream));
   free_ws(w);
-  w.g = make_geom(m->n, m->nind, fit_mode);
+  w.g = make_geom(m->n, m->nind, fit_mode, m->model_type != KB_TYPE_KPLS);
   const KbAugGeom& g = w.g;
   const int d = m->d, nind = m->nind;
   CK(cudaMalloc(&w.aug, sizeof(double) * g.stride * B));

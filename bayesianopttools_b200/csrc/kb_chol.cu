@@ -205,7 +205,64 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
     __syncthreads();
   }
   if (stamps && tid == 0) stamps[3] = kb_globaltimer();
+  // Seated right-hand sides (KbAugGeom::seated): in the LAST tile rows nv .. nv+q-1 are [y F]^T, already
+  // carried through every column (they are Z there) and updated by the product above.  Only the leading
+  // nv x nv block is factored; the rows below get the triangular solve and the q x q corner becomes the
+  // Schur block -Z Z^T the GLS kernel reads.  C1 (no longer needed) holds the saved rows and Z.
+  const bool seated_last = P.g.seated && k == P.g.nb - 1;
+  const int nv = P.g.n - k * KB_TILE;
+  double (*Yb)[KB_LDC] = C1;
+  if (seated_last) {
+    for (int e = tid; e < 16 * KB_TILE; e += KB_THREADS) {
+      const int j = e >> 6, c = e & 63, r = nv + j;
+      double v = 0.0;
+      if (r < KB_TILE) {
+        v = C2[r][c];
+        C2[r][c] = (r == c) ? 1.0 : 0.0;          // the factor routine sees identity padding, as always
+      }
+      Yb[j][c] = v;
+    }
+    for (int e = tid; e < nv * (KB_TILE - nv); e += KB_THREADS) C2[e / (KB_TILE - nv)][nv + e % (KB_TILE - nv)] = 0.0;
+    __syncthreads();
+  }
   kb_diag_factor_inverse(C2, Dk, xch, &P.info[b], k * KB_TILE);
+  if (seated_last) {
+    __syncthreads();
+    {
+      // Z[j][i] = sum_{t <= i} Y[j][t] Linv[i][t]  (i < nv): four interleaved dot products per thread
+      const int j = tid >> 4, i0 = tid & 15;
+      double z[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int t = 0; t < nv; ++t) {
+        const double yt = Yb[j][t];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 16 * u;
+          if (t <= i && i < nv) z[u] = fma(yt, Dk[i][t], z[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Yb[16 + j][i0 + 16 * u] = z[u];
+    }
+    __syncthreads();
+    {
+      const int a = tid >> 4, c = tid & 15;
+      if (c <= a && nv + a < KB_TILE) {
+        double s0 = 0.0, s1 = 0.0;
+        int i = 0;
+        for (; i + 1 < nv; i += 2) {
+          s0 = fma(Yb[16 + a][i], Yb[16 + c][i], s0);
+          s1 = fma(Yb[16 + a][i + 1], Yb[16 + c][i + 1], s1);
+        }
+        if (i < nv) s0 = fma(Yb[16 + a][i], Yb[16 + c][i], s0);
+        C2[nv + a][nv + c] = Yb[a][nv + c] - (s0 + s1);
+      }
+    }
+    for (int e = tid; e < 16 * nv; e += KB_THREADS) {
+      const int j = e / nv, i = e - j * nv;
+      if (nv + j < KB_TILE) C2[nv + j][i] = Yb[16 + j][i];
+    }
+    __syncthreads();
+  }
   if (stamps && tid == 0) stamps[6] = kb_globaltimer();
   double* Dg = P.dinv + ((size_t)b * P.g.nb + k) * (KB_TILE * KB_TILE);
   for (int e = tid; e < KB_TILE * KB_TILE / 2; e += KB_THREADS) {

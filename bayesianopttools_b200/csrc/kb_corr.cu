@@ -205,6 +205,11 @@ kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ 
           const int c = col + e;
           double val;
           if (row < m.n && c < m.n) val = out[a][a2][e] + ((row == c) ? eps : 0.0);
+          else if (g.seated && row >= m.n && row < m.n + g.q) {
+            // seated right-hand sides: row n is y, rows n+1.. the trend columns; zero Schur corner
+            const int qr = row - m.n;
+            val = (c < m.n) ? (qr == 0 ? m.y[c] : m.F[(size_t)c * m.nind + (qr - 1)]) : 0.0;
+          }
           else val = (row == c) ? 1.0 : 0.0;       // identity padding
           pv[e] = val;
         }

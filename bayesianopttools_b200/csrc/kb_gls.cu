@@ -32,7 +32,7 @@ kb_gls_kernel(KbAugGeom g, const double* __restrict__ aug, int trainvar,
   const int b = blockIdx.x, tid = threadIdx.x;
   const double* A = aug + (size_t)b * g.stride;
   const int n = g.n, nind = g.nind, ld = g.ld;
-  const size_t rhs0 = (size_t)g.nb * KB_TILE;
+  const size_t rhs0 = g.seated ? (size_t)g.n : (size_t)g.nb * KB_TILE;   // first right-hand-side row = column
   double* Mb = Mbuf + (size_t)b * nind * nind;
   double* be = beta + (size_t)b * nind;
   double* Ms = gsm;                                   // packed lower triangle (SMEM only)

@@ -29,6 +29,9 @@ struct KbAugGeom {
   int NT;             // nb + sb + ib
   int ld;             // (nb + sb) * 64 doubles per row
   size_t stride;      // doubles per matrix = NT*64*ld
+  int seated;         // population mode, q <= 16, (n mod 64) + q <= 64: the right-hand sides [y F]^T sit in the
+                      // padding rows n .. n+q-1 of the last tile row of R (sb = 0, no right-hand-side or Schur
+                      // tasks: the regular tile tasks produce Z and the last chain step the Schur corner)
 };
 
 // Per-candidate decoded hyper-parameters (device arrays, B rows each).
