@@ -191,7 +191,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   }
   CK(cudaStreamSynchronize(m->stream));
   free_ws(w);
-  w.g = make_geom(m->n, m->nind, fit_mode, m->model_type != KB_TYPE_KPLS);
+  w.g = make_geom(m->n, m->nind, fit_mode, true);
   const KbAugGeom& g = w.g;
   const int d = m->d, nind = m->nind;
   CK(cudaMalloc(&w.aug, sizeof(double) * g.stride * B));

@@ -285,6 +285,7 @@ static cudaError_t kb_build_aug_launch(cudaStream_t st, const KbModelDev& m, con
   const int nR = g.nb * (g.nb + 1) / 2;
   const int ntiles = nR + (g.sb + g.ib) * (g.nb + g.sb);
   const int t_begin = skip_r_tiles ? nR : 0;
+  if (ntiles - t_begin <= 0) return cudaSuccess;     // seated right-hand sides: nothing left to build
   dim3 grid(ntiles - t_begin, B);
   kb_build_aug_kernel<MASK><<<grid, KB_THREADS, smem, st>>>(m, g, hp, aug, t_begin);
   return cudaGetLastError();
@@ -410,8 +411,17 @@ kb_build_aug_kpls_kernel(KbModelDev m, KbAugGeom g, int B, int h, KbHyper hp, co
         if (row == col) v.x += seps[bb];
         if (row == col + 1) v.y += seps[bb];
         if (!inside) {
-          if (row >= m.n || col >= m.n) v.x = (row == col) ? 1.0 : 0.0;
-          if (row >= m.n || col + 1 >= m.n) v.y = (row == col + 1) ? 1.0 : 0.0;
+          // padding: identity, except the seated right-hand-side rows n .. n+q-1 (y, trend columns; zero corner)
+          const bool rhs_row = g.seated && row >= m.n && row < m.n + g.q;
+          const int qr = row - m.n;
+          if (row >= m.n || col >= m.n) {
+            if (rhs_row) v.x = (col < m.n) ? (qr == 0 ? m.y[col] : m.F[(size_t)col * m.nind + (qr - 1)]) : 0.0;
+            else v.x = (row == col) ? 1.0 : 0.0;
+          }
+          if (row >= m.n || col + 1 >= m.n) {
+            if (rhs_row) v.y = (col + 1 < m.n) ? (qr == 0 ? m.y[col + 1] : m.F[(size_t)(col + 1) * m.nind + (qr - 1)]) : 0.0;
+            else v.y = (row == col + 1) ? 1.0 : 0.0;
+          }
         }
         *reinterpret_cast<double2*>(&aug[(size_t)(b0 + bb) * g.stride + (size_t)row * g.ld + col]) = v;
       }

@@ -455,3 +455,41 @@ def test_few_sites_predictor_matches_strip_kernel_and_oracle(lib, n, d, order, k
     b, _ = mdl.predict(xq[:3], ("ei",), **acq)
     assert np.array_equal(a["ei"], b["ei"])
     mdl.close()
+
+
+@pytest.mark.parametrize("n,nind,kernel", [(193, 1, "gaussian"), (254, 1, "matern52"), (240, 15, "gaussian"),
+                                           (241, 15, "gaussian"), (305, 7, "exponential"), (448, 1, "gaussian")])
+def test_seated_right_hand_sides_at_their_limits(lib, n, nind, kernel):
+    """The right-hand sides [y F]^T ride in the padding rows of the last tile row when (n mod 64) + q <= 64 and
+    q <= 16 (kb_chol.cu, KbAugGeom::seated): one row of padding used (n = 193), the last two (254), all
+    sixteen exactly filling the tile (240, q = 16), one too many (241: classic layout), a mid case with a
+    trend (305) and no padding at all (448: classic layout).  NLL, beta, sigma^2 against the oracle, for a
+    population larger than the chain-worker count on one of them."""
+    rng = np.random.default_rng(n + nind)
+    d = 3
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sum(np.sin(2 * X) + 0.3 * X ** 2, axis=1) + 0.02 * rng.standard_normal(n)
+    F = np.hstack([np.ones((n, 1)), rng.normal(size=(n, nind - 1))]) if nind > 1 else np.ones((n, 1))
+    B = 70 if n == 254 else 5
+    xpop = rng.uniform(-0.5, 0.6, (B, d))
+    mdl = lib.DeviceModel(X, y, F, [kernel])
+    nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
+    assert np.all(info == 0)
+    beta, s2 = mdl.nll_extras(B)
+    for b in range(0, B, max(1, B // 5)):
+        ref = ko.nll(xpop[b], X, y, F, kernels=(kernel,), full=True)
+        assert abs(nll[b] - ref["NegLnLike"]) <= TOL * max(1.0, abs(ref["NegLnLike"])), (b, nll[b], ref["NegLnLike"])
+        assert relerr(beta[b], ref["BE"]) < 1e-7 and abs(s2[b] - ref["SigmaSqr"]) / ref["SigmaSqr"] < 1e-8
+    # a duplicated LAST site with a vanishing nugget: the pivot test of the seated last tile
+    Xd = X.copy()
+    Xd[n - 1] = Xd[n - 2]
+    bad = lib.DeviceModel(Xd, y, F, [kernel])
+    xbad = np.array([[0.0] * d + [-30.0], [0.0] * d + [-6.0]])
+    f, i = bad.nll_batch(xbad, False, -6.0, return_info=True)
+    rf, ri = ko.nll_batch(xbad, Xd, y, F, kernels=(kernel,))
+    assert i[1] == 0 and ri[1] == 0 and abs(f[1] - rf[1]) <= 1e-7 * abs(rf[1])
+    # exact duplicates: the last pivot is zero up to rounding, so either path may or may not call it positive;
+    # what matters is that a flagged candidate is +inf, an unflagged one finite, and its neighbour untouched
+    assert (i[0] != 0 and np.isinf(f[0])) or (i[0] == 0 and np.isfinite(f[0]))
+    bad.close()
+    mdl.close()
