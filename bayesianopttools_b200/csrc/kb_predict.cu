@@ -705,23 +705,28 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   }
 }
 
-// Deterministic final reduction over the per-CTA partials (lowest index on ties).
+// Deterministic final reduction over the per-CTA partials (lowest index on ties; the counters are integers):
+// one warp, lanes stride over the partials, then a shuffle tree.
 __global__ void kb_sweep_final_kernel(const KbSweepResult* __restrict__ partials, int nparts,
                                       long long npoints, KbSweepResult* __restrict__ result) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  KbSweepResult r = partials[0];
-  for (int i = 1; i < nparts; ++i) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  KbRunning run;
+  kb_run_init(run);
+  for (int i = threadIdx.x; i < nparts; i += 32) {
     const KbSweepResult q = partials[i];
-    if (q.best_val < r.best_val || (q.best_val == r.best_val && q.best_idx < r.best_idx)) {
-      r.best_val = q.best_val; r.best_idx = q.best_idx;
+    if (q.best_val < run.best_val || (q.best_val == run.best_val && q.best_idx < run.best_idx)) {
+      run.best_val = q.best_val; run.best_idx = q.best_idx;
     }
-    if (q.min_u < r.min_u || (q.min_u == r.min_u && q.min_u_idx < r.min_u_idx)) {
-      r.min_u = q.min_u; r.min_u_idx = q.min_u_idx;
+    if (q.min_u < run.min_u || (q.min_u == run.min_u && q.min_u_idx < run.min_u_idx)) {
+      run.min_u = q.min_u; run.min_u_idx = q.min_u_idx;
     }
-    r.n_fail += q.n_fail; r.n_fail_minus += q.n_fail_minus; r.n_fail_plus += q.n_fail_plus;
+    run.c0 += q.n_fail; run.c1 += q.n_fail_minus; run.c2 += q.n_fail_plus;
   }
-  r.n_points = npoints;
-  *result = r;
+  KbSweepResult r = kb_run_warp_reduce(run);
+  if (threadIdx.x == 0) {
+    r.n_points = npoints;
+    *result = r;
+  }
 }
 
 template <int MASK, bool RESIDENT>
