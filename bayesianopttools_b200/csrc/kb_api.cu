@@ -47,7 +47,45 @@ struct KbPopWs {       // one augmented-matrix workspace (population or fit geom
   double *Mbuf = nullptr, *beta = nullptr, *sigma2 = nullptr, *nll = nullptr, *lndet = nullptr;
   double* xpop = nullptr;
   int xpop_cap = 0;
+  void* slab = nullptr;   // ONE device allocation behind every pointer above except xpop (cudaMalloc / cudaFree cost
+                          // 0.25-0.3 ms each, and the callers re-create the model at every design update)
 };
+
+// Pinned host memory comes from a process-wide pool of power-of-two blocks that are never returned to the
+// driver: cudaMallocHost / cudaFreeHost cost 0.3-0.8 ms / 0.13 ms each (tools/ubench/host_costs.cu), and
+// SOBO / AK-MCS / MOBO re-create the model handle at every design update.
+#include <mutex>
+namespace {
+struct KbPinnedPool {
+  std::mutex mu;
+  std::vector<void*> free_blocks[40];
+  static int cls(size_t bytes) {
+    int c = 12;                                   // smallest block 4 KB
+    while (((size_t)1 << c) < bytes) ++c;
+    return c;
+  }
+  void* get(size_t bytes) {
+    const int c = cls(bytes);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!free_blocks[c].empty()) {
+        void* p = free_blocks[c].back();
+        free_blocks[c].pop_back();
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)1 << c) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+  }
+  void put(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    free_blocks[cls(bytes)].push_back(p);
+  }
+};
+KbPinnedPool g_pinned;
+}  // namespace
 
 // Replayable capture of one host-buffer likelihood call (copy in -> decode -> build -> factor -> GLS ->
 // copy out) for a fixed (B, nbhyp, trainvar, nugget): at KrigDemo / AK-MCS sizes the call is launch-bound
@@ -57,9 +95,10 @@ struct KbNllGraph {
   cudaGraphExec_t exec = nullptr;
   int B = 0, nbhyp = 0, trainvar = 0;
   double nugget = 0.0;
-  double* h_x = nullptr;      // pinned staging
+  double* h_x = nullptr;      // pinned staging: one pooled block  x | nll | info
   double* h_nll = nullptr;
   int* h_info = nullptr;
+  size_t h_bytes = 0;
   unsigned long long stamp = 0;   // last use (LRU)
 };
 // A few shapes alternate in practice (a GA's population / offspring / mutants, an optimiser's value and
@@ -69,8 +108,10 @@ struct KbNllGraphCache {
   KbNllGraph g[4];
   unsigned long long clock = 0;
   int disabled = 0;               // capture failed once: plain launches from then on
-  int miss_B = 0, miss_nbhyp = 0, miss_trainvar = 0;
-  double miss_nugget = 0.0;
+  // shapes requested without a graph, and how often (an optimiser alternates a few shapes: value and
+  // gradient calls, a GA's population / offspring / mutants): a shape is captured on its third request
+  struct Seen { int B = 0, nbhyp = 0, trainvar = 0, count = 0; double nugget = 0.0; unsigned long long stamp = 0; } seen[4];
+  int miss_B = 0;                 // (non-zero once anything has been seen; cleared with the cache)
   const void* ws_aug = nullptr;   // workspace buffers the cached graphs point into
   const void* ws_xpop = nullptr;
 };
@@ -161,25 +202,32 @@ static KbAugGeom make_geom(int n, int nind, bool fit_mode, bool allow_seated) {
 
 static void drop_nll_graph(KbNllGraph& g) {
   if (g.exec) cudaGraphExecDestroy(g.exec);
-  cudaFreeHost(g.h_x); cudaFreeHost(g.h_nll); cudaFreeHost(g.h_info);
+  g_pinned.put(g.h_x, g.h_bytes);
   g = KbNllGraph{};
 }
 static void drop_nll_graphs(KbNllGraphCache& c) {
   for (KbNllGraph& g : c.g) drop_nll_graph(g);
+  for (auto& sn : c.seen) sn = KbNllGraphCache::Seen{};
   c.miss_B = 0;
 }
 
 static void free_ws(KbPopWs& w) {
-  cudaFree(w.aug); cudaFree(w.dinv); cudaFree(w.sync_words); cudaFree(w.tasks);
-  cudaFree(w.info); cudaFree(w.hp.gw); cudaFree(w.hp.ith); cudaFree(w.hp.wk); cudaFree(w.hp.eps);
-  cudaFree(w.hp.sigma2); cudaFree(w.hp.nugget); cudaFree(w.hp.gk); cudaFree(w.Mbuf); cudaFree(w.beta); cudaFree(w.sigma2);
-  cudaFree(w.nll); cudaFree(w.lndet); cudaFree(w.xpop);
+  cudaFree(w.slab); cudaFree(w.xpop);
   w = KbPopWs{};
+}
+
+// One-tile designs (n <= 64) take the single-launch kernel of kb_small.cu and never run the task queue.
+static bool use_small_kernel(const kb_model* m, const KbPopWs& w) {
+  static const char* small_env = getenv("KB_SMALL_NLL");            // debug aid: 0 disables
+  return (&w == &m->pop) && kb_small_applies(w.g, m->d, m->model_type == KB_TYPE_KPLS) &&
+         !(small_env && atoi(small_env) == 0);
 }
 
 static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   if (B <= w.B_cap) {
-    if (w.tasks_B != B) {
+    // (one-tile designs never run the task queue: kb_small.cu)
+    const bool queue_unused = use_small_kernel(m, w);
+    if (w.tasks_B != B && !queue_unused) {
       std::vector<int4> tasks;
       kb_chol_build_tasks(w.g, B, 2 * m->num_sms, tasks);
       CK(cudaMemcpyAsync(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, m->stream));
@@ -194,28 +242,50 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   w.g = make_geom(m->n, m->nind, fit_mode, true);
   const KbAugGeom& g = w.g;
   const int d = m->d, nind = m->nind;
-  CK(cudaMalloc(&w.aug, sizeof(double) * g.stride * B));
-  CK(cudaMalloc(&w.dinv, sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE));
-  CK(cudaMalloc(&w.sync_words, sizeof(int) * kb_chol_sync_words(g, B)));
   std::vector<int4> tasks;
   kb_chol_build_tasks(g, B, 2 * m->num_sms, tasks);
-  CK(cudaMalloc(&w.tasks, tasks.size() * sizeof(int4)));
+  // one slab, 256-byte aligned pieces
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_aug = carve(sizeof(double) * g.stride * B);
+  const size_t o_dinv = carve(sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE);
+  const size_t o_sync = carve(sizeof(int) * kb_chol_sync_words(g, B));
+  const size_t o_tasks = carve(tasks.size() * sizeof(int4));
+  const size_t o_info = carve(sizeof(int) * B);
+  const size_t o_gw = carve(sizeof(double) * (size_t)B * d);
+  const size_t o_ith = carve(sizeof(double) * (size_t)B * d);
+  const size_t o_wk = carve(sizeof(double) * B * 4);
+  const size_t o_eps = carve(sizeof(double) * B);
+  const size_t o_s2h = carve(sizeof(double) * B);
+  const size_t o_nug = carve(sizeof(double) * B);
+  const size_t o_gk = carve(sizeof(double) * B * KB_KPLS_MAX_H);
+  const size_t o_M = carve(sizeof(double) * (size_t)B * nind * nind);
+  const size_t o_beta = carve(sizeof(double) * (size_t)B * nind);
+  const size_t o_s2 = carve(sizeof(double) * B);
+  const size_t o_nll = carve(sizeof(double) * B);
+  const size_t o_lndet = carve(sizeof(double) * B);
+  CK(cudaMalloc(&w.slab, off));
+  char* base = static_cast<char*>(w.slab);
+  w.aug = reinterpret_cast<double*>(base + o_aug);
+  w.dinv = reinterpret_cast<double*>(base + o_dinv);
+  w.sync_words = reinterpret_cast<int*>(base + o_sync);
+  w.tasks = reinterpret_cast<int4*>(base + o_tasks);
+  w.info = reinterpret_cast<int*>(base + o_info);
+  w.hp.gw = reinterpret_cast<double*>(base + o_gw);
+  w.hp.ith = reinterpret_cast<double*>(base + o_ith);
+  w.hp.wk = reinterpret_cast<double*>(base + o_wk);
+  w.hp.eps = reinterpret_cast<double*>(base + o_eps);
+  w.hp.sigma2 = reinterpret_cast<double*>(base + o_s2h);
+  w.hp.nugget = reinterpret_cast<double*>(base + o_nug);
+  w.hp.gk = reinterpret_cast<double*>(base + o_gk);
+  w.Mbuf = reinterpret_cast<double*>(base + o_M);
+  w.beta = reinterpret_cast<double*>(base + o_beta);
+  w.sigma2 = reinterpret_cast<double*>(base + o_s2);
+  w.nll = reinterpret_cast<double*>(base + o_nll);
+  w.lndet = reinterpret_cast<double*>(base + o_lndet);
   CK(cudaMemcpy(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
   w.ntasks = (int)tasks.size();
   w.tasks_B = B;
-  CK(cudaMalloc(&w.info, sizeof(int) * B));
-  CK(cudaMalloc(&w.hp.gw, sizeof(double) * (size_t)B * d));
-  CK(cudaMalloc(&w.hp.ith, sizeof(double) * (size_t)B * d));
-  CK(cudaMalloc(&w.hp.wk, sizeof(double) * B * 4));
-  CK(cudaMalloc(&w.hp.eps, sizeof(double) * B));
-  CK(cudaMalloc(&w.hp.sigma2, sizeof(double) * B));
-  CK(cudaMalloc(&w.hp.nugget, sizeof(double) * B));
-  CK(cudaMalloc(&w.hp.gk, sizeof(double) * B * KB_KPLS_MAX_H));
-  CK(cudaMalloc(&w.Mbuf, sizeof(double) * (size_t)B * nind * nind));
-  CK(cudaMalloc(&w.beta, sizeof(double) * (size_t)B * nind));
-  CK(cudaMalloc(&w.sigma2, sizeof(double) * B));
-  CK(cudaMalloc(&w.nll, sizeof(double) * B));
-  CK(cudaMalloc(&w.lndet, sizeof(double) * B));
   w.B_cap = B;
   return KB_OK;
 }
@@ -246,9 +316,7 @@ static kb_status run_pipeline(kb_model* m, KbPopWs& w, int B, int nbhyp, const d
   KbModelDev md{m->n, m->d, m->nind, m->n_pad, m->nb, m->kmask, m->XT, m->y, m->F};
   const bool prof = m->profile && (&w == &m->pop);
   // One-tile designs (n <= 64): a single launch decodes, builds, factors and solves (kb_small.cu)
-  static const char* small_env = getenv("KB_SMALL_NLL");            // debug aid: 0 disables
-  const bool small = (&w == &m->pop) && kb_small_applies(w.g, m->d, m->model_type == KB_TYPE_KPLS) &&
-                     !(small_env && atoi(small_env) == 0);
+  const bool small = use_small_kernel(m, w);
   if (small) {
     if (prof) {
       CK(cudaEventRecord(m->ev[m->pop_calls % KB_PROF_RING][0], m->stream));
@@ -381,7 +449,7 @@ void kb_model_destroy(kb_model* m) {
   cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
   cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
   cudaFree(m->result_dev); cudaFree(m->results_dev); cudaFree(m->few_scratch);
-  cudaFreeHost(m->pin_small);
+  g_pinned.put(m->pin_small, m->pin_small_bytes);
   cudaFree(m->ehvi.xd); cudaFree(m->ehvi.buf); cudaFree(m->ehvi.table); cudaFree(m->ehvi.red);
   if (m->ehvi.ev_x) cudaEventDestroy(m->ehvi.ev_x);
   if (m->ehvi.ev_p2) cudaEventDestroy(m->ehvi.ev_p2);
@@ -499,19 +567,35 @@ kb_status kb_nll_batch(kb_model* m, int B, int nbhyp, const double* xpop, int tr
     for (KbNllGraph& g : GC.g)
       if (matches(g)) G = &g;
     if (!G) {
-      const bool again = GC.miss_B == B && GC.miss_nbhyp == nbhyp && GC.miss_trainvar == trainvar &&
-                         GC.miss_nugget == fixed_nugget_log10;
-      GC.miss_B = B; GC.miss_nbhyp = nbhyp; GC.miss_trainvar = trainvar; GC.miss_nugget = fixed_nugget_log10;
+      KbNllGraphCache::Seen* sn = nullptr;
+      for (auto& e : GC.seen)
+        if (e.count > 0 && e.B == B && e.nbhyp == nbhyp && e.trainvar == trainvar && e.nugget == fixed_nugget_log10) sn = &e;
+      if (!sn) {
+        sn = &GC.seen[0];
+        for (auto& e : GC.seen)
+          if (e.stamp < sn->stamp) sn = &e;
+        *sn = KbNllGraphCache::Seen{};
+        sn->B = B; sn->nbhyp = nbhyp; sn->trainvar = trainvar; sn->nugget = fixed_nugget_log10;
+      }
+      sn->count += 1;
+      sn->stamp = ++GC.clock;
+      GC.miss_B = B;
+      const bool again = sn->count >= 3;
       if (again) {
+        sn->count = 0;
         KbNllGraph* slot = &GC.g[0];
         for (KbNllGraph& g : GC.g)
           if (g.stamp < slot->stamp) slot = &g;                 // empty slots have stamp 0
         drop_nll_graph(*slot);
         CK(cudaStreamSynchronize(m->stream));
         cudaGraph_t graph = nullptr;
-        bool ok = cudaMallocHost(&slot->h_x, sizeof(double) * B * nbhyp) == cudaSuccess &&
-                  cudaMallocHost(&slot->h_nll, sizeof(double) * B) == cudaSuccess &&
-                  cudaMallocHost(&slot->h_info, sizeof(int) * B) == cudaSuccess;
+        slot->h_bytes = sizeof(double) * ((size_t)B * nbhyp + B) + sizeof(int) * (size_t)B;
+        slot->h_x = static_cast<double*>(g_pinned.get(slot->h_bytes));
+        bool ok = slot->h_x != nullptr;
+        if (ok) {
+          slot->h_nll = slot->h_x + (size_t)B * nbhyp;
+          slot->h_info = reinterpret_cast<int*>(slot->h_nll + B);
+        }
         if (ok) ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
           ok = cudaMemcpyAsync(m->pop.xpop, slot->h_x, sizeof(double) * B * nbhyp, cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
@@ -817,11 +901,12 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
       const size_t need = sizeof(double) * ((size_t)npts * m->d + (size_t)nout * npts) + sizeof(KbSweepResult);
       if (need > m->pin_small_bytes) {
         CK(cudaStreamSynchronize(m->stream));
-        cudaFreeHost(m->pin_small);
+        g_pinned.put(m->pin_small, m->pin_small_bytes);
         m->pin_small = nullptr; m->pin_small_bytes = 0;
         size_t cap = 1 << 16;
         while (cap < need) cap *= 2;
-        CK(cudaMallocHost(&m->pin_small, cap));
+        m->pin_small = static_cast<double*>(g_pinned.get(cap));
+        if (!m->pin_small) KB_FAIL(KB_ERR_CUDA, "cannot allocate %zu bytes of pinned staging", cap);
         m->pin_small_bytes = cap;
       }
       hx = m->pin_small;
