@@ -55,6 +55,7 @@ struct KbPopWs {       // one augmented-matrix workspace (population or fit geom
 // driver: cudaMallocHost / cudaFreeHost cost 0.3-0.8 ms / 0.13 ms each (tools/ubench/host_costs.cu), and
 // SOBO / AK-MCS / MOBO re-create the model handle at every design update.
 #include <mutex>
+#include <unordered_map>
 namespace {
 struct KbPinnedPool {
   std::mutex mu;
@@ -85,7 +86,81 @@ struct KbPinnedPool {
   }
 };
 KbPinnedPool g_pinned;
+
+// Device memory likewise: blocks up to 32 MB are recycled through per-device power-of-two free lists
+// (cudaMalloc / cudaFree cost 0.25-0.3 ms each and cudaFree synchronises the device; a model handle makes about
+// forty allocations in its life and SOBO / AK-MCS / MOBO create one per design update).  Larger blocks -- the
+// augmented-matrix slab of a big population -- go straight to the driver.  A recycled block is only handed out
+// again after a device synchronisation at release time, which is what cudaFree would have done.
+struct KbDevicePool {
+  static constexpr size_t kMaxPooled = (size_t)32 << 20;
+  static constexpr size_t kMaxCached = (size_t)1 << 30;     // per process
+  std::mutex mu;
+  std::unordered_map<void*, std::pair<int, int>> live;       // pointer -> (device, size class), pooled blocks only
+  std::unordered_map<long long, std::vector<void*>> free_blocks;   // (device << 8 | class) -> blocks
+  size_t cached = 0;
+  static int cls(size_t bytes) {
+    int c = 9;                                    // smallest block 512 B
+    while (((size_t)1 << c) < bytes) ++c;
+    return c;
+  }
+  cudaError_t get(void** out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (bytes > kMaxPooled) return cudaMalloc(out, bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int c = cls(bytes);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto& fl = free_blocks[((long long)dev << 8) | c];
+      if (!fl.empty()) {
+        *out = fl.back();
+        fl.pop_back();
+        cached -= (size_t)1 << c;
+        live[*out] = {dev, c};
+        return cudaSuccess;
+      }
+    }
+    const cudaError_t e = cudaMalloc(out, (size_t)1 << c);
+    if (e == cudaSuccess) {
+      std::lock_guard<std::mutex> lk(mu);
+      live[*out] = {dev, c};
+    }
+    return e;
+  }
+  void put(void* p) {
+    if (!p) return;
+    std::pair<int, int> dc;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      auto it = live.find(p);
+      if (it == live.end()) {                     // a large block: straight back to the driver
+        lk.unlock();
+        cudaFree(p);
+        return;
+      }
+      dc = it->second;
+      live.erase(it);
+    }
+    cudaDeviceSynchronize();                      // nothing in flight may still use the block
+    bool keep;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      keep = cached + ((size_t)1 << dc.second) <= kMaxCached;
+      if (keep) {
+        free_blocks[((long long)dc.first << 8) | dc.second].push_back(p);
+        cached += (size_t)1 << dc.second;
+      }
+    }
+    if (!keep) cudaFree(p);
+  }
+};
+KbDevicePool g_devpool;
 }  // namespace
+template <typename T>
+static inline cudaError_t kb_dev_malloc(T** out, size_t bytes) { return g_devpool.get(reinterpret_cast<void**>(out), bytes); }
+static inline void kb_dev_free(void* p) { g_devpool.put(p); }
 
 // Replayable capture of one host-buffer likelihood call (copy in -> decode -> build -> factor -> GLS ->
 // copy out) for a fixed (B, nbhyp, trainvar, nugget): at KrigDemo / AK-MCS sizes the call is launch-bound
@@ -212,7 +287,7 @@ static void drop_nll_graphs(KbNllGraphCache& c) {
 }
 
 static void free_ws(KbPopWs& w) {
-  cudaFree(w.slab); cudaFree(w.xpop);
+  kb_dev_free(w.slab); kb_dev_free(w.xpop);
   w = KbPopWs{};
 }
 
@@ -264,7 +339,7 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   const size_t o_s2 = carve(sizeof(double) * B);
   const size_t o_nll = carve(sizeof(double) * B);
   const size_t o_lndet = carve(sizeof(double) * B);
-  CK(cudaMalloc(&w.slab, off));
+  CK(kb_dev_malloc(&w.slab, off));
   char* base = static_cast<char*>(w.slab);
   w.aug = reinterpret_cast<double*>(base + o_aug);
   w.dinv = reinterpret_cast<double*>(base + o_dinv);
@@ -292,9 +367,9 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
 
 static kb_status ensure_xpop(KbPopWs& w, int count) {
   if (count <= w.xpop_cap) return KB_OK;
-  cudaFree(w.xpop);
+  kb_dev_free(w.xpop);
   w.xpop = nullptr;
-  CK(cudaMalloc(&w.xpop, sizeof(double) * count));
+  CK(kb_dev_malloc(&w.xpop, sizeof(double) * count));
   w.xpop_cap = count;
   return KB_OK;
 }
@@ -384,14 +459,17 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
   if (ndev == 0) KB_FAIL(KB_ERR_CUDA, "no CUDA device visible: the krig-b200 path has no CPU fallback");
   if (device < 0 || device >= ndev) KB_FAIL(KB_ERR_INVALID, "device %d out of range (%d)", device, ndev);
   CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    KB_FAIL(KB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
-            prop.minor);
+  // (three attribute queries instead of cudaGetDeviceProperties: that call alone costs 1-2 ms, and the callers
+  //  create a handle per design update)
+  int cc_major = 0, cc_minor = 0, sm_count = 0;
+  CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  CK(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major != 10)
+    KB_FAIL(KB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, cc_major, cc_minor);
   kb_model* m = new kb_model();
   m->device = device;
-  m->num_sms = prop.multiProcessorCount;
+  m->num_sms = sm_count;
   m->n = n; m->d = d; m->nind = nind; m->nkernel = nkernel; m->model_type = model_type; m->h = h;
   m->n_pad = round_up(n, KB_TILE);
   m->nb = m->n_pad / KB_TILE;
@@ -407,33 +485,33 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
   CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
   double* Xtmp = nullptr;
-  CK(cudaMalloc(&Xtmp, sizeof(double) * (size_t)n * d));
+  CK(kb_dev_malloc(&Xtmp, sizeof(double) * (size_t)n * d));
   CK(cudaMemcpy(Xtmp, Xnorm, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&m->XT, sizeof(double) * (size_t)d * m->n_pad));
+  CK(kb_dev_malloc(&m->XT, sizeof(double) * (size_t)d * m->n_pad));
   CK(kb_launch_transpose_pad(m->stream, Xtmp, n, d, m->XT, m->n_pad));
   g_launches += 1;
   CK(cudaStreamSynchronize(m->stream));
-  cudaFree(Xtmp);
-  CK(cudaMalloc(&m->y, sizeof(double) * n));
+  kb_dev_free(Xtmp);
+  CK(kb_dev_malloc(&m->y, sizeof(double) * n));
   CK(cudaMemcpy(m->y, y, sizeof(double) * n, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&m->F, sizeof(double) * (size_t)n * nind));
+  CK(kb_dev_malloc(&m->F, sizeof(double) * (size_t)n * nind));
   CK(cudaMemcpy(m->F, F, sizeof(double) * (size_t)n * nind, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&m->kernel_ids_dev, sizeof(int) * nkernel));
+  CK(kb_dev_malloc(&m->kernel_ids_dev, sizeof(int) * nkernel));
   CK(cudaMemcpy(m->kernel_ids_dev, kernel_ids, sizeof(int) * nkernel, cudaMemcpyHostToDevice));
   if (model_type == KB_TYPE_KPLS) {
-    CK(cudaMalloc(&m->pls, sizeof(double) * (size_t)d * h));
+    CK(kb_dev_malloc(&m->pls, sizeof(double) * (size_t)d * h));
     CK(cudaMemcpy(m->pls, plscoeff, sizeof(double) * (size_t)d * h, cudaMemcpyHostToDevice));
   }
   if (model_type == KB_TYPE_KPLS && h <= KB_KPLS_MAX_H) {
     // kernelfunc.py:43-49: the per-component distance sums do not depend on theta -> once per design
     const size_t ntile = (size_t)m->nb * (m->nb + 1) / 2;
-    CK(cudaMalloc(&m->kpls_dtiles, sizeof(double) * ntile * h * KB_TILE * KB_TILE));
+    CK(kb_dev_malloc(&m->kpls_dtiles, sizeof(double) * ntile * h * KB_TILE * KB_TILE));
     KbModelDev md{m->n, m->d, m->nind, m->n_pad, m->nb, m->kmask, m->XT, m->y, m->F};
     CK(kb_launch_kpls_dist(m->stream, md, h, m->pls, m->kpls_dtiles));
     g_launches += 1;
     CK(cudaStreamSynchronize(m->stream));
   }
-  CK(cudaMalloc(&m->result_dev, sizeof(KbSweepResult)));
+  CK(kb_dev_malloc(&m->result_dev, sizeof(KbSweepResult)));
   *out = m;
   return KB_OK;
 }
@@ -445,16 +523,16 @@ void kb_model_destroy(kb_model* m) {
   drop_nll_graphs(m->nll_graphs);
   free_ws(m->pop);
   free_ws(m->fit);
-  cudaFree(m->XT); cudaFree(m->y); cudaFree(m->F); cudaFree(m->pls); cudaFree(m->kpls_dtiles); cudaFree(m->kernel_ids_dev);
-  cudaFree(m->AT); cudaFree(m->rt); cudaFree(m->dense_tmp); cudaFree(m->idx_dev); cudaFree(m->p0);
-  cudaFree(m->p1); cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
-  cudaFree(m->result_dev); cudaFree(m->results_dev); cudaFree(m->few_scratch);
+  kb_dev_free(m->XT); kb_dev_free(m->y); kb_dev_free(m->F); kb_dev_free(m->pls); kb_dev_free(m->kpls_dtiles); kb_dev_free(m->kernel_ids_dev);
+  kb_dev_free(m->AT); kb_dev_free(m->rt); kb_dev_free(m->dense_tmp); kb_dev_free(m->idx_dev); kb_dev_free(m->p0);
+  kb_dev_free(m->p1); kb_dev_free(m->psi_scratch); kb_dev_free(m->ex_scratch); kb_dev_free(m->partials);
+  kb_dev_free(m->result_dev); kb_dev_free(m->results_dev); kb_dev_free(m->few_scratch);
   g_pinned.put(m->pin_small, m->pin_small_bytes);
-  cudaFree(m->ehvi.xd); cudaFree(m->ehvi.buf); cudaFree(m->ehvi.table); cudaFree(m->ehvi.red);
+  kb_dev_free(m->ehvi.xd); kb_dev_free(m->ehvi.buf); kb_dev_free(m->ehvi.table); kb_dev_free(m->ehvi.red);
   if (m->ehvi.ev_x) cudaEventDestroy(m->ehvi.ev_x);
   if (m->ehvi.ev_p2) cudaEventDestroy(m->ehvi.ev_p2);
   for (int i = 0; i < 2; ++i) {
-    cudaFree(m->stage_x[i]); cudaFree(m->stage_out[i]);
+    kb_dev_free(m->stage_x[i]); kb_dev_free(m->stage_out[i]);
     if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     if (m->ev_swept[i]) cudaEventDestroy(m->ev_swept[i]);
   }
@@ -659,13 +737,13 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
   const KbAugGeom& g = m->fit.g;
   const int n = m->n;
   if (!m->rt) {
-    CK(cudaMalloc(&m->rt, sizeof(double) * g.n_pad));
+    CK(kb_dev_malloc(&m->rt, sizeof(double) * g.n_pad));
     CK(cudaMemset(m->rt, 0, sizeof(double) * g.n_pad));
   }
   if (!m->AT) {
     m->nrows = round_up(g.n_pad + g.q, 128);
     m->ldat = m->nrows;
-    CK(cudaMalloc(&m->AT, sizeof(double) * (size_t)g.n_pad * m->ldat));
+    CK(kb_dev_malloc(&m->AT, sizeof(double) * (size_t)g.n_pad * m->ldat));
   }
   m->fitted = false;
   CK(cudaMemcpyAsync(m->fit.xpop, x, sizeof(double) * nbhyp, cudaMemcpyHostToDevice, m->stream));
@@ -699,7 +777,7 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
     }
   }
   if (U || Psi) {
-    if (!m->dense_tmp) CK(cudaMalloc(&m->dense_tmp, sizeof(double) * (size_t)n * n));
+    if (!m->dense_tmp) CK(kb_dev_malloc(&m->dense_tmp, sizeof(double) * (size_t)n * n));
     if (U) {
       kb_export_upper_kernel<<<1184, 256, 0, m->stream>>>(m->fit.aug, g.ld, n, m->dense_tmp);
       CK(cudaGetLastError());
@@ -721,13 +799,13 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
 kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d) {
   if (!m || !idx || nind != m->nind || d != m->d) KB_FAIL(KB_ERR_INVALID, "trend index shape mismatch");
   CK(cudaSetDevice(m->device));
-  cudaFree(m->idx_dev);
+  kb_dev_free(m->idx_dev);
   m->idx_dev = nullptr;
   int maxo = 0;
   for (int i = 0; i < nind * d; ++i) maxo = idx[i] > maxo ? idx[i] : maxo;
   m->maxorder = maxo;
   if (nind == 1 && maxo == 0) return KB_OK;   // ordinary Kriging: constant basis, fast path
-  CK(cudaMalloc(&m->idx_dev, sizeof(int) * (size_t)nind * d));
+  CK(kb_dev_malloc(&m->idx_dev, sizeof(int) * (size_t)nind * d));
   CK(cudaMemcpy(m->idx_dev, idx, sizeof(int) * (size_t)nind * d, cudaMemcpyHostToDevice));
   return KB_OK;
 }
@@ -738,8 +816,8 @@ kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const 
   CK(cudaSetDevice(m->device));
   m->norm_type = norm_type;
   if (norm_type == KB_NORM_NONE) return KB_OK;
-  if (!m->p0) CK(cudaMalloc(&m->p0, sizeof(double) * m->d));
-  if (!m->p1) CK(cudaMalloc(&m->p1, sizeof(double) * m->d));
+  if (!m->p0) CK(kb_dev_malloc(&m->p0, sizeof(double) * m->d));
+  if (!m->p1) CK(kb_dev_malloc(&m->p1, sizeof(double) * m->d));
   CK(cudaMemcpy(m->p0, p0, sizeof(double) * m->d, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(m->p1, p1, sizeof(double) * m->d, cudaMemcpyHostToDevice));
   return KB_OK;
@@ -751,7 +829,7 @@ static kb_status ensure_predict_scratch(kb_model* m) {
                            ? 2
                            : (kb_predict_can_reside(m->d, m->n_pad, qx, m->idx_dev ? 1 : 0) ? 1 : 0);
   if (m->ex_scratch && resident == m->pred_resident) return KB_OK;
-  cudaFree(m->psi_scratch); cudaFree(m->ex_scratch); cudaFree(m->partials);
+  kb_dev_free(m->psi_scratch); kb_dev_free(m->ex_scratch); kb_dev_free(m->partials);
   m->psi_scratch = m->ex_scratch = nullptr; m->partials = nullptr;
   m->pred_resident = resident;
   m->pred_stage_x = 1;
@@ -772,9 +850,9 @@ static kb_status ensure_predict_scratch(kb_model* m) {
     KB_FAIL(KB_ERR_CUDA, "the predictor keeps one 64-site strip and a 16-site training tile per dimension in shared "
                          "memory: d = %d does not fit (limit about 180)", m->d);
   const size_t strip = kb_predict_strip(resident != 0);
-  if (!resident) CK(cudaMalloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip));
-  CK(cudaMalloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * strip));
-  CK(cudaMalloc(&m->partials, sizeof(KbSweepResult) * m->pred_grid));
+  if (!resident) CK(kb_dev_malloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip));
+  CK(kb_dev_malloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * strip));
+  CK(kb_dev_malloc(&m->partials, sizeof(KbSweepResult) * m->pred_grid));
   return KB_OK;
 }
 
@@ -813,13 +891,13 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   if (few_fits && m->pred_resident == 0 && !(few_env && atoi(few_env) == 0)) {
     if (few_ny > m->few_slices) {
       CK(cudaStreamSynchronize(m->stream));
-      cudaFree(m->few_scratch);
+      kb_dev_free(m->few_scratch);
       m->few_scratch = nullptr;
       int cap = m->few_slices > 0 ? m->few_slices : 1;
       while (cap < few_ny) cap *= 2;
       while (cap > few_ny && kb_predict_few_scratch_doubles(m->n_pad, a.qx, cap) * sizeof(double) > (256u << 20)) --cap;
       const size_t nd = kb_predict_few_scratch_doubles(m->n_pad, a.qx, cap);
-      CK(cudaMalloc(&m->few_scratch, sizeof(double) * nd));
+      CK(kb_dev_malloc(&m->few_scratch, sizeof(double) * nd));
       CK(cudaMemsetAsync(m->few_scratch, 0, sizeof(double) * nd, m->stream));
       m->few_slices = cap;
     }
@@ -877,18 +955,18 @@ kb_status kb_predict(kb_model* m, long long npts, const double* x, const kb_acq_
     const long long cp = chunk > m->stage_pts ? chunk : m->stage_pts;
     const int no = nout > m->stage_nout ? nout : m->stage_nout;
     for (int i = 0; i < 2; ++i) {
-      cudaFree(m->stage_x[i]); cudaFree(m->stage_out[i]);
+      kb_dev_free(m->stage_x[i]); kb_dev_free(m->stage_out[i]);
       m->stage_x[i] = m->stage_out[i] = nullptr;
-      CK(cudaMalloc(&m->stage_x[i], sizeof(double) * (size_t)cp * m->d));
-      if (no > 0) CK(cudaMalloc(&m->stage_out[i], sizeof(double) * (size_t)cp * no));
+      CK(kb_dev_malloc(&m->stage_x[i], sizeof(double) * (size_t)cp * m->d));
+      if (no > 0) CK(kb_dev_malloc(&m->stage_out[i], sizeof(double) * (size_t)cp * no));
     }
     m->stage_pts = cp; m->stage_nout = no;
   }
   if (nchunks > m->results_cap) {
     CK(cudaStreamSynchronize(m->stream));
-    cudaFree(m->results_dev);
+    kb_dev_free(m->results_dev);
     m->results_dev = nullptr;
-    CK(cudaMalloc(&m->results_dev, sizeof(KbSweepResult) * (size_t)nchunks));
+    CK(kb_dev_malloc(&m->results_dev, sizeof(KbSweepResult) * (size_t)nchunks));
     m->results_cap = nchunks;
   }
   if (nchunks == 1) {
@@ -981,7 +1059,7 @@ kb_status kb_points_create(kb_points** out, int device, long long npts, int d, c
   CK(cudaSetDevice(device));
   kb_points* p = new kb_points();
   p->device = device; p->d = d; p->npts = npts;
-  if (cudaMalloc(&p->x, sizeof(double) * (size_t)npts * d) != cudaSuccess) {
+  if (kb_dev_malloc(&p->x, sizeof(double) * (size_t)npts * d) != cudaSuccess) {
     delete p;
     KB_FAIL(KB_ERR_CUDA, "cannot allocate %lld x %d points on device %d", npts, d, device);
   }
@@ -1004,23 +1082,23 @@ kb_status kb_points_generate(kb_points** out, int device, long long npts, int d,
   CK(cudaSetDevice(device));
   kb_points* p = new kb_points();
   p->device = device; p->d = d; p->npts = npts;
-  if (cudaMalloc(&p->x, sizeof(double) * (size_t)npts * d) != cudaSuccess) {
+  if (kb_dev_malloc(&p->x, sizeof(double) * (size_t)npts * d) != cudaSuccess) {
     delete p;
     KB_FAIL(KB_ERR_CUDA, "cannot allocate %lld x %d points on device %d", npts, d, device);
   }
   double* bounds = nullptr;
   if (dist == KB_DIST_UNIFORM) {
-    CK(cudaMalloc(&bounds, sizeof(double) * 2 * d));
+    CK(kb_dev_malloc(&bounds, sizeof(double) * 2 * d));
     CK(cudaMemcpy(bounds, lb, sizeof(double) * d, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(bounds + d, ub, sizeof(double) * d, cudaMemcpyHostToDevice));
   }
   cudaError_t e = kb_launch_points_generate(nullptr, p->x, npts, d, dist, p0, p1, bounds, bounds ? bounds + d : nullptr,
                                             seed, first_index);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  cudaFree(bounds);
+  kb_dev_free(bounds);
   g_launches += 1;
   if (e != cudaSuccess) {
-    cudaFree(p->x);
+    kb_dev_free(p->x);
     delete p;
     KB_FAIL(KB_ERR_CUDA, "population generator: %s", cudaGetErrorString(e));
   }
@@ -1051,17 +1129,17 @@ kb_status kb_points_generate_lowdisc(kb_points** out, int device, long long npts
   unsigned int* dirs_dev = nullptr;
   int* primes_dev = nullptr;
   double* bounds = nullptr;
-  cudaError_t e = cudaMalloc(&p->x, sizeof(double) * (size_t)npts * d);
+  cudaError_t e = kb_dev_malloc(&p->x, sizeof(double) * (size_t)npts * d);
   if (e == cudaSuccess && kind == KB_DIST_SOBOL) {
-    e = cudaMalloc(&dirs_dev, sizeof(unsigned int) * 32 * d);
+    e = kb_dev_malloc(&dirs_dev, sizeof(unsigned int) * 32 * d);
     if (e == cudaSuccess) e = cudaMemcpy(dirs_dev, dirs, sizeof(unsigned int) * 32 * d, cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess && kind == KB_DIST_HALTON) {
-    e = cudaMalloc(&primes_dev, sizeof(int) * d);
+    e = kb_dev_malloc(&primes_dev, sizeof(int) * d);
     if (e == cudaSuccess) e = cudaMemcpy(primes_dev, primes.data(), sizeof(int) * d, cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess && lb) {
-    e = cudaMalloc(&bounds, sizeof(double) * 2 * d);
+    e = kb_dev_malloc(&bounds, sizeof(double) * 2 * d);
     if (e == cudaSuccess) e = cudaMemcpy(bounds, lb, sizeof(double) * d, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(bounds + d, ub, sizeof(double) * d, cudaMemcpyHostToDevice);
   }
@@ -1069,10 +1147,10 @@ kb_status kb_points_generate_lowdisc(kb_points** out, int device, long long npts
     e = kb_launch_points_lowdisc(nullptr, p->x, npts, d, kind, dirs_dev, primes_dev, bounds, bounds ? bounds + d : nullptr,
                                  first_index);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  cudaFree(dirs_dev); cudaFree(primes_dev); cudaFree(bounds);
+  kb_dev_free(dirs_dev); kb_dev_free(primes_dev); kb_dev_free(bounds);
   g_launches += 1;
   if (e != cudaSuccess) {
-    cudaFree(p->x);
+    kb_dev_free(p->x);
     delete p;
     KB_FAIL(KB_ERR_CUDA, "low-discrepancy generator: %s", cudaGetErrorString(e));
   }
@@ -1090,7 +1168,7 @@ kb_status kb_points_get_rows(const kb_points* p, long long row0, long long nrows
 void kb_points_destroy(kb_points* p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  cudaFree(p->x); cudaFree(p->out);
+  kb_dev_free(p->x); kb_dev_free(p->out);
   delete p;
 }
 
@@ -1119,9 +1197,9 @@ kb_status kb_predict_points(kb_model* m, const kb_points* pts, const kb_acq_para
   const long long chunk = pts->npts < (1LL << 22) ? pts->npts : (1LL << 22);
   if ((long long)nout * chunk > pw->out_cap) {
     CK(cudaStreamSynchronize(m->stream));
-    cudaFree(pw->out);
+    kb_dev_free(pw->out);
     pw->out = nullptr;
-    CK(cudaMalloc(&pw->out, sizeof(double) * (size_t)nout * chunk));
+    CK(kb_dev_malloc(&pw->out, sizeof(double) * (size_t)nout * chunk));
     pw->out_cap = (long long)nout * chunk;
   }
   KbSweepResult total{};
@@ -1152,7 +1230,7 @@ static kb_status ehvi_table_to_device(int k, const double* front, const double* 
   if (k < 1 || !front || !ref) KB_FAIL(KB_ERR_INVALID, "bad Pareto front");
   std::vector<double> table(kb_ehvi_table_doubles(k));
   kb_ehvi_build_table(k, front, ref, table.data());
-  CK(cudaMalloc(table_dev, sizeof(double) * table.size()));
+  CK(kb_dev_malloc(table_dev, sizeof(double) * table.size()));
   CK(cudaMemcpy(*table_dev, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
   return KB_OK;
 }
@@ -1176,15 +1254,15 @@ kb_status kb_exi2d(int device, long long npts, const double* mu, const double* s
   double* buf = nullptr;
   void* red = nullptr;
   const int grid = kb_ehvi_grid(npts, num_sms);
-  cudaError_t e = cudaMalloc(&buf, sizeof(double) * (size_t)5 * npts);
-  if (e == cudaSuccess) e = cudaMalloc(&red, sizeof(KbEhviBestHost) * (size_t)(grid + 1));
+  cudaError_t e = kb_dev_malloc(&buf, sizeof(double) * (size_t)5 * npts);
+  if (e == cudaSuccess) e = kb_dev_malloc(&red, sizeof(KbEhviBestHost) * (size_t)(grid + 1));
   if (e == cudaSuccess) e = cudaMemcpy(buf, cols.data(), sizeof(double) * cols.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
     e = kb_launch_ehvi2d(nullptr, npts, buf, buf + npts, buf + 2 * npts, buf + 3 * npts, table_dev, k, 0, buf + 4 * npts,
                          (KbEhviBestHost*)red + 1, red, 0, num_sms);
   if (e == cudaSuccess) e = cudaMemcpy(out, buf + 4 * npts, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost);
   g_launches += 2;
-  cudaFree(buf); cudaFree(red); cudaFree(table_dev);
+  kb_dev_free(buf); kb_dev_free(red); kb_dev_free(table_dev);
   if (e != cudaSuccess) KB_FAIL(KB_ERR_CUDA, "exi2d: %s", cudaGetErrorString(e));
   return KB_OK;
 }
@@ -1210,13 +1288,13 @@ static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const d
   if (chunk > W.cap_pts || grid > W.cap_grid) {
     CK(cudaStreamSynchronize(m1->stream));
     CK(cudaStreamSynchronize(m2->stream));
-    cudaFree(W.xd); cudaFree(W.buf); cudaFree(W.red);
+    kb_dev_free(W.xd); kb_dev_free(W.buf); kb_dev_free(W.red);
     W.xd = W.buf = nullptr; W.red = nullptr;
     const long long cp = chunk > W.cap_pts ? chunk : W.cap_pts;
     const int cg = kb_ehvi_grid(cp, m1->num_sms);
-    CK(cudaMalloc(&W.xd, sizeof(double) * (size_t)cp * d));
-    CK(cudaMalloc(&W.buf, sizeof(double) * (size_t)5 * cp));
-    CK(cudaMalloc(&W.red, sizeof(KbEhviBestHost) * (size_t)(cg + 1)));
+    CK(kb_dev_malloc(&W.xd, sizeof(double) * (size_t)cp * d));
+    CK(kb_dev_malloc(&W.buf, sizeof(double) * (size_t)5 * cp));
+    CK(kb_dev_malloc(&W.red, sizeof(KbEhviBestHost) * (size_t)(cg + 1)));
     W.cap_pts = cp; W.cap_grid = cg;
   }
   // the cell table depends on the front and the reference point only: rebuilt when they change
@@ -1229,9 +1307,9 @@ static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const d
       kb_ehvi_build_table(k, front, ref, table.data());
       CK(cudaStreamSynchronize(m1->stream));
       if (table.size() > W.cap_table) {
-        cudaFree(W.table);
+        kb_dev_free(W.table);
         W.table = nullptr;
-        CK(cudaMalloc(&W.table, sizeof(double) * table.size()));
+        CK(kb_dev_malloc(&W.table, sizeof(double) * table.size()));
         W.cap_table = table.size();
       }
       CK(cudaMemcpy(W.table, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
@@ -1353,9 +1431,9 @@ kb_status kb_train_cmaes(kb_model* m, int nbhyp, int trainvar, double fixed_nugg
   }
   for (int i = 0; i < P.mu; ++i) V.w[i] = w[i];
   double *state = nullptr, *xpop = nullptr, *fdev = nullptr;
-  cudaError_t e = cudaMalloc(&state, sizeof(double) * nstate);
-  if (e == cudaSuccess) e = cudaMalloc(&xpop, sizeof(double) * (size_t)P.lam * nbhyp);
-  if (e == cudaSuccess) e = cudaMalloc(&fdev, sizeof(double) * (size_t)P.lam);
+  cudaError_t e = kb_dev_malloc(&state, sizeof(double) * nstate);
+  if (e == cudaSuccess) e = kb_dev_malloc(&xpop, sizeof(double) * (size_t)P.lam * nbhyp);
+  if (e == cudaSuccess) e = kb_dev_malloc(&fdev, sizeof(double) * (size_t)P.lam);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(state, init.data(), sizeof(double) * nstate, cudaMemcpyHostToDevice, m->stream);
   if (e == cudaSuccess) e = kb_launch_cmaes_step(m->stream, P, state, fdev, xpop, 1);
@@ -1384,7 +1462,7 @@ kb_status kb_train_cmaes(kb_model* m, int nbhyp, int trainvar, double fixed_nugg
       if (hist) for (int g = 0; g < (int)V.scal[2]; ++g) hist[g] = V.hist[g];
     }
   }
-  cudaFree(state); cudaFree(xpop); cudaFree(fdev);
+  kb_dev_free(state); kb_dev_free(xpop); kb_dev_free(fdev);
   if (s != KB_OK) return s;
   if (e != cudaSuccess) KB_FAIL(KB_ERR_CUDA, "cmaes: %s", cudaGetErrorString(e));
   return KB_OK;
@@ -1394,7 +1472,7 @@ kb_status kb_loocv(kb_model* m, double* pred_out) {
   if (!m || !pred_out) KB_FAIL(KB_ERR_INVALID, "bad argument");
   if (!m->fitted) KB_FAIL(KB_ERR_STATE, "loocv called before kb_fit_state");
   CK(cudaSetDevice(m->device));
-  if (!m->dense_tmp) CK(cudaMalloc(&m->dense_tmp, sizeof(double) * (size_t)m->n * m->n));
+  if (!m->dense_tmp) CK(kb_dev_malloc(&m->dense_tmp, sizeof(double) * (size_t)m->n * m->n));
   CK(kb_launch_loocv(m->stream, m->n, m->n_pad, m->nind, m->AT, m->ldat, m->fit.Mbuf, m->y, m->dense_tmp));
   g_launches += 1;
   CK(cudaMemcpyAsync(pred_out, m->dense_tmp, sizeof(double) * m->n, cudaMemcpyDeviceToHost, m->stream));
@@ -1425,7 +1503,7 @@ kb_status kb_corr_matrix(int device, int n, int mm, int d, const double* XN, con
   cudaStream_t st = nullptr;
   kb_status rc = KB_OK;
   auto cleanup = [&]() {
-    cudaFree(dXN); cudaFree(dXM); cudaFree(dXNT); cudaFree(dXMT); cudaFree(dpar); cudaFree(dout);
+    kb_dev_free(dXN); kb_dev_free(dXM); kb_dev_free(dXNT); kb_dev_free(dXMT); kb_dev_free(dpar); kb_dev_free(dout);
   };
 #define CKC(call)                                                                          \
   do {                                                                                     \
@@ -1436,12 +1514,12 @@ kb_status kb_corr_matrix(int device, int n, int mm, int d, const double* XN, con
       g_err = buf_; cleanup(); return KB_ERR_CUDA;                                         \
     }                                                                                      \
   } while (0)
-  CKC(cudaMalloc(&dXN, sizeof(double) * (size_t)n * d));
-  CKC(cudaMalloc(&dXM, sizeof(double) * (size_t)mm * d));
-  CKC(cudaMalloc(&dXNT, sizeof(double) * (size_t)ldn * d));
-  CKC(cudaMalloc(&dXMT, sizeof(double) * (size_t)ldm * d));
-  CKC(cudaMalloc(&dpar, sizeof(double) * (2 * d + 4)));
-  CKC(cudaMalloc(&dout, sizeof(double) * (size_t)n * mm));
+  CKC(kb_dev_malloc(&dXN, sizeof(double) * (size_t)n * d));
+  CKC(kb_dev_malloc(&dXM, sizeof(double) * (size_t)mm * d));
+  CKC(kb_dev_malloc(&dXNT, sizeof(double) * (size_t)ldn * d));
+  CKC(kb_dev_malloc(&dXMT, sizeof(double) * (size_t)ldm * d));
+  CKC(kb_dev_malloc(&dpar, sizeof(double) * (2 * d + 4)));
+  CKC(kb_dev_malloc(&dout, sizeof(double) * (size_t)n * mm));
   CKC(cudaMemcpy(dXN, XN, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice));
   CKC(cudaMemcpy(dXM, XM, sizeof(double) * (size_t)mm * d, cudaMemcpyHostToDevice));
   CKC(cudaMemcpy(dpar, gw.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
@@ -1470,7 +1548,7 @@ kb_status kb_measure_peak(int device, int which, double* value) {
   float ms = 0.f;
   if (which < 2) {
     double* sink = nullptr;
-    CK(cudaMalloc(&sink, sizeof(double)));
+    CK(kb_dev_malloc(&sink, sizeof(double)));
     const int grid = prop.multiProcessorCount * 4, iters = 20000;
     CK(kb_launch_peak(nullptr, which, 2000, grid, sink));
     CK(cudaDeviceSynchronize());
@@ -1486,13 +1564,13 @@ kb_status kb_measure_peak(int device, int which, double* value) {
       if (tf > best) best = tf;
     }
     g_launches += 4;
-    cudaFree(sink);
+    kb_dev_free(sink);
     *value = best;
   } else {
     const size_t bytes = (size_t)1 << 30;
     double *a = nullptr, *b = nullptr;
-    CK(cudaMalloc(&a, bytes));
-    CK(cudaMalloc(&b, bytes));
+    CK(kb_dev_malloc(&a, bytes));
+    CK(kb_dev_malloc(&b, bytes));
     CK(cudaMemset(a, 0, bytes));
     CK(cudaMemcpy(b, a, bytes, cudaMemcpyDeviceToDevice));
     CK(cudaDeviceSynchronize());
@@ -1506,7 +1584,7 @@ kb_status kb_measure_peak(int device, int which, double* value) {
       const double gbs = 2.0 * bytes / (ms * 1e-3) / 1e9;
       if (gbs > best) best = gbs;
     }
-    cudaFree(a); cudaFree(b);
+    kb_dev_free(a); kb_dev_free(b);
     *value = best;
   }
   cudaEventDestroy(e0);
