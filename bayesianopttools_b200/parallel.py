@@ -102,3 +102,38 @@ def gather_sweep_result(local):
         recs.append(dict(best_val=float(f[0]), best_idx=int(a[1]), min_u=float(f[2]), min_u_idx=int(a[3]),
                          n_fail=int(a[4]), n_fail_minus=int(a[5]), n_fail_plus=int(a[6]), n_points=int(a[7])))
     return merge_results(recs)
+
+
+def gather_counts(n_local):
+    """Sizes of every rank's shard (all-gather of one int64), e.g. to turn local site indices into
+    indices of the whole Monte-Carlo population."""
+    rank, size = world()
+    if size == 1:
+        return [int(n_local)]
+    mine = torch.tensor([int(n_local)], dtype=torch.int64, device=_comm_device())
+    outs = [torch.empty_like(mine) for _ in range(size)]
+    dist.all_gather(outs, mine)
+    return [int(o.item()) for o in outs]
+
+
+def owner_of(index, counts):
+    """Rank whose contiguous shard holds global site `index`, and the index inside that shard."""
+    start = 0
+    for r, c in enumerate(counts):
+        if index < start + c:
+            return r, int(index - start)
+        start += c
+    raise IndexError("site %d is outside the %d-site population" % (index, start))
+
+
+def broadcast_row(row, src, d):
+    """The d coordinates of one site, sent by rank `src` to every rank (`row` is ignored elsewhere)."""
+    rank, size = world()
+    if size == 1:
+        return np.asarray(row, dtype=np.float64).reshape(-1)
+    buf = torch.zeros(d, dtype=torch.float64)
+    if rank == src:
+        buf = torch.as_tensor(np.asarray(row, dtype=np.float64).reshape(-1).copy())
+    buf = buf.to(_comm_device())
+    dist.broadcast(buf, src=src)
+    return buf.cpu().numpy()

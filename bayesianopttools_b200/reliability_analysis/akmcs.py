@@ -4,11 +4,19 @@ Per update the reference predicts (mean, s) over the whole Monte-Carlo populatio
 10 000-row chunks and then runs three Python list comprehensions over N for the failure
 counts.  Here one fused launch returns pred, s and the reductions: #{G<=0},
 #{G-1.96s<=0}, #{G+1.96s<=0}, min U and its first index (csrc/kb_predict.cu).
+
+Several GPUs (BASELINE configs[4]): under torch.distributed every rank holds
+one contiguous shard of the Monte-Carlo population as its `init_samp`, resident on its GPU across
+all updates.  Per update each rank sweeps its shard; one 64-byte record per rank is all-gathered
+(the three failure counters are summed, min U is merged with the lowest whole-population index on
+ties, `parallel.gather_sweep_result`), the rank that owns the new site broadcasts its d
+coordinates, and every rank retrains the (small) model redundantly from identical inputs.
 """
 import time
 
 import numpy as np
 
+from bayesianopttools_b200 import parallel
 from bayesianopttools_b200.misc.sampling.samplingplan import realval
 from bayesianopttools_b200.testcase.RA.testcase import evaluate
 
@@ -20,9 +28,16 @@ class AKMCS:
         self.akmcsInfo = akmcsInfo
         self.init_samp = akmcsInfo["init_samp"]         # (N, d) array, or a _lib.DevicePoints set
         self.maxupdate = akmcsInfo["maxupdate"]
-        self.nsamp = self.init_samp.n if hasattr(self.init_samp, "_h") else np.size(self.init_samp, axis=0)
-        self.Gx = np.zeros((self.nsamp, 1))
-        self.sigmaG = np.zeros((1, self.nsamp))
+        self.nsamp_local = self.init_samp.n if hasattr(self.init_samp, "_h") else np.size(self.init_samp, axis=0)
+        # akmcsInfo["shard_population"] (default: on whenever torch.distributed runs more than one rank):
+        # init_samp is this rank's shard, nsamp the size of the whole population
+        self._rank, world_size = parallel.world()
+        self.sharded = world_size > 1 and bool(akmcsInfo.get("shard_population", True))
+        self._counts = parallel.gather_counts(self.nsamp_local) if self.sharded else [self.nsamp_local]
+        self._offset = int(sum(self._counts[:self._rank])) if self.sharded else 0
+        self.nsamp = int(sum(self._counts))
+        self.Gx = np.zeros((self.nsamp_local, 1))
+        self.sigmaG = np.zeros((1, self.nsamp_local))
         self.stop_criteria = 100
         self.keep_fields = akmcsInfo.get("keep_fields", True)
         # the Monte-Carlo population is the same in every update (akmcs.py:66-206): it is uploaded
@@ -46,11 +61,21 @@ class AKMCS:
         if self.keep_fields:
             self.Gx = outs["pred"].reshape(-1, 1)
             self.sigmaG = outs["s"].reshape(1, -1)
+        if self.sharded:
+            res = dict(res)
+            res["min_u_idx"] += self._offset          # indices of the whole population
+            res["best_idx"] += self._offset
+            res = parallel.gather_sweep_result(res)
+            owner, local = parallel.owner_of(res["min_u_idx"], self._counts)
+            row = self.init_samp[local, :] if owner == self._rank else None
+            xnew = parallel.broadcast_row(row, owner, self.krigobj.KrigInfo["nvar"])
+        else:
+            xnew = self.init_samp[res["min_u_idx"], :]
         self._res = res
         N = self.nsamp
         self.Pf = res["n_fail"] / N                                   # pfcalc   akmcs.py:208-212
         self.minU = res["min_u"]                                       # lfucalc  akmcs.py:222-226
-        self.xnew = self.init_samp[res["min_u_idx"], :]
+        self.xnew = xnew
         pf0 = res["n_fail"] / N                                        # stopcrit akmcs.py:228-238
         self.stop_criteria = 100 if pf0 == 0 else (res["n_fail_minus"] / N - res["n_fail_plus"] / N) / pf0
         if self.keep_fields:
@@ -100,13 +125,18 @@ class AKMCS:
 
 
 def mcpopgen_device(lb=None, ub=None, n_order=6, n_coeff=1, type="random", ndim=2, stddev=1, mean=0, seed=0,
-                    first_index=0):
+                    first_index=0, shard=False):
     """mcpopgen (akmcs.py:241-260) with the population generated and kept on the device: same arguments
     and distributions, counter-based Philox stream instead of numpy's global Mersenne Twister (so the
     sample differs from numpy's, like any re-seeding would); returns a `_lib.DevicePoints` set that AKMCS
-    accepts as `init_samp`."""
+    accepts as `init_samp`.  `shard=True` under torch.distributed: this rank generates only its contiguous
+    share of the same stream (site i has the same coordinates whatever the number of ranks)."""
     from .. import _lib
     nmc = int(n_coeff * 10 ** n_order)
+    if shard:
+        rank, size = parallel.world()
+        start, stop = parallel.point_shard(nmc, rank, size)
+        first_index, nmc = first_index + start, stop - start
     if type.lower() == "random":
         if lb is None or ub is None:
             raise ValueError("type 'random' is selected, please input lower bound and upper bound value")

@@ -47,6 +47,84 @@ def _worker(rank, size, port, q):
         dist.destroy_process_group()
 
 
+class _FakeKrig:
+    """Stands in for the fitted Kriging model (the device is not available on CPU): mean = the limit
+    state plus a bias that shrinks with every added sample, s = distance to the nearest sample.  Only
+    the reductions matter here -- they follow csrc/kb_predict.cu (first index on ties)."""
+
+    def __init__(self, X, y):
+        self.KrigInfo = dict(X=np.array(X, dtype=float), y=np.array(y, dtype=float).reshape(-1, 1), nvar=2,
+                             nsamp=len(X))
+
+    def standardize(self):
+        pass
+
+    def train(self, disp=False):
+        pass
+
+    def predict_sweep(self, x, acq="u", want=()):
+        x = np.asarray(x, dtype=float)
+        X = self.KrigInfo["X"]
+        g = _limit_state(x) + 2.0 / len(X) * np.sin(3 * x[:, 0])
+        s = np.sqrt(((x[:, None, :] - X[None, :, :]) ** 2).sum(-1)).min(1) + 0.01
+        u = np.abs(g) / s
+        res = dict(best_val=float(u.min()), best_idx=int(np.argmin(u)), min_u=float(u.min()),
+                   min_u_idx=int(np.argmin(u)), n_fail=int((g <= 0).sum()),
+                   n_fail_minus=int((g - 1.96 * s <= 0).sum()), n_fail_plus=int((g + 1.96 * s <= 0).sum()),
+                   n_points=len(x))
+        return res, dict(pred=g, s=s)
+
+
+def _limit_state(x):
+    x = np.atleast_2d(x)
+    return 2.5 - x[:, 0] ** 2 - 0.5 * x[:, 1]
+
+
+def _akmcs_history(pop, shard):
+    from bayesianopttools_b200.reliability_analysis.akmcs import AKMCS
+    X0 = np.array([[0.0, 0.0], [1.0, -1.0], [-2.0, 1.0], [2.0, 2.0]])
+    krig = _FakeKrig(X0, _limit_state(X0))
+    info = dict(init_samp=pop, maxupdate=4, evaluate=_limit_state, resident_population=False,
+                shard_population=shard)
+    ak = AKMCS(krig, info)
+    ak.run(disp=False)
+    return ak, np.hstack([ak.updateX, ak.minUiter.reshape(-1, 1)]), (ak.Pf, ak.stop_criteria, ak.cov, ak.nsamp)
+
+
+def _akmcs_worker(rank, size, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        pop = np.random.default_rng(11).normal(size=(1001, 2))         # uneven shards: 501 + 500
+        pop[700] = pop[3]                                              # a tie across the shard boundary
+        lo, hi = parallel.point_shard(len(pop), rank, size)
+        ak, hist, tail = _akmcs_history(pop[lo:hi], True)
+        assert ak.sharded and ak.nsamp == 1001 and ak.nsamp_local == hi - lo and ak.Gx.shape == (hi - lo, 1)
+        _, hist1, tail1 = _akmcs_history(pop, False)                   # the whole population on one rank
+        assert np.array_equal(hist, hist1), (hist, hist1)
+        assert tail == tail1, (tail, tail1)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_akmcs_sharded_over_two_ranks_equals_one_rank():
+    """AKMCS.run with the Monte-Carlo population split over 2 ranks (counter sum, min-U merge, owner
+    broadcast of the new site) walks exactly the path of the unsharded run."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_akmcs_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(out) == [(0, "ok"), (1, "ok")], out
+
+
 def test_world_size_2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
