@@ -25,6 +25,20 @@ def likelihood_batch(xpop, KrigInfo, trainvar=True, return_info=False):
     xpop = np.atleast_2d(np.asarray(xpop, dtype=float))
     if KrigInfo["kernel"] == ["iso_gaussian"]:
         xpop = np.repeat(xpop[:, :1], int(KrigInfo["nvar"]), axis=1)
+    if KrigInfo.get("shard_population", False):
+        # candidate b is evaluated by rank b mod G, the NLL slices (8 B per candidate) are
+        # all-gathered.  Opt-in, because EVERY rank must then make the same calls with the same population (the
+        # optimisers here are deterministic, so ranks that train the same design stay in lockstep).
+        from bayesianopttools_b200 import parallel
+        rank, size = parallel.world()
+        if size > 1 and len(xpop) >= size:
+            mine = parallel.candidate_slice(len(xpop), rank, size)
+            nll, info = holder.model.nll_batch(xpop[mine], trainvar, fixed_nugget_of(KrigInfo), return_info=True)
+            full, _ = parallel.gather_population_nll(nll, len(xpop))
+            if not return_info:
+                return full
+            flags, _ = parallel.gather_population_nll(info.astype(np.float64), len(xpop))
+            return full, flags.astype(info.dtype)
     return holder.model.nll_batch(xpop, trainvar, fixed_nugget_of(KrigInfo), return_info=return_info)
 
 

@@ -125,6 +125,63 @@ def test_akmcs_sharded_over_two_ranks_equals_one_rank():
     assert sorted(out) == [(0, "ok"), (1, "ok")], out
 
 
+class _FakeHolder:
+    """likelihood_batch only needs holder.model.nll_batch: a deterministic stand-in for the device."""
+
+    class model:
+        calls = []
+
+        @classmethod
+        def nll_batch(cls, xpop, trainvar, nugget, return_info=False):
+            cls.calls.append(len(xpop))
+            f = np.sum((xpop - 0.25) ** 2, axis=1) + 3.0
+            info = (xpop[:, 0] > 0.9).astype(np.int32)
+            f = np.where(info != 0, np.inf, f)
+            return (f, info) if return_info else f
+
+
+def _likelihood_worker(rank, size, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from bayesianopttools_b200.surrogate_models.supports import likelihood_func as lf
+        lf.get_model = lambda K: _FakeHolder
+        K = dict(kernel=["gaussian"], nvar=3, nugget=-6, shard_population=True)
+        xpop = np.random.default_rng(5).uniform(0, 1, (7, 3))
+        want, want_info = _FakeHolder.model.nll_batch(xpop, False, -6.0, return_info=True)
+        _FakeHolder.model.calls.clear()
+        got, info = lf.likelihood_batch(xpop, K, trainvar=False, return_info=True)
+        assert np.array_equal(got, want) and np.array_equal(info, want_info) and info.dtype == want_info.dtype
+        assert _FakeHolder.model.calls == [4 - rank]                    # 7 candidates: ranks own 4 and 3
+        assert np.array_equal(lf.likelihood_batch(xpop, K, trainvar=False), want)
+        # fewer candidates than ranks, or the switch off: evaluated locally, no exchange
+        _FakeHolder.model.calls.clear()
+        assert np.array_equal(lf.likelihood_batch(xpop[:1], K, trainvar=False), want[:1])
+        K["shard_population"] = False
+        assert np.array_equal(lf.likelihood_batch(xpop, K, trainvar=False), want)
+        assert _FakeHolder.model.calls == [1, 7]
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_likelihood_population_sharded_over_two_ranks():
+    """likelihood_batch with KrigInfo['shard_population']: rank r evaluates candidates b = r mod 2 and the
+    all-gathered population equals the unsharded evaluation, flags included."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_likelihood_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(out) == [(0, "ok"), (1, "ok")], out
+
+
 def test_world_size_2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
