@@ -10,6 +10,7 @@ with the arg-min reduced on the device (the batched equivalent of the reference'
 import numpy as np
 from scipy.optimize import fmin_cobyla, minimize
 
+from bayesianopttools_b200 import parallel
 from bayesianopttools_b200.misc.sampling.samplingplan import realval
 from .cmaes import fmin_batched
 from .ehvi.EHVIcomputation import ehvi_best, ehvicalc
@@ -19,23 +20,26 @@ from .ga.uncGA import uncGA
 _sweep_calls = 0
 
 
-def sweep_candidates(krigobj, ncand, rng=None, sampler="sobol", seed=None):
+def sweep_candidates(krigobj, ncand, rng=None, sampler="sobol", seed=None, span=None):
     """Candidate designs of the `sweep` optimisers.  Default: a Sobol design generated ON the device
     (no host->device copy of the candidates; a different stretch of the sequence on every call so that
     successive updates do not re-score the same sites); `sampler='random'` draws device Philox uniforms;
-    a caller-supplied numpy `rng` keeps everything on the host (reproducible tests)."""
+    a caller-supplied numpy `rng` keeps everything on the host (reproducible tests).  `span=(lo, hi)`:
+    only candidates lo .. hi-1 of that same set (one rank's shard)."""
     global _sweep_calls
     K = krigobj.KrigInfo
+    lo, hi = (0, int(ncand)) if span is None else span
     if rng is not None:
-        return realval(K["lb"], K["ub"], rng.random((int(ncand), K["nvar"])))
+        return realval(K["lb"], K["ub"], rng.random((int(ncand), K["nvar"])))[lo:hi]
     from .. import _lib
     call = _sweep_calls
     _sweep_calls += 1
     if sampler.lower() == "random":
-        return _lib.DevicePoints.generate(int(ncand), K["nvar"], dist="random", lb=K["lb"], ub=K["ub"],
-                                          seed=call if seed is None else seed)
+        return _lib.DevicePoints.generate(hi - lo, K["nvar"], dist="random", lb=K["lb"], ub=K["ub"],
+                                          seed=call if seed is None else seed, first_index=lo)
     first = 1 + (call * int(ncand)) % max(1, (1 << 32) - 2 * int(ncand))
-    return _lib.DevicePoints.generate(int(ncand), K["nvar"], dist="sobol", lb=K["lb"], ub=K["ub"], first_index=first)
+    return _lib.DevicePoints.generate(hi - lo, K["nvar"], dist="sobol", lb=K["lb"], ub=K["ub"],
+                                      first_index=first + lo)
 
 
 def run_single_opt(krigobj, soboInfo, krigconstlist=None, cheapconstlist=None):
@@ -52,10 +56,26 @@ def run_single_opt(krigobj, soboInfo, krigconstlist=None, cheapconstlist=None):
     lbv, ubv = np.asarray(K["lb"], dtype=float), np.asarray(K["ub"], dtype=float)
 
     if acquifuncopt == "sweep":
-        cand = sweep_candidates(krigobj, soboInfo.get("ncandidates", 1_000_000), soboInfo.get("rng"),
-                                soboInfo.get("sweep_sampler", "sobol"), soboInfo.get("seed"))
+        # soboInfo["shard_candidates"] under torch.distributed: every rank scores a contiguous
+        # share of the SAME candidate set, one 64-byte record per rank is all-gathered (lowest candidate index on
+        # ties) and the owner of the winner broadcasts its coordinates; all ranks must make this call.
+        ncand = int(soboInfo.get("ncandidates", 1_000_000))
+        rank, size = parallel.world() if soboInfo.get("shard_candidates", False) else (0, 1)
+        lo, hi = parallel.point_shard(ncand, rank, size)
+        cand = sweep_candidates(krigobj, ncand, soboInfo.get("rng"), soboInfo.get("sweep_sampler", "sobol"),
+                                soboInfo.get("seed"), span=(lo, hi) if size > 1 else None)
         res, _ = krigobj.predict_sweep(cand, acq=acquifunc)
-        xnext, fnext = np.array(cand[res["best_idx"]], dtype=float), res["best_val"]
+        if size > 1:
+            res = dict(res)
+            res["best_idx"] += lo
+            res["min_u_idx"] += lo
+            res = parallel.gather_sweep_result(res)
+            counts = [b - a for a, b in (parallel.point_shard(ncand, r, size) for r in range(size))]
+            owner, local = parallel.owner_of(res["best_idx"], counts)
+            xnext = parallel.broadcast_row(cand[local] if owner == rank else None, owner, nvar)
+        else:
+            xnext = np.array(cand[res["best_idx"]], dtype=float)
+        fnext = res["best_val"]
         if soboInfo.get("sweep_polish", True):
             r = minimize(krigobj.predict, xnext, method="L-BFGS-B", bounds=np.column_stack((lbv, ubv)),
                          args=(acquifunc,))

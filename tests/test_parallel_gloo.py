@@ -182,6 +182,40 @@ def test_likelihood_population_sharded_over_two_ranks():
     assert sorted(out) == [(0, "ok"), (1, "ok")], out
 
 
+def _sweep_worker(rank, size, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from bayesianopttools_b200.optim_tools.acquifunc_opt import run_single_opt
+        X0 = np.array([[0.0, 0.0], [1.0, -1.0], [-2.0, 1.0], [2.0, 2.0]])
+        krig = _FakeKrig(X0, _limit_state(X0))
+        krig.KrigInfo.update(lb=-3 * np.ones(2), ub=3 * np.ones(2))
+        info = dict(acquifuncopt="sweep", acquifunc="EI", nrestart=1, ncandidates=777, sweep_polish=False)
+        x1, f1 = run_single_opt(krig, dict(info, rng=np.random.default_rng(9)))
+        x2, f2 = run_single_opt(krig, dict(info, rng=np.random.default_rng(9), shard_candidates=True))
+        assert np.array_equal(x1, x2) and f1 == f2, (x1, x2, f1, f2)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sobo_sweep_sharded_over_two_ranks_equals_one_rank():
+    """run_single_opt(acquifuncopt='sweep', shard_candidates=True): 777 candidates split 389 + 388, the merged
+    winner and its coordinates equal the unsharded sweep on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(out) == [(0, "ok"), (1, "ok")], out
+
+
 def test_world_size_2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
