@@ -579,11 +579,15 @@ int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
   return (2 * (kb_predict_warp_smem_bytes(d, (n + 7) & ~7, qx) + 1024) <= 227 * 1024) ? 2 : 1;
 }
 
-template <int MASK>
+// D > 0: the design has exactly D columns (compile-time: the per-dimension weights live in registers, no
+// predicated dimension loop); D = 0: any d <= PW_MAXD.  U = correlation chains in flight per lane.
+// The triangular product takes the 8-row blocks in pairs (6 fragment loads per 8 DMMA instead of 10).
+template <int MASK, int D, int U>
 __global__ void __launch_bounds__(256, 2)
 kb_predict_warp_kernel(KbPredictArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int n = P.n, d = P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
+  constexpr int DD = D ? D : PW_MAXD;
+  const int n = P.n, d = D ? D : P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
   KbSweepResult* red = reinterpret_cast<KbSweepResult*>(smem_raw);
   double* swk = reinterpret_cast<double*>(smem_raw + sizeof(KbSweepResult) * 8);   // [4] (+4 pad)
   double* XTs = swk + 8;                    // [d][n8]
@@ -618,15 +622,21 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   const int nrb = n8 >> 3;
   KbRunning run;
   kb_run_init(run);
+  double rgw[DD], rith[DD];                 // D > 0: per-dimension weights in registers
+#pragma unroll
+  for (int dim = 0; dim < DD; ++dim) {
+    rgw[dim] = (D && dim < d) ? sgw[dim] : 0.0;
+    rith[dim] = (D && dim < d) ? sith[dim] : 0.0;
+  }
 
   const long long ngroups = (P.m + 31) / 32;
   for (long long grp = (long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (long long)gridDim.x * 8) {
     const long long site = grp * 32 + lane;
     const bool valid = site < P.m;
     // ---- this lane's site, standardised ------------------------------------
-    double xv[PW_MAXD];
+    double xv[DD];
 #pragma unroll
-    for (int dim = 0; dim < PW_MAXD; ++dim) {
+    for (int dim = 0; dim < DD; ++dim) {
       double v = 0.0;
       if (dim < d && valid) {
         v = P.x[(size_t)site * d + dim];
@@ -641,13 +651,15 @@ kb_predict_warp_kernel(KbPredictArgs P) {
     }
     // ---- psi column of this site; psi' alpha and 1' R^-1 psi on the way --------
     double ex0 = 0.0, ex1 = 0.0;
-#pragma unroll 2
+#pragma unroll U
     for (int k = 0; k < n8; ++k) {
       KbPairAcc acc;
       kb_pair_init(acc);
 #pragma unroll
-      for (int dim = 0; dim < PW_MAXD; ++dim)
-        if (dim < d) kb_pair_dim(acc, xv[dim] - XTs[dim * n8 + k], sgw[dim], sith[dim], MASK);
+      for (int dim = 0; dim < DD; ++dim) {
+        if (D) kb_pair_dim(acc, xv[dim] - XTs[dim * n8 + k], rgw[dim], rith[dim], MASK);
+        else if (dim < d) kb_pair_dim(acc, xv[dim] - XTs[dim * n8 + k], sgw[dim], sith[dim], MASK);
+      }
       double val = kb_pair_finish(acc, swk, MASK);
       if (k >= n) val = 0.0;
       ex0 = fma(val, exts[k], ex0);
@@ -659,7 +671,42 @@ kb_predict_warp_kernel(KbPredictArgs P) {
     double sq[4][2];
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) sq[cb][0] = sq[cb][1] = 0.0;
-    for (int rb = 0; rb < nrb; ++rb) {
+    int rb = 0;
+    {
+      // two 8-row blocks per pass: the psi fragments of a k-step serve both
+      for (; rb + 1 < nrb; rb += 2) {
+        double acc[2][4][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) acc[h][cb][0] = acc[h][cb][1] = 0.0;
+        const int kmax = 2 * (rb + 1);               // block rb needs k < 8 (rb + 1), block rb + 1 eight more
+        for (int ks = 0; ks < kmax; ++ks) {
+          const double a0 = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + gq];
+          const double a1 = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + 8 + gq];
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            const double bf = psiW[ks * 4 + tq][cb * 8 + gq];
+            kb_dmma(acc[0][cb][0], acc[0][cb][1], a0, bf);
+            kb_dmma(acc[1][cb][0], acc[1][cb][1], a1, bf);
+          }
+        }
+#pragma unroll
+        for (int ks = kmax; ks < kmax + 2; ++ks) {
+          const double a1 = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + 8 + gq];
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[1][cb][0], acc[1][cb][1], a1, psiW[ks * 4 + tq][cb * 8 + gq]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            sq[cb][0] = fma(acc[h][cb][0], acc[h][cb][0], sq[cb][0]);
+            sq[cb][1] = fma(acc[h][cb][1], acc[h][cb][1], sq[cb][1]);
+          }
+      }
+    }
+    for (; rb < nrb; ++rb) {
       double acc[4][2];
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
@@ -747,13 +794,37 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
     default: { constexpr int M_ = 15; CALL; } break;                     \
   }
 
-template <int MASK>
-static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int MASK, int D, int U>
+static cudaError_t kb_predict_warp_launch_v(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_warp_kernel<MASK><<<grid, 256, smem, st>>>(a);
+  kb_predict_warp_kernel<MASK, D, U><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
+}
+// The kernel is compiled for every design width it serves (1 .. PW_MAXD; the reliability problems AK-MCS
+// sweeps are 2-D); KB_PW_D=0 forces the runtime-d variant (debug aid).
+template <int MASK>
+static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+  static const char* env_d = getenv("KB_PW_D");
+  const int dsel = (env_d && atoi(env_d) == 0) ? 0 : a.d;
+  switch (dsel) {
+    case 1: return kb_predict_warp_launch_v<MASK, 1, 4>(st, a, grid, smem);
+    case 2: return kb_predict_warp_launch_v<MASK, 2, 4>(st, a, grid, smem);
+    case 3: return kb_predict_warp_launch_v<MASK, 3, 4>(st, a, grid, smem);
+    default: break;
+  }
+  if constexpr (MASK != 15) {       // composite kernels carry both weight sets: wider designs would spill
+    switch (dsel) {
+      case 4: return kb_predict_warp_launch_v<MASK, 4, 4>(st, a, grid, smem);
+      case 5: return kb_predict_warp_launch_v<MASK, 5, 2>(st, a, grid, smem);
+      case 6: return kb_predict_warp_launch_v<MASK, 6, 2>(st, a, grid, smem);
+      case 7: return kb_predict_warp_launch_v<MASK, 7, 2>(st, a, grid, smem);
+      case 8: return kb_predict_warp_launch_v<MASK, 8, 2>(st, a, grid, smem);
+      default: break;
+    }
+  }
+  return kb_predict_warp_launch_v<MASK, 0, 2>(st, a, grid, smem);
 }
 
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {

@@ -122,7 +122,9 @@ def test_population_larger_than_chain_workers(lib):
 
 @pytest.mark.parametrize("n,d,kernel", [(100, 3, "matern52"), (128, 2, "gaussian"), (65, 5, "exponential"),
                                         (129, 2, "gaussian"), (40, 2, "gaussian"), (64, 3, "matern32"),
-                                        (24, 8, "gaussian"), (30, 9, "gaussian"), (7, 1, "exponential")])
+                                        (24, 8, "gaussian"), (30, 9, "gaussian"), (7, 1, "exponential"),
+                                        (48, 4, "matern52"), (33, 5, "gaussian"), (56, 2, "matern32"),
+                                        (50, 6, "exponential"), (16, 7, "matern52")])
 def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
     """The three predictor variants around their switch-over points: warp-autonomous (n <= 64, d <= 8;
     two CTAs/SM up to n = 40, one above), shared-memory resident (n_pad <= 128) and streaming
