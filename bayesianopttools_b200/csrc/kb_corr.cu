@@ -407,7 +407,7 @@ kb_build_aug_kpls_kernel(KbModelDev m, KbAugGeom g, int B, int h, KbHyper hp, co
           s0 = fma(dv[k].x, sgk[bb][k], s0);
           s1 = fma(dv[k].y, sgk[bb][k], s1);
         }
-        double2 v = make_double2(exp(-s0), exp(-s1));
+        double2 v = make_double2(kb_exp_nonpos(-s0), kb_exp_nonpos(-s1));
         if (row == col) v.x += seps[bb];
         if (row == col + 1) v.y += seps[bb];
         if (!inside) {

@@ -301,9 +301,12 @@ kb_predict_kernel(KbPredictArgs P) {
           kb_pair_dim(acc[3], x - xb.y, gw, ith, MASK);
         }
         const int k0 = t * PK_TK + kg * 4;
+        double vals[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vals[i] = kb_pair_finish(acc[i], sm.wk, MASK);   // four interleaved exp chains
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          double val = kb_pair_finish(acc[i], sm.wk, MASK);
+          double val = vals[i];
           if (k0 + i >= n) val = 0.0;
           if (qin) {
 #pragma unroll
@@ -651,20 +654,36 @@ kb_predict_warp_kernel(KbPredictArgs P) {
     }
     // ---- psi column of this site; psi' alpha and 1' R^-1 psi on the way --------
     double ex0 = 0.0, ex1 = 0.0;
-#pragma unroll U
-    for (int k = 0; k < n8; ++k) {
-      KbPairAcc acc;
-      kb_pair_init(acc);
+    // U training sites per pass (n8 is a multiple of 8, U of 2 or 4): all shared-memory reads first, then the U
+    // independent correlation chains (branch-free exp: the compiler interleaves them), then the stores
+    for (int k = 0; k < n8; k += U) {
+      KbPairAcc acc[U];
+      double e0[U], e1[U], val[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        kb_pair_init(acc[u]);
+        e0[u] = exts[k + u];
+        e1[u] = exts[n8 + k + u];
+      }
 #pragma unroll
       for (int dim = 0; dim < DD; ++dim) {
-        if (D) kb_pair_dim(acc, xv[dim] - XTs[dim * n8 + k], rgw[dim], rith[dim], MASK);
-        else if (dim < d) kb_pair_dim(acc, xv[dim] - XTs[dim * n8 + k], sgw[dim], sith[dim], MASK);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (D) kb_pair_dim(acc[u], xv[dim] - XTs[dim * n8 + k + u], rgw[dim], rith[dim], MASK);
+          else if (dim < d) kb_pair_dim(acc[u], xv[dim] - XTs[dim * n8 + k + u], sgw[dim], sith[dim], MASK);
+        }
       }
-      double val = kb_pair_finish(acc, swk, MASK);
-      if (k >= n) val = 0.0;
-      ex0 = fma(val, exts[k], ex0);
-      ex1 = fma(val, exts[n8 + k], ex1);
-      psiW[k][lane] = val;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        val[u] = kb_pair_finish(acc[u], swk, MASK);
+        if (k + u >= n) val[u] = 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ex0 = fma(val[u], e0[u], ex0);
+        ex1 = fma(val[u], e1[u], ex1);
+        psiW[k + u][lane] = val[u];
+      }
     }
     __syncwarp();
     // ---- v = L^-1 psi for the 32 sites, keep the column sums of squares --------
