@@ -60,6 +60,30 @@ def test_calckernel_ragged_shapes(lib):
             assert relerr(lib.corr_matrix(XN, XM, th, k), ko.corr(XN, XM, th, k)) < 1e-13
 
 
+def test_correlation_exp_over_its_whole_range(lib):
+    """The kernels evaluate exp through a branch-free routine for non-positive arguments (kb_common.cuh): every
+    result down to exp(-708) = 3.3e-308 must agree with numpy's exp to the last bits (pointwise, not
+    scale-relative), anything smaller may come back as 0, and a NaN coordinate stays NaN."""
+    # 1-D exponential kernel with theta = 1: the correlation is exp(-|x - x'|) exactly
+    arg = np.concatenate([np.linspace(0.0, 40.0, 4001), np.linspace(40.0, 700.0, 3301), np.linspace(700.0, 760.0, 2401)])
+    XN, XM = np.zeros((1, 1)), arg.reshape(-1, 1)
+    got = lib.corr_matrix(XN, XM, np.ones(1), "exponential").ravel()
+    want = np.exp(-arg)
+    normal = arg <= 708.0
+    assert np.max(np.abs(got[normal] - want[normal]) / want[normal]) < 5e-16
+    assert np.all((got[~normal] == 0.0) | (np.abs(got[~normal] - want[~normal]) <= 5e-324 + 1e-15 * want[~normal]))
+    assert np.all(got[arg > 746.0] == 0.0)
+    # Gaussian: exp(-d^2 / (2 theta^2)) with theta = 0.5
+    x = np.linspace(0.0, 19.0, 3001)
+    got = lib.corr_matrix(np.zeros((1, 1)), x.reshape(-1, 1), 0.5 * np.ones(1), "gaussian").ravel()
+    want = np.exp(-2.0 * x * x)
+    normal = 2.0 * x * x <= 708.0
+    assert np.all(np.abs(got[normal] - want[normal]) / want[normal] < 5e-16 + 2.3e-16 * 2.0 * x[normal] ** 2)
+    XM2 = np.array([[1.0], [np.nan], [2.0]])
+    got = lib.corr_matrix(np.zeros((1, 1)), XM2, np.ones(1), "gaussian").ravel()
+    assert np.isnan(got[1]) and np.isfinite(got[0]) and np.isfinite(got[2])
+
+
 @pytest.mark.parametrize("name", RANDOM_CASES)
 def test_nll_population_matches_reference(lib, name):
     g = load_golden(name)
