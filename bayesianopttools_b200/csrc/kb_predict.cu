@@ -569,13 +569,24 @@ kb_predict_kernel(KbPredictArgs P) {
 #define PW_LDP 36          // padded psi row: 32 sites + 4 (== 4 mod 16 -> conflict-free B fragments)
 #define PW_MAXD 8
 
+// Up to 64 training sites: 8 warps per CTA, L^-1 as a full k-major matrix, two CTAs per SM.  65 .. 128 sites:
+// 4 warps per CTA (one per SM sub-partition), L^-1 packed as its lower 8x8 blocks, one CTA per SM -- the psi
+// tiles of the warps (n8 x 36 doubles each) are what fills the shared memory.
+static int kb_predict_warp_nw(int n8) { return n8 <= 64 ? 8 : 4; }
+static size_t kb_predict_warp_at_doubles(int n8) {
+  const int nrb = n8 >> 3;
+  return n8 <= 64 ? (size_t)n8 * (n8 + 4) : (size_t)(nrb * (nrb + 1) / 2) * 64;
+}
 size_t kb_predict_warp_smem_bytes(int d, int n8, int qx) {
-  return sizeof(double) * ((size_t)d * n8 + 2 * (size_t)d + (size_t)qx * n8 + (size_t)n8 * (n8 + 4) +
-                           8 * (size_t)n8 * PW_LDP + 8 * 32) + sizeof(KbSweepResult) * 8 + 64;
+  const int nw = kb_predict_warp_nw(n8);
+  return sizeof(double) * ((size_t)d * n8 + 2 * (size_t)d + (size_t)qx * n8 + kb_predict_warp_at_doubles(n8) +
+                           nw * (size_t)n8 * PW_LDP + 8 * 32) + sizeof(KbSweepResult) * 8 + 64;
 }
 bool kb_predict_can_warp(int d, int n, int qx, int nind_trend) {
   const int n8 = (n + 7) & ~7;
-  return n8 <= 64 && d <= PW_MAXD && nind_trend == 0 && qx == 2 &&
+  static const char* big_env = getenv("KB_PW_BIG");       // debug aid: KB_PW_BIG=0 keeps n > 64 on the CTA kernel
+  const int nmax = (big_env && atoi(big_env) == 0) ? 64 : 128;
+  return n8 <= nmax && d <= PW_MAXD && nind_trend == 0 && qx == 2 &&
          kb_predict_warp_smem_bytes(d, n8, qx) + 1024 <= 227 * 1024;
 }
 int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
@@ -585,9 +596,11 @@ int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
 // D > 0: the design has exactly D columns (compile-time: the per-dimension weights live in registers, no
 // predicated dimension loop); D = 0: any d <= PW_MAXD.  U = correlation chains in flight per lane.
 // The triangular product takes the 8-row blocks in pairs (6 fragment loads per 8 DMMA instead of 10).
-template <int MASK, int D, int U>
-__global__ void __launch_bounds__(256, 2)
+template <int MASK, int D, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
 kb_predict_warp_kernel(KbPredictArgs P) {
+  constexpr bool PACKED = (NW != 8);       // L^-1 as lower 8x8 blocks [rb (rb + 1) / 2 + kb][k % 8][row % 8]
+  constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int DD = D ? D : PW_MAXD;
   const int n = P.n, d = D ? D : P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
@@ -597,27 +610,37 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   double* sgw = XTs + (size_t)d * n8;       // [d]
   double* sith = sgw + d;                   // [d]
   double* exts = sith + d;                  // [2][n8]  alpha | R^-1 1
-  double* ATs = exts + 2 * (size_t)n8;      // [n8][n8 + 4]  k-major L^-1
-  double* psiAll = ATs + (size_t)n8 * lda;  // [8 warps][n8][PW_LDP]
-  double* vvAll = psiAll + 8 * (size_t)n8 * PW_LDP;   // [8 warps][32]
+  double* ATs = exts + 2 * (size_t)n8;      // [n8][n8 + 4]  k-major L^-1, or its packed lower blocks
+  double* psiAll = ATs + (PACKED ? (size_t)((n8 >> 3) * ((n8 >> 3) + 1) / 2) * 64 : (size_t)n8 * lda);  // [NW][n8][PW_LDP]
+  double* vvAll = psiAll + NW * (size_t)n8 * PW_LDP;   // [NW warps][32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
 
-  for (int e = tid; e < d * n8; e += 256) {
+  for (int e = tid; e < d * n8; e += NTH) {
     const int dim = e / n8, k = e - dim * n8;
     XTs[e] = (k < n) ? P.XT[(size_t)dim * P.n_pad + k] : 0.0;
   }
-  for (int e = tid; e < d; e += 256) { sgw[e] = P.gw[e]; sith[e] = P.ith[e]; }
+  for (int e = tid; e < d; e += NTH) { sgw[e] = P.gw[e]; sith[e] = P.ith[e]; }
   if (tid < 4) swk[tid] = P.wk[tid];
-  for (int e = tid; e < 2 * n8; e += 256) {
+  for (int e = tid; e < 2 * n8; e += NTH) {
     const int j = e / n8, k = e - j * n8;
     exts[e] = (k < n) ? P.AT[(size_t)k * P.ldat + P.n_pad + j] : 0.0;
   }
-  for (int e = tid; e < n8 * n8; e += 256) {
+  for (int e = tid; e < n8 * n8; e += NTH) {
     const int k = e / n8, i = e - k * n8;
-    ATs[(size_t)k * lda + i] = P.AT[(size_t)k * P.ldat + i];
+    if (PACKED) {
+      const int rbk = i >> 3, kbk = k >> 3;
+      if (kbk <= rbk) ATs[(size_t)(rbk * (rbk + 1) / 2 + kbk) * 64 + (k & 7) * 8 + (i & 7)] = P.AT[(size_t)k * P.ldat + i];
+    } else {
+      ATs[(size_t)k * lda + i] = P.AT[(size_t)k * P.ldat + i];
+    }
   }
   __syncthreads();
+  // A fragment of 8-row block rb at k-step ks (rows rb*8 + gq, k = ks*4 + tq)
+  auto a_frag = [&](int rb, int ks) -> double {
+    return PACKED ? ATs[(size_t)(rb * (rb + 1) / 2 + (ks >> 1)) * 64 + ((ks & 1) * 4 + tq) * 8 + gq]
+                  : ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + gq];
+  };
 
   double (*psiW)[PW_LDP] = reinterpret_cast<double (*)[PW_LDP]>(psiAll + (size_t)warp * n8 * PW_LDP);
   double* vvW = vvAll + warp * 32;
@@ -633,7 +656,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   }
 
   const long long ngroups = (P.m + 31) / 32;
-  for (long long grp = (long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (long long)gridDim.x * 8) {
+  for (long long grp = (long long)blockIdx.x * NW + warp; grp < ngroups; grp += (long long)gridDim.x * NW) {
     const long long site = grp * 32 + lane;
     const bool valid = site < P.m;
     // ---- this lane's site, standardised ------------------------------------
@@ -701,8 +724,8 @@ kb_predict_warp_kernel(KbPredictArgs P) {
           for (int cb = 0; cb < 4; ++cb) acc[h][cb][0] = acc[h][cb][1] = 0.0;
         const int kmax = 2 * (rb + 1);               // block rb needs k < 8 (rb + 1), block rb + 1 eight more
         for (int ks = 0; ks < kmax; ++ks) {
-          const double a0 = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + gq];
-          const double a1 = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + 8 + gq];
+          const double a0 = a_frag(rb, ks);
+          const double a1 = a_frag(rb + 1, ks);
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             const double bf = psiW[ks * 4 + tq][cb * 8 + gq];
@@ -712,7 +735,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
         }
 #pragma unroll
         for (int ks = kmax; ks < kmax + 2; ++ks) {
-          const double a1 = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + 8 + gq];
+          const double a1 = a_frag(rb + 1, ks);
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[1][cb][0], acc[1][cb][1], a1, psiW[ks * 4 + tq][cb * 8 + gq]);
         }
@@ -731,7 +754,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
       for (int cb = 0; cb < 4; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
       const int kmax = 2 * (rb + 1);
       for (int ks = 0; ks < kmax; ++ks) {
-        const double af = ATs[(size_t)(ks * 4 + tq) * lda + rb * 8 + gq];
+        const double af = a_frag(rb, ks);
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
       }
@@ -766,7 +789,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   __syncthreads();
   if (tid == 0) {
     KbSweepResult r = red[0];
-    for (int w = 1; w < 8; ++w) kb_result_merge(r, red[w]);
+    for (int w = 1; w < NW; ++w) kb_result_merge(r, red[w]);
     P.partials[blockIdx.x] = r;
   }
 }
@@ -813,13 +836,18 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
     default: { constexpr int M_ = 15; CALL; } break;                     \
   }
 
+template <int MASK, int D, int U, int NW>
+static cudaError_t kb_predict_warp_launch_w(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U, NW>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kb_predict_warp_kernel<MASK, D, U, NW><<<grid, NW * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
 template <int MASK, int D, int U>
 static cudaError_t kb_predict_warp_launch_v(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return e;
-  kb_predict_warp_kernel<MASK, D, U><<<grid, 256, smem, st>>>(a);
-  return cudaGetLastError();
+  if (((a.n + 7) & ~7) <= 64) return kb_predict_warp_launch_w<MASK, D, U, 8>(st, a, grid, smem);
+  return kb_predict_warp_launch_w<MASK, D, U, 4>(st, a, grid, smem);
 }
 // The kernel is compiled for every design width it serves (1 .. PW_MAXD; the reliability problems AK-MCS
 // sweeps are 2-D); KB_PW_D=0 forces the runtime-d variant (debug aid).
