@@ -124,7 +124,9 @@ def test_population_larger_than_chain_workers(lib):
                                         (129, 2, "gaussian"), (40, 2, "gaussian"), (64, 3, "matern32"),
                                         (24, 8, "gaussian"), (30, 9, "gaussian"), (7, 1, "exponential"),
                                         (48, 4, "matern52"), (33, 5, "gaussian"), (56, 2, "matern32"),
-                                        (50, 6, "exponential"), (16, 7, "matern52")])
+                                        (50, 6, "exponential"), (16, 7, "matern52"),
+                                        (120, 2, "gaussian"), (72, 8, "exponential"), (96, 4, "matern32"),
+                                        (128, 1, "matern52"), (104, 7, "gaussian")])
 def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
     """The three predictor variants around their switch-over points: warp-autonomous (n <= 64, d <= 8;
     two CTAs/SM up to n = 40, one above), shared-memory resident (n_pad <= 128) and streaming
