@@ -154,10 +154,23 @@ def run_multi_opt(kriglist, moboInfo, ypar, krigconstlist=None, cheapconstlist=N
             I = int(np.argmin(f))
             xnext, fnext = cand[I].copy(), float(f[I])
         else:
-            cand = sweep_candidates(kriglist[0], moboInfo.get("ncandidates", 1_000_000), moboInfo.get("rng"),
-                                    moboInfo.get("sweep_sampler", "sobol"), moboInfo.get("seed"))
+            # moboInfo["shard_candidates"]: as in run_single_opt, every rank scores its share of the same set
+            ncand = int(moboInfo.get("ncandidates", 1_000_000))
+            rank, size = parallel.world() if moboInfo.get("shard_candidates", False) else (0, 1)
+            lo, hi = parallel.point_shard(ncand, rank, size)
+            cand = sweep_candidates(kriglist[0], ncand, moboInfo.get("rng"), moboInfo.get("sweep_sampler", "sobol"),
+                                    moboInfo.get("seed"), span=(lo, hi) if size > 1 else None)
             I, val = ehvi_best(cand, ypar, moboInfo, kriglist)
-            xnext, fnext = np.array(cand[I], dtype=float), -val
+            if size > 1:
+                rec = dict(best_val=-float(val), best_idx=int(I) + lo, min_u=np.inf, min_u_idx=0, n_fail=0,
+                           n_fail_minus=0, n_fail_plus=0, n_points=hi - lo)
+                rec = parallel.gather_sweep_result(rec)
+                counts = [b - a for a, b in (parallel.point_shard(ncand, r, size) for r in range(size))]
+                owner, local = parallel.owner_of(rec["best_idx"], counts)
+                xnext = parallel.broadcast_row(cand[local] if owner == rank else None, owner, nvar)
+                fnext = rec["best_val"]
+            else:
+                xnext, fnext = np.array(cand[I], dtype=float), -val
         if moboInfo.get("sweep_polish", True):
             r = minimize(fun, xnext, method="L-BFGS-B", bounds=np.column_stack((lbv, ubv)), args=args)
             if r.fun < fnext:

@@ -201,6 +201,46 @@ def _sweep_worker(rank, size, port, q):
         dist.destroy_process_group()
 
 
+def _mobo_sweep_worker(rank, size, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from bayesianopttools_b200.optim_tools import acquifunc_opt as ao
+
+        def fake_ehvi_best(cand, ypar, moboInfo, kriglist):        # stands in for the device EHVI arg-max
+            v = np.cos(3 * cand[:, 0]) * np.sin(2 * cand[:, 1]) + 1.5
+            i = int(np.argmax(v))
+            return i, float(v[i])
+        ao.ehvi_best = fake_ehvi_best
+        X0 = np.zeros((3, 2))
+        krig = _FakeKrig(X0, np.zeros(3))
+        krig.KrigInfo.update(lb=-3 * np.ones(2), ub=3 * np.ones(2))
+        info = dict(acquifuncopt="sweep", acquifunc="ehvi", nrestart=1, ncandidates=1001, sweep_polish=False,
+                    refpoint=np.array([1.0, 1.0]))
+        ypar = np.array([[0.0, 1.0], [1.0, 0.0]])
+        x1, f1 = ao.run_multi_opt([krig, krig], dict(info, rng=np.random.default_rng(4)), ypar)
+        x2, f2 = ao.run_multi_opt([krig, krig], dict(info, rng=np.random.default_rng(4), shard_candidates=True), ypar)
+        assert np.array_equal(x1, x2) and f1 == f2, (x1, x2, f1, f2)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mobo_sweep_sharded_over_two_ranks_equals_one_rank():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mobo_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(out) == [(0, "ok"), (1, "ok")], out
+
+
 def test_sobo_sweep_sharded_over_two_ranks_equals_one_rank():
     """run_single_opt(acquifuncopt='sweep', shard_candidates=True): 777 candidates split 389 + 388, the merged
     winner and its coordinates equal the unsharded sweep on every rank."""
@@ -237,3 +277,19 @@ def test_shards_cover_everything():
     for B, size in ((64, 8), (7, 2), (3, 4)):
         idx = np.sort(np.concatenate([parallel.candidate_slice(B, r, size) for r in range(size)]))
         assert np.array_equal(idx, np.arange(B))
+
+
+def test_owner_lookup_and_single_rank_helpers():
+    counts = [5, 0, 3, 4]
+    assert [parallel.owner_of(i, counts) for i in (0, 4, 5, 7, 8, 11)] == [(0, 0), (0, 4), (2, 0), (2, 2), (3, 0), (3, 3)]
+    try:
+        parallel.owner_of(12, counts)
+        raise AssertionError("expected IndexError")
+    except IndexError:
+        pass
+    # without an initialised process group every helper degenerates to the local answer
+    assert parallel.world() == (0, 1)
+    assert parallel.gather_counts(17) == [17]
+    assert np.array_equal(parallel.broadcast_row([1.5, -2.0], 0, 2), np.array([1.5, -2.0]))
+    full, best = parallel.gather_population_nll([3.0, 1.0, 1.0], 3)
+    assert best == 1 and np.array_equal(full, [3.0, 1.0, 1.0])
