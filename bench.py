@@ -118,7 +118,7 @@ def run_reference(args):
                                        "of likelihood_func.py; sweep sample %d points" % (sample_nll, sample_pred)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "sweep": {"value": p, "unit": "points/s"}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -335,14 +335,30 @@ def run_gpu(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "not_pd_candidates": int(np.count_nonzero(info0)), "best_nll": best_nll,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     mdl.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries write to stdout behind Python's back (NCCL prints its version banner there when the communicator
+    # comes up): file descriptor 1 is pointed at stderr for the whole run and only emit() uses the real stdout.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
