@@ -567,26 +567,28 @@ kb_predict_kernel(KbPredictArgs P) {
 // finishes its sites, all with __syncwarp only.
 // ---------------------------------------------------------------------------
 #define PW_LDP 36          // padded psi row: 32 sites + 4 (== 4 mod 16 -> conflict-free B fragments)
-#define PW_MAXD 8
+#define PW_MAXD 8           // widest design of the 8-warp kernel (128 registers per thread)
+#define PW_MAXD_WIDE 16     // ... of the 4-warp kernel (255 registers per thread): runtime-d loop
 
 // Up to 64 training sites: 8 warps per CTA, L^-1 as a full k-major matrix, two CTAs per SM.  65 .. 128 sites:
 // 4 warps per CTA (one per SM sub-partition), L^-1 packed as its lower 8x8 blocks, one CTA per SM -- the psi
 // tiles of the warps (n8 x 36 doubles each) are what fills the shared memory.
-static int kb_predict_warp_nw(int n8) { return n8 <= 64 ? 8 : 4; }
-static size_t kb_predict_warp_at_doubles(int n8) {
+static int kb_predict_warp_nw(int n8, int d) { return (n8 <= 64 && d <= PW_MAXD) ? 8 : 4; }
+static size_t kb_predict_warp_at_doubles(int n8, int nw) {
   const int nrb = n8 >> 3;
-  return n8 <= 64 ? (size_t)n8 * (n8 + 4) : (size_t)(nrb * (nrb + 1) / 2) * 64;
+  return nw == 8 ? (size_t)n8 * (n8 + 4) : (size_t)(nrb * (nrb + 1) / 2) * 64;
 }
 size_t kb_predict_warp_smem_bytes(int d, int n8, int qx) {
-  const int nw = kb_predict_warp_nw(n8);
-  return sizeof(double) * ((size_t)d * n8 + 2 * (size_t)d + (size_t)qx * n8 + kb_predict_warp_at_doubles(n8) +
+  const int nw = kb_predict_warp_nw(n8, d);
+  return sizeof(double) * ((size_t)d * n8 + 2 * (size_t)d + (size_t)qx * n8 + kb_predict_warp_at_doubles(n8, nw) +
                            nw * (size_t)n8 * PW_LDP + 8 * 32) + sizeof(KbSweepResult) * 8 + 64;
 }
 bool kb_predict_can_warp(int d, int n, int qx, int nind_trend) {
   const int n8 = (n + 7) & ~7;
   static const char* big_env = getenv("KB_PW_BIG");       // debug aid: KB_PW_BIG=0 keeps n > 64 on the CTA kernel
   const int nmax = (big_env && atoi(big_env) == 0) ? 64 : 128;
-  return n8 <= nmax && d <= PW_MAXD && nind_trend == 0 && qx == 2 &&
+  const int dmax = (big_env && atoi(big_env) == 0) ? PW_MAXD : PW_MAXD_WIDE;
+  return n8 <= nmax && d <= dmax && nind_trend == 0 && qx == 2 &&
          kb_predict_warp_smem_bytes(d, n8, qx) + 1024 <= 227 * 1024;
 }
 int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
@@ -602,7 +604,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   constexpr bool PACKED = (NW != 8);       // L^-1 as lower 8x8 blocks [rb (rb + 1) / 2 + kb][k % 8][row % 8]
   constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int DD = D ? D : PW_MAXD;
+  constexpr int DD = D ? D : (NW == 8 ? PW_MAXD : PW_MAXD_WIDE);
   const int n = P.n, d = D ? D : P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
   KbSweepResult* red = reinterpret_cast<KbSweepResult*>(smem_raw);
   double* swk = reinterpret_cast<double*>(smem_raw + sizeof(KbSweepResult) * 8);   // [4] (+4 pad)
@@ -846,7 +848,7 @@ static cudaError_t kb_predict_warp_launch_w(cudaStream_t st, const KbPredictArgs
 }
 template <int MASK, int D, int U>
 static cudaError_t kb_predict_warp_launch_v(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  if (((a.n + 7) & ~7) <= 64) return kb_predict_warp_launch_w<MASK, D, U, 8>(st, a, grid, smem);
+  if (((a.n + 7) & ~7) <= 64 && a.d <= PW_MAXD) return kb_predict_warp_launch_w<MASK, D, U, 8>(st, a, grid, smem);
   // one warp per SM sub-partition: twice the correlation chains per lane (registers are plentiful at 128
   // threads; measured +3 % at d = 2, +17 % at d = 6)
   return kb_predict_warp_launch_w<MASK, D, 2 * U, 4>(st, a, grid, smem);

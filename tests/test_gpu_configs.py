@@ -126,7 +126,8 @@ def test_population_larger_than_chain_workers(lib):
                                         (48, 4, "matern52"), (33, 5, "gaussian"), (56, 2, "matern32"),
                                         (50, 6, "exponential"), (16, 7, "matern52"),
                                         (120, 2, "gaussian"), (72, 8, "exponential"), (96, 4, "matern32"),
-                                        (128, 1, "matern52"), (104, 7, "gaussian")])
+                                        (128, 1, "matern52"), (104, 7, "gaussian"),
+                                        (100, 12, "gaussian"), (64, 16, "matern32"), (128, 10, "exponential")])
 def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
     """The three predictor variants around their switch-over points: warp-autonomous (n <= 64, d <= 8;
     two CTAs/SM up to n = 40, one above), shared-memory resident (n_pad <= 128) and streaming
