@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libkrigb200.so")
+# KRIGB200_LIB: development aid, an A/B build of the same library (bayesianopttools_b200/build.py --variant=)
+LIB_PATH = os.environ.get("KRIGB200_LIB") or os.path.join(_HERE, "csrc", "libkrigb200.so")
 
 KERNEL_IDS = {"gaussian": 0, "iso_gaussian": 0, "exponential": 1, "matern32": 2, "matern52": 3}
 OUT_IDS = {"pred": 0, "ssqr": 1, "s": 2, "ei": 3, "poi": 4, "pof": 5, "lcb": 6, "ebe": 7, "u": 8,

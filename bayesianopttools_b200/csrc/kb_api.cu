@@ -42,6 +42,8 @@ struct KbPopWs {       // one augmented-matrix workspace (population or fit geom
   int* sync_words = nullptr;
   int4* tasks = nullptr;
   int ntasks = 0, tasks_B = 0;
+  size_t tasks_cap = 0;   // int4 entries the `tasks` carve holds (the worst case over every B <= B_cap)
+  unsigned long long gen = 0;   // changes whenever any device buffer of this workspace is re-allocated
   int* info = nullptr;
   KbHyper hp{};
   double *Mbuf = nullptr, *beta = nullptr, *sigma2 = nullptr, *nll = nullptr, *lndet = nullptr;
@@ -187,8 +189,7 @@ struct KbNllGraphCache {
   // gradient calls, a GA's population / offspring / mutants): a shape is captured on its third request
   struct Seen { int B = 0, nbhyp = 0, trainvar = 0, count = 0; double nugget = 0.0; unsigned long long stamp = 0; } seen[4];
   int miss_B = 0;                 // (non-zero once anything has been seen; cleared with the cache)
-  const void* ws_aug = nullptr;   // workspace buffers the cached graphs point into
-  const void* ws_xpop = nullptr;
+  unsigned long long ws_gen = 0;  // generation of the workspace the cached graphs were captured on
 };
 
 struct kb_model {
@@ -298,6 +299,16 @@ static bool use_small_kernel(const kb_model* m, const KbPopWs& w) {
          !(small_env && atoi(small_env) == 0);
 }
 
+static std::atomic<unsigned long long> g_ws_gen{0};
+
+// Copy from caller-owned (possibly pageable) host memory on the handle's stream and wait: the blocking
+// cudaMemcpy targets the legacy stream, which the handle's non-blocking stream does not order against.
+static cudaError_t h2d_sync(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
+
 static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   if (B <= w.B_cap) {
     // (one-tile designs never run the task queue: kb_small.cu)
@@ -305,27 +316,40 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
     if (w.tasks_B != B && !queue_unused) {
       std::vector<int4> tasks;
       kb_chol_build_tasks(w.g, B, 2 * m->num_sms, tasks);
-      CK(cudaMemcpyAsync(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, m->stream));
-      CK(cudaStreamSynchronize(m->stream));
+      if (tasks.size() > w.tasks_cap)
+        KB_FAIL(KB_ERR_STATE, "task queue of %zu entries exceeds the workspace carve of %zu (B=%d, B_cap=%d)",
+                tasks.size(), w.tasks_cap, B, w.B_cap);
+      CK(h2d_sync(m->stream, w.tasks, tasks.data(), tasks.size() * sizeof(int4)));
       w.ntasks = (int)tasks.size();
       w.tasks_B = B;
     }
     return KB_OK;
   }
   CK(cudaStreamSynchronize(m->stream));
+  // graphs captured on the old workspace carry its slab offsets: they die with it (the pooled allocator
+  // may hand the very same block back, so pointer identity proves nothing)
+  if (&w == &m->pop) drop_nll_graphs(m->nll_graphs);
   free_ws(w);
   w.g = make_geom(m->n, m->nind, fit_mode, true);
   const KbAugGeom& g = w.g;
   const int d = m->d, nind = m->nind;
   std::vector<int4> tasks;
   kb_chol_build_tasks(g, B, 2 * m->num_sms, tasks);
+  // The task count is NOT monotone in B (two tile rows share a task only while that leaves every CTA a task
+  // per column), so the carve is sized for the unpaired queue at B_cap, which bounds every B <= B_cap.
+  size_t tasks_cap = tasks.size();
+  {
+    std::vector<int4> worst;
+    kb_chol_build_tasks(g, B, 0x7fffffff, worst);
+    if (worst.size() > tasks_cap) tasks_cap = worst.size();
+  }
   // one slab, 256-byte aligned pieces
   size_t off = 0;
   auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_aug = carve(sizeof(double) * g.stride * B);
   const size_t o_dinv = carve(sizeof(double) * (size_t)B * g.nb * KB_TILE * KB_TILE);
   const size_t o_sync = carve(sizeof(int) * kb_chol_sync_words(g, B));
-  const size_t o_tasks = carve(tasks.size() * sizeof(int4));
+  const size_t o_tasks = carve(tasks_cap * sizeof(int4));
   const size_t o_info = carve(sizeof(int) * B);
   const size_t o_gw = carve(sizeof(double) * (size_t)B * d);
   const size_t o_ith = carve(sizeof(double) * (size_t)B * d);
@@ -358,10 +382,12 @@ static kb_status ensure_ws(kb_model* m, KbPopWs& w, int B, bool fit_mode) {
   w.sigma2 = reinterpret_cast<double*>(base + o_s2);
   w.nll = reinterpret_cast<double*>(base + o_nll);
   w.lndet = reinterpret_cast<double*>(base + o_lndet);
-  CK(cudaMemcpy(w.tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CK(h2d_sync(m->stream, w.tasks, tasks.data(), tasks.size() * sizeof(int4)));
   w.ntasks = (int)tasks.size();
   w.tasks_B = B;
+  w.tasks_cap = tasks_cap;
   w.B_cap = B;
+  w.gen = ++g_ws_gen;
   return KB_OK;
 }
 
@@ -371,6 +397,7 @@ static kb_status ensure_xpop(KbPopWs& w, int count) {
   w.xpop = nullptr;
   CK(kb_dev_malloc(&w.xpop, sizeof(double) * count));
   w.xpop_cap = count;
+  w.gen = ++g_ws_gen;
   return KB_OK;
 }
 
@@ -468,6 +495,10 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
   if (cc_major != 10)
     KB_FAIL(KB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, cc_major, cc_minor);
   kb_model* m = new kb_model();
+  struct Guard {               // any failure below releases the handle, its stream and its device memory
+    kb_model* m;
+    ~Guard() { if (m) kb_model_destroy(m); }
+  } guard{m};
   m->device = device;
   m->num_sms = sm_count;
   m->n = n; m->d = d; m->nind = nind; m->nkernel = nkernel; m->model_type = model_type; m->h = h;
@@ -475,32 +506,30 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
   m->nb = m->n_pad / KB_TILE;
   m->kernel_ids.assign(kernel_ids, kernel_ids + nkernel);
   for (int k = 0; k < nkernel; ++k) {
-    if (kernel_ids[k] < 0 || kernel_ids[k] > 3) { delete m; KB_FAIL(KB_ERR_INVALID, "Kernel option not available!"); }
-    if (model_type == KB_TYPE_KPLS && kernel_ids[k] != KB_GAUSSIAN) {
-      delete m;
+    if (kernel_ids[k] < 0 || kernel_ids[k] > 3) KB_FAIL(KB_ERR_INVALID, "Kernel option not available!");
+    if (model_type == KB_TYPE_KPLS && kernel_ids[k] != KB_GAUSSIAN)
       KB_FAIL(KB_ERR_INVALID, "KPLS supports the gaussian kernel only (kernelfunc.py:43-49)");
-    }
     m->kmask |= 1 << kernel_ids[k];
   }
   CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
   double* Xtmp = nullptr;
   CK(kb_dev_malloc(&Xtmp, sizeof(double) * (size_t)n * d));
-  CK(cudaMemcpy(Xtmp, Xnorm, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice));
+  CK(h2d_sync(m->stream, Xtmp, Xnorm, sizeof(double) * (size_t)n * d));
   CK(kb_dev_malloc(&m->XT, sizeof(double) * (size_t)d * m->n_pad));
   CK(kb_launch_transpose_pad(m->stream, Xtmp, n, d, m->XT, m->n_pad));
   g_launches += 1;
   CK(cudaStreamSynchronize(m->stream));
   kb_dev_free(Xtmp);
   CK(kb_dev_malloc(&m->y, sizeof(double) * n));
-  CK(cudaMemcpy(m->y, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+  CK(h2d_sync(m->stream, m->y, y, sizeof(double) * n));
   CK(kb_dev_malloc(&m->F, sizeof(double) * (size_t)n * nind));
-  CK(cudaMemcpy(m->F, F, sizeof(double) * (size_t)n * nind, cudaMemcpyHostToDevice));
+  CK(h2d_sync(m->stream, m->F, F, sizeof(double) * (size_t)n * nind));
   CK(kb_dev_malloc(&m->kernel_ids_dev, sizeof(int) * nkernel));
-  CK(cudaMemcpy(m->kernel_ids_dev, kernel_ids, sizeof(int) * nkernel, cudaMemcpyHostToDevice));
+  CK(h2d_sync(m->stream, m->kernel_ids_dev, kernel_ids, sizeof(int) * nkernel));
   if (model_type == KB_TYPE_KPLS) {
     CK(kb_dev_malloc(&m->pls, sizeof(double) * (size_t)d * h));
-    CK(cudaMemcpy(m->pls, plscoeff, sizeof(double) * (size_t)d * h, cudaMemcpyHostToDevice));
+    CK(h2d_sync(m->stream, m->pls, plscoeff, sizeof(double) * (size_t)d * h));
   }
   if (model_type == KB_TYPE_KPLS && h <= KB_KPLS_MAX_H) {
     // kernelfunc.py:43-49: the per-component distance sums do not depend on theta -> once per design
@@ -512,6 +541,7 @@ kb_status kb_model_create(kb_model** out, int device, int n, int d, int nind, co
     CK(cudaStreamSynchronize(m->stream));
   }
   CK(kb_dev_malloc(&m->result_dev, sizeof(KbSweepResult)));
+  guard.m = nullptr;
   *out = m;
   return KB_OK;
 }
@@ -630,9 +660,9 @@ kb_status kb_nll_batch(kb_model* m, int B, int nbhyp, const double* xpop, int tr
   // (most of the gain is at launch-bound sizes, a few tile columns and small populations).
   static const char* graph_env = getenv("KB_NLL_GRAPH");            // debug aid: 0 disables
   KbNllGraphCache& GC = m->nll_graphs;
-  if (GC.ws_aug != m->pop.aug || GC.ws_xpop != m->pop.xpop) {      // the workspace was re-allocated
+  if (GC.ws_gen != m->pop.gen) {      // the workspace (or its candidate buffer) was re-allocated
     drop_nll_graphs(GC);
-    GC.ws_aug = m->pop.aug; GC.ws_xpop = m->pop.xpop;
+    GC.ws_gen = m->pop.gen;
   }
   // (measured: 82 -> 66 us at n=40, 216 -> 198 us at n=500 B=16, 1337 -> 1326 us at n=1000 B=64)
   const bool want_graph = !m->profile && m->stream == m->own_stream && !GC.disabled &&
@@ -738,7 +768,7 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
   const int n = m->n;
   if (!m->rt) {
     CK(kb_dev_malloc(&m->rt, sizeof(double) * g.n_pad));
-    CK(cudaMemset(m->rt, 0, sizeof(double) * g.n_pad));
+    CK(cudaMemsetAsync(m->rt, 0, sizeof(double) * g.n_pad, m->stream));
   }
   if (!m->AT) {
     m->nrows = round_up(g.n_pad + g.q, 128);
@@ -806,7 +836,7 @@ kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d) {
   m->maxorder = maxo;
   if (nind == 1 && maxo == 0) return KB_OK;   // ordinary Kriging: constant basis, fast path
   CK(kb_dev_malloc(&m->idx_dev, sizeof(int) * (size_t)nind * d));
-  CK(cudaMemcpy(m->idx_dev, idx, sizeof(int) * (size_t)nind * d, cudaMemcpyHostToDevice));
+  CK(h2d_sync(m->stream, m->idx_dev, idx, sizeof(int) * (size_t)nind * d));
   return KB_OK;
 }
 
@@ -818,8 +848,9 @@ kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const 
   if (norm_type == KB_NORM_NONE) return KB_OK;
   if (!m->p0) CK(kb_dev_malloc(&m->p0, sizeof(double) * m->d));
   if (!m->p1) CK(kb_dev_malloc(&m->p1, sizeof(double) * m->d));
-  CK(cudaMemcpy(m->p0, p0, sizeof(double) * m->d, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(m->p1, p1, sizeof(double) * m->d, cudaMemcpyHostToDevice));
+  CK(cudaStreamSynchronize(m->stream));          // a sweep in flight may still read the old vectors
+  CK(h2d_sync(m->stream, m->p0, p0, sizeof(double) * m->d));
+  CK(h2d_sync(m->stream, m->p1, p1, sizeof(double) * m->d));
   return KB_OK;
 }
 
@@ -1312,7 +1343,7 @@ static kb_status ehvi2d_core(kb_model* m1, kb_model* m2, long long npts, const d
         CK(kb_dev_malloc(&W.table, sizeof(double) * table.size()));
         W.cap_table = table.size();
       }
-      CK(cudaMemcpy(W.table, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+      CK(h2d_sync(m1->stream, W.table, table.data(), sizeof(double) * table.size()));
       W.key.swap(key);
     }
   }

@@ -52,6 +52,8 @@ struct KbCholSmem {
   int task;
   int ready;
   int misc[6];
+  int rf[8];          // chain worker: refinement flag of the last finished tile of each home candidate
+  int knext[8];       // chain worker: next step of each home candidate
 };
 static_assert(sizeof(double) * KB_RING_ROWS * KB_LDK >= sizeof(double) * (3 * KB_TILE * KB_LDC + KB_DIAG_SCRATCH),
               "three padded tiles and the exchange scratch must fit in the pipeline ring");
@@ -100,6 +102,152 @@ __device__ __forceinline__ void kb_tri_multiply(const double (*Cs)[KB_LDC], cons
   }
 }
 
+// The same product with the A operand read from global memory (through L2): X0 has just been stored to the
+// output tile by this CTA, and shared memory has no room for a fourth tile.  Rare path (see kb_refined_solve).
+template <int MI>
+__device__ __forceinline__ void kb_tri_multiply_g(const double* __restrict__ Xg, int ld, const double (*Ds)[KB_LDC],
+                                                  double (&acc)[4][4][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 4
+  for (int ks = 0; ks < KB_TILE / 4; ++ks) {
+    double af[MI];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) af[mi] = __ldcg(&Xg[(size_t)(wr * (8 * MI) + mi * 8 + gq) * ld + ks * 4 + tq]);
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      if (ks < 2 * (2 * ni + wc + 1)) {
+        const double bf = Ds[(2 * ni + wc) * 8 + gq][ks * 4 + tq];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) kb_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
+      }
+    }
+  }
+}
+
+// X = C L^-T with one step of residual correction,
+//     X0 = C W^T,   X1 = X0 + (C - X0 L^T) W^T          (W = the explicit inverse of the diagonal tile L),
+// for diagonal tiles whose pivots span orders of magnitude (flag planted in the stored inverse by the chain).  The plain product with the
+// explicit inverse leaves a residual of the order eps cond(L) |C|; on such tiles (the FIRST tile column of a
+// smooth-kernel design with a tiny nugget: pivots from 1 down to the nugget) that put the likelihood 3-30x
+// further from an 80-bit evaluation than LAPACK's triangular solve; with the correction it is as close as LAPACK
+// (tools/emulate_blocking.py, profiles/r02_emulate_blocking.txt).  Well-conditioned tiles -- every tile of the
+// reference's default nugget on space-filling designs -- take the single product.
+// On entry Cs holds C and Bs holds W; Wg / Lg are the global copies of W and L (L with row stride ldl); X0 goes
+// through the output tile Xg (row stride ld).  On exit Xg (and the shared tile Xs, when given; it may alias Cs)
+// holds X1; Cs and Bs are clobbered.  All 256 threads; out of line so that the common path keeps its registers.
+template <int MI>
+__device__ __noinline__ void kb_refined_solve(double (*Cs)[KB_LDC], double (*Bs)[KB_LDC], const double* Wg,
+                                              const double* Lg, int ldl, double* Xg, int ld, double (*Xs)[KB_LDC]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
+  double acc[4][4][2];
+  kb_tri_multiply<MI>(Cs, Bs, acc);
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int r = wr * (8 * MI) + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+      *reinterpret_cast<double2*>(&Xg[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    }
+  __syncthreads();
+  kb_load_tile_async(Bs, Lg, ldl);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+  kb_tri_multiply_g<MI>(Xg, ld, Bs, acc);
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int r = wr * (8 * MI) + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+      double2 v = *reinterpret_cast<double2*>(&Cs[r][c]);
+      v.x -= acc[mi][ni][0];
+      v.y -= acc[mi][ni][1];
+      *reinterpret_cast<double2*>(&Cs[r][c]) = v;
+    }
+  __syncthreads();
+  kb_load_tile_async(Bs, Wg, KB_TILE);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+  kb_tri_multiply<MI>(Cs, Bs, acc);
+  if (Xs) __syncthreads();                      // every warp is done reading Cs (== Xs) as an operand
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int r = wr * (8 * MI) + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+      const double2 x0 = __ldcg(reinterpret_cast<const double2*>(&Xg[(size_t)r * ld + c]));
+      const double2 x1 = make_double2(x0.x + acc[mi][ni][0], x0.y + acc[mi][ni][1]);
+      *reinterpret_cast<double2*>(&Xg[(size_t)r * ld + c]) = x1;
+      if (Xs) *reinterpret_cast<double2*>(&Xs[r][c]) = x1;
+    }
+}
+
+// The same for a 16-row strip of right-hand sides (THIN tasks): warp w owns column block w.
+__device__ __noinline__ void kb_refined_solve_thin(double (*Cs)[KB_LDC], double (*Bs)[KB_LDC], const double* Wg,
+                                                   const double* Lg, int ldl, double* Xg, int ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int kmax = 2 * (warp + 1);
+  double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int ks = 0; ks < kmax; ++ks) {
+    const double bf = Bs[warp * 8 + gq][ks * 4 + tq];
+    kb_dmma(o[0][0], o[0][1], Cs[gq][ks * 4 + tq], bf);
+    kb_dmma(o[1][0], o[1][1], Cs[8 + gq][ks * 4 + tq], bf);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+    *reinterpret_cast<double2*>(&Xg[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) = make_double2(o[mi][0], o[mi][1]);
+  __syncthreads();
+  kb_load_tile_async(Bs, Lg, ldl);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+  double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int ks = 0; ks < kmax; ++ks) {
+    const double bf = Bs[warp * 8 + gq][ks * 4 + tq];
+    kb_dmma(p[0][0], p[0][1], __ldcg(&Xg[(size_t)gq * ld + ks * 4 + tq]), bf);
+    kb_dmma(p[1][0], p[1][1], __ldcg(&Xg[(size_t)(8 + gq) * ld + ks * 4 + tq]), bf);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    double2 v = *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]);
+    v.x -= p[mi][0];
+    v.y -= p[mi][1];
+    *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]) = v;
+  }
+  __syncthreads();
+  kb_load_tile_async(Bs, Wg, KB_TILE);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+  double dl[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int ks = 0; ks < kmax; ++ks) {
+    const double bf = Bs[warp * 8 + gq][ks * 4 + tq];
+    kb_dmma(dl[0][0], dl[0][1], Cs[gq][ks * 4 + tq], bf);
+    kb_dmma(dl[1][0], dl[1][1], Cs[8 + gq][ks * 4 + tq], bf);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+    *reinterpret_cast<double2*>(&Xg[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
+        make_double2(o[mi][0] + dl[mi][0], o[mi][1] + dl[mi][1]);
+}
+
+// pivots of a diagonal tile spanning more than this ratio (as max L_ii / min L_ii) switch its column to
+// kb_refined_solve.  tools/emulate_blocking.py sweep: any threshold from 10 to 1000 selects the same tiles.
+#define KB_REFINE_RATIO 100.0
+#ifdef KB_NO_REFINE            // A/B build aid: compile the corrected solves out
+#define KB_REFINE_ON 0
+#else
+#define KB_REFINE_ON 1
+#endif
+
 struct KbCholArgs {
   KbAugGeom g;
   double* aug;
@@ -115,6 +263,7 @@ struct KbCholArgs {
   int chain_sms;      // SMs reserved for chain workers
   int chain_wps;      // chain workers per reserved SM (1 or 2)
   int* info;
+  int force_refine;   // debug aid KB_CHOL_REFINE: 1 = residual-corrected solves everywhere, -1 = nowhere (0: by pivot spread)
   unsigned long long* trace;
 };
 
@@ -122,7 +271,7 @@ struct KbCholArgs {
 // Chain worker: critical path of its home candidates, round robin, never blocks on a step
 // that is not ready.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& sm, int b, int k,
+__device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& sm, int b, int k, int slot,
                                               unsigned long long* stamps) {
   double* raw = &sm.ring[0][0];
   double (*C2)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw);
@@ -148,18 +297,24 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
   if (k > 0) {
     // L[k,k-1] = C1 Dinv_{k-1}^T  -> shared (in place) and global, published at once
     double acc[4][4][2];
-    kb_tri_multiply<2>(C1, Dk, acc);
-    __syncthreads();
     double* Tsub = Tkk - KB_TILE;
+    if (KB_REFINE_ON && sm.rf[slot] != 0) {              // set by this worker's previous step on the same candidate
+      // ill-conditioned diagonal tile k-1: residual-corrected solve (writes shared C1 and global Tsub)
+      kb_refined_solve<2>(C1, Dk, P.dinv + ((size_t)b * P.g.nb + (k - 1)) * (KB_TILE * KB_TILE),
+                          Tkk - (size_t)KB_TILE * ld - KB_TILE, ld, Tsub, ld, C1);
+    } else {
+      kb_tri_multiply<2>(C1, Dk, acc);
+      __syncthreads();
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+      for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int r = wr * 16 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
-        const double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        *reinterpret_cast<double2*>(&C1[r][c]) = v;
-        *reinterpret_cast<double2*>(&Tsub[(size_t)r * ld + c]) = v;
-      }
+        for (int ni = 0; ni < 4; ++ni) {
+          const int r = wr * 16 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+          const double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          *reinterpret_cast<double2*>(&C1[r][c]) = v;
+          *reinterpret_cast<double2*>(&Tsub[(size_t)r * ld + c]) = v;
+        }
+    }
     __syncthreads();
     if (tid == 0) {
       kb_flag_release(&fl[k], k);      // st.release.gpu: cumulative over the CTA barrier above
@@ -245,6 +400,42 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
     }
     __syncthreads();
     {
+      // one step of residual correction (as kb_refined_solve; always: 16 rows cost nothing):
+      //   r = Y - Z L^T  (rows 32..47 of Yb),   Z += r Linv^T
+      const int j = tid >> 4, i0 = tid & 15;
+      double rr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rr[u] = (i0 + 16 * u < nv) ? Yb[j][i0 + 16 * u] : 0.0;
+      for (int i = 0; i < nv; ++i) {
+        const double zi = Yb[16 + j][i];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = i0 + 16 * u;
+          if (i <= c && c < nv) rr[u] = fma(-zi, C2[c][i], rr[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Yb[32 + j][i0 + 16 * u] = rr[u];
+    }
+    __syncthreads();
+    {
+      const int j = tid >> 4, i0 = tid & 15;
+      double z[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) z[u] = Yb[16 + j][i0 + 16 * u];
+      for (int t = 0; t < nv; ++t) {
+        const double rt = Yb[32 + j][t];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 16 * u;
+          if (t <= i && i < nv) z[u] = fma(rt, Dk[i][t], z[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Yb[16 + j][i0 + 16 * u] = z[u];
+    }
+    __syncthreads();
+    {
       const int a = tid >> 4, c = tid & 15;
       if (c <= a && nv + a < KB_TILE) {
         double s0 = 0.0, s1 = 0.0;
@@ -264,6 +455,25 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
     __syncthreads();
   }
   if (stamps && tid == 0) stamps[6] = kb_globaltimer();
+  // pivot spread of this tile (its real rows only): beyond KB_REFINE_RATIO the panel solves of column k take the
+  // residual-corrected path.  Every lane of warp 0 ends up with the flag; lane 31 plants it in the stored inverse.
+  int rf_tile = 0;
+  if (warp == 0) {
+    const int nreal = (P.g.n - k * KB_TILE < KB_TILE) ? (P.g.n - k * KB_TILE) : KB_TILE;
+    double lo = __longlong_as_double(0x7ff0000000000000LL), hi = 0.0;
+    for (int i = lane; i < nreal; i += 32) {
+      const double v = C2[i][i];
+      lo = fmin(lo, v);
+      hi = fmax(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    rf_tile = (P.force_refine > 0 || (P.force_refine == 0 && hi > KB_REFINE_RATIO * lo)) ? 1 : 0;
+    if (lane == 0) sm.rf[slot] = rf_tile;      // this worker's next step on the same candidate reads it
+  }
   double* Dg = P.dinv + ((size_t)b * P.g.nb + k) * (KB_TILE * KB_TILE);
   for (int e = tid; e < KB_TILE * KB_TILE / 2; e += KB_THREADS) {
     const int r = e >> 5, c = (e & 31) * 2;
@@ -271,7 +481,11 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
     if (c > r) l.x = 0.0;
     if (c + 1 > r) l.y = 0.0;
     *reinterpret_cast<double2*>(&Tkk[(size_t)r * ld + c]) = l;
-    *reinterpret_cast<double2*>(&Dg[r * KB_TILE + c]) = *reinterpret_cast<double2*>(&Dk[r][c]);
+    double2 w = *reinterpret_cast<double2*>(&Dk[r][c]);
+    // element [0][63] of the stored inverse (above the diagonal: never an operand) carries the refinement flag
+    // of this tile to the bulk tasks, which stage the tile through shared memory anyway
+    if (r == 0 && c == KB_TILE - 2) w.y = (double)rf_tile;      // (thread 31: warp 0)
+    *reinterpret_cast<double2*>(&Dg[r * KB_TILE + c]) = w;
   }
   __syncthreads();
   if (tid == 0) kb_flag_release(&fl[k], k + 1);
@@ -280,20 +494,22 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
 __device__ __forceinline__ void kb_chain_worker(const KbCholArgs& P, KbCholSmem& sm, int wid, int nworkers) {
   const int tid = threadIdx.x;
   const int nb = P.g.nb;
-  // home candidates b = wid + j * nworkers; next step per candidate in shared memory (<= 6 kept)
+  // home candidates b = wid + j * nworkers (at most 8: the host sizes chain_sms for it); the next step of each
+  // lives in shared memory so that the round-robin loop stays ROLLED: one copy of the (large) step in the
+  // instruction stream instead of eight
   int nhome = 0;
   for (int b = wid; b < P.B; b += nworkers) ++nhome;
+  if (tid < 8) sm.knext[tid] = 0;
+  __syncthreads();
   int done = 0;
-  int knext[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) knext[j] = 0;
   while (done < nhome) {
     bool progressed = false;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       const int b = wid + j * nworkers;
-      if (b >= P.B || knext[j] >= nb) continue;
-      const int k = knext[j];
+      if (b >= P.B) break;
+      const int k = sm.knext[j];
+      if (k >= nb) continue;
       __syncthreads();
       if (tid == 0) sm.ready = (k <= 1) ? 1 : kb_flag_acquire(&P.pre[(size_t)b * nb + k]);
       __syncthreads();
@@ -301,20 +517,20 @@ __device__ __forceinline__ void kb_chain_worker(const KbCholArgs& P, KbCholSmem&
       unsigned long long tr0 = 0;
       if (P.trace && tid == 0) tr0 = kb_globaltimer();
       unsigned long long* trec = P.trace ? P.trace + ((size_t)P.ntasks + (size_t)b * nb + k) * 8 : nullptr;
-      kb_chain_step(P, sm, b, k, trec);
+      kb_chain_step(P, sm, b, k, j, trec);
       if (P.trace && tid == 0) {
         // chain record: start | tiles loaded | sub-diagonal tile published | factor start | end | meta | factor end
         trec[0] = tr0; trec[4] = kb_globaltimer();
         trec[5] = ((unsigned long long)b << 40) | ((unsigned long long)k << 24) | ((unsigned long long)k << 8) | 0;
         trec[7] = blockIdx.x;
       }
-      knext[j] = k + 1;
+      if (tid == 0) sm.knext[j] = k + 1;
+      __syncthreads();
       if (k + 1 == nb) ++done;
       progressed = true;
     }
     if (!progressed) __nanosleep(200);
   }
-  // more than 8 home candidates per worker never happens: the host sizes chain_sms for it
   if (tid == 0) atomicAdd(&P.ctl[2], nhome);
 }
 
@@ -469,7 +685,8 @@ __device__ __forceinline__ int kb_wait_rows(KbCholSmem& sm, const int* fa, const
 
 // wait for the chain's Dinv_k and start staging it behind the C tile(s); the copy overlaps the
 // read of the tile being updated.  kb_dinv_land() completes it.
-__device__ __forceinline__ void kb_dinv_issue(const KbCholArgs& P, double (*Ds)[KB_LDC], const int* flk, int b, int tkc) {
+__device__ __forceinline__ void kb_dinv_issue(const KbCholArgs& P, KbCholSmem& sm, double (*Ds)[KB_LDC], const int* flk,
+                                              int b, int tkc) {
   if (threadIdx.x == 0)
     while (kb_flag_acquire(flk) < tkc + 1) __nanosleep(64);
   __syncthreads();
@@ -606,28 +823,33 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
               make_double2(c0v[mi][0], c0v[mi][1]);
       } else {
         double (*Ds)[KB_LDC] = Cs + KB_TILE;
-        kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
+        kb_dinv_issue(P, sm, Ds, &fl[tkc], b, tkc);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
           *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]) = make_double2(c0v[mi][0], c0v[mi][1]);
         kb_dinv_land();
         if (P.trace && tid == 0) tr3 = kb_globaltimer();
-        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        const int kmax = 2 * (warp + 1);
-        for (int ks = 0; ks < kmax; ++ks) {
-          const double bf = Ds[warp * 8 + gq][ks * 4 + tq];
-          kb_dmma(o[0][0], o[0][1], Cs[gq][ks * 4 + tq], bf);
-          kb_dmma(o[1][0], o[1][1], Cs[8 + gq][ks * 4 + tq], bf);
-        }
+        if (KB_REFINE_ON && Ds[0][KB_TILE - 1] != 0.0) {
+          kb_refined_solve_thin(Cs, Ds, P.dinv + ((size_t)b * nb + tkc) * (KB_TILE * KB_TILE),
+                                A + (size_t)tkc * KB_TILE * ld + (size_t)tkc * KB_TILE, ld, Atile, ld);
+        } else {
+          double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          const int kmax = 2 * (warp + 1);
+          for (int ks = 0; ks < kmax; ++ks) {
+            const double bf = Ds[warp * 8 + gq][ks * 4 + tq];
+            kb_dmma(o[0][0], o[0][1], Cs[gq][ks * 4 + tq], bf);
+            kb_dmma(o[1][0], o[1][1], Cs[8 + gq][ks * 4 + tq], bf);
+          }
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-          *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
-              make_double2(o[mi][0], o[mi][1]);
+          for (int mi = 0; mi < 2; ++mi)
+            *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
+                make_double2(o[mi][0], o[mi][1]);
+        }
       }
     } else if (two) {
       // 128 x 64: C = A[i..i+1, k] - acc -> shared, one triangular multiply for both tile rows
       double (*Ds)[KB_LDC] = Cs + 2 * KB_TILE;
-      kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
+      kb_dinv_issue(P, sm, Ds, &fl[tkc], b, tkc);
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -638,14 +860,19 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
         }
       kb_dinv_land();
       if (P.trace && tid == 0) tr3 = kb_globaltimer();
-      kb_tri_multiply<4>(Cs, Ds, acc);
+      if (KB_REFINE_ON && Ds[0][KB_TILE - 1] != 0.0) {
+        kb_refined_solve<4>(Cs, Ds, P.dinv + ((size_t)b * nb + tkc) * (KB_TILE * KB_TILE),
+                            A + (size_t)tkc * KB_TILE * ld + (size_t)tkc * KB_TILE, ld, Atile, ld, nullptr);
+      } else {
+        kb_tri_multiply<4>(Cs, Ds, acc);
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int r = wr * 32 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
-          *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        }
+          for (int ni = 0; ni < 4; ++ni) {
+            const int r = wr * 32 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+            *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          }
+      }
     } else {
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
@@ -667,7 +894,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
       } else {
         // L[i,k] = C * inv(L[k,k])^T : wait for the chain, then one triangular 64^3 DMMA multiply
         double (*Ds)[KB_LDC] = Cs + KB_TILE;
-        kb_dinv_issue(P, Ds, &fl[tkc], b, tkc);
+        kb_dinv_issue(P, sm, Ds, &fl[tkc], b, tkc);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -677,14 +904,19 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
           }
         kb_dinv_land();
         if (P.trace && tid == 0) tr3 = kb_globaltimer();
-        kb_tri_multiply<2>(Cs, Ds, acc);
+        if (KB_REFINE_ON && Ds[0][KB_TILE - 1] != 0.0) {
+          kb_refined_solve<2>(Cs, Ds, P.dinv + ((size_t)b * nb + tkc) * (KB_TILE * KB_TILE),
+                              A + (size_t)tkc * KB_TILE * ld + (size_t)tkc * KB_TILE, ld, Atile, ld, nullptr);
+        } else {
+          kb_tri_multiply<2>(Cs, Ds, acc);
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+          for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            const int r = wr * 16 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
-            *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-          }
+            for (int ni = 0; ni < 4; ++ni) {
+              const int r = wr * 16 + mi * 8 + gq, c = (2 * ni + wc) * 8 + 2 * tq;
+              *reinterpret_cast<double2*>(&Atile[(size_t)r * ld + c]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+        }
       }
     }
     // ---- publish (st.release.gpu is cumulative over the CTA barrier) and, in parallel on another
@@ -767,6 +999,8 @@ cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* a
   P.prog = sync_words + KB_CHOL_CTL_WORDS;
   P.pre = P.prog + (size_t)B * g.NT;
   P.pre_a = P.pre + (size_t)B * g.nb;
+  static const char* refine_env = getenv("KB_CHOL_REFINE");       // debug aid: 1 everywhere, 0 nowhere
+  P.force_refine = refine_env ? (atoi(refine_env) > 0 ? 1 : -1) : 0;
   P.tasks = tasks; P.ntasks = ntasks; P.B = B; P.info = info;
   // chain SMs: up to 16; one worker per SM while that covers the population, else two; a
   // worker serves at most 8 candidates

@@ -13,6 +13,9 @@
 #ifndef KB_DIAG_STAMP
 #define KB_DIAG_STAMP(i)
 #endif
+// 16x16 diagonal blocks whose pivots span more than this ratio (as max L_jj / min L_jj) get the residual-corrected
+// panel product in phase 2 (same criterion as KB_REFINE_RATIO of the tile Cholesky, kb_chol.cu).
+#define KB_DIAG_REFINE_RATIO 100.0
 
 // 1/sqrt(p) to full FP64 accuracy with a 4-deep dependent chain: hardware approximation
 // (relative error ~2^-23) + one third-order step  y (1 + e/2 + 3e^2/8),  e = 1 - p y^2.
@@ -162,6 +165,18 @@ __device__ __forceinline__ void kb_diag_factor_inverse(double (*Cs)[KB_LDC], dou
     // ---- phase 2: panel rows (warps 0..nrb-1) and the finished inverse block row (next 2*jb warps)
     if (warp < nrb) {
       const int r0 = c0 + 16 + 8 * warp;
+      // pivot spread of the 16x16 block just factored (xch[0..15] = its unscaled pivots L_jj^2)
+#ifdef KB_DIAG_NO_REFINE                // A/B build aid
+      const bool refine = false;
+#else
+      double plo = xch[lane & 15], phi = plo;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        plo = fmin(plo, __shfl_xor_sync(0xffffffffu, plo, o));
+        phi = fmax(phi, __shfl_xor_sync(0xffffffffu, phi, o));
+      }
+      const bool refine = phi > (KB_DIAG_REFINE_RATIO * KB_DIAG_REFINE_RATIO) * plo;
+#endif
       double af[4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) af[ks] = Cs[r0 + gq][c0 + ks * 4 + tq];
@@ -170,6 +185,45 @@ __device__ __forceinline__ void kb_diag_factor_inverse(double (*Cs)[KB_LDC], dou
       for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int ni = 0; ni < 2; ++ni) kb_dmma(p[ni][0], p[ni][1], af[ks], Ds[c0 + ni * 8 + gq][c0 + ks * 4 + tq]);
+      if (refine) {
+        // The product with the explicit 16x16 inverse leaves a residual ~ eps cond(L_D) |A|: when the pivots of
+        // the block span orders of magnitude (smooth kernel, tiny nugget, first panel of the first tile) take
+        // one step of residual correction   P <- P + (A - P L_D^T) W_D^T   -- all inside the warp that owns the
+        // 8 rows.  Well-conditioned blocks never come here.
+        double rs[2][2];
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          const double2 a = *reinterpret_cast<const double2*>(&Cs[r0 + gq][c0 + ni * 8 + 2 * tq]);
+          rs[ni][0] = a.x;
+          rs[ni][1] = a.y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+          *reinterpret_cast<double2*>(&Cs[r0 + gq][c0 + ni * 8 + 2 * tq]) = make_double2(p[ni][0], p[ni][1]);
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double x = Cs[r0 + gq][c0 + ks * 4 + tq];
+#pragma unroll
+          for (int ni = 0; ni < 2; ++ni) {
+            const int kk = ks * 4 + tq, nn = ni * 8 + gq;             // B[k][n] = L_D[n][k], lower triangular
+            const double l = (kk <= nn) ? Cs[c0 + nn][c0 + kk] : 0.0;
+            kb_dmma(rs[ni][0], rs[ni][1], -x, l);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+          *reinterpret_cast<double2*>(&Cs[r0 + gq][c0 + ni * 8 + 2 * tq]) = make_double2(rs[ni][0], rs[ni][1]);
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double r = Cs[r0 + gq][c0 + ks * 4 + tq];
+#pragma unroll
+          for (int ni = 0; ni < 2; ++ni) kb_dmma(p[ni][0], p[ni][1], r, Ds[c0 + ni * 8 + gq][c0 + ks * 4 + tq]);
+        }
+      }
       __syncwarp();
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni)

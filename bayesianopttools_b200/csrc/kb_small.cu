@@ -141,6 +141,43 @@ kb_nll_small_kernel(KbModelDev m, KbAugGeom g, int nbhyp, const double* __restri
     for (int t = 0; t < 4; ++t) sm.Z[j][i0 + 16 * t] = s[t];
   }
   __syncthreads();
+  // one step of residual correction, as the tile Cholesky's kb_refined_solve (kb_chol.cu): the product with the
+  // explicit inverse alone leaves a residual ~ eps cond(L) |Y|.   r = Y - Z L^T (overwrites Y),   Z += r L^-T
+  {
+    const int j = tid >> 4, c0 = tid & 15;
+    double r[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) r[t] = sm.Y[j][c0 + 16 * t];
+    for (int i = 0; i < KB_TILE; ++i) {
+      const double zi = sm.Z[j][i];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int c = c0 + 16 * t;
+        if (i <= c) r[t] = fma(-zi, sm.C[c][i], r[t]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) sm.Y[j][c0 + 16 * t] = r[t];
+  }
+  __syncthreads();
+  {
+    const int j = tid >> 4, i0 = tid & 15;
+    double s[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s[t] = sm.Z[j][i0 + 16 * t];
+    for (int k = 0; k < KB_TILE; ++k) {
+      const double rk = sm.Y[j][k];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = i0 + 16 * t;
+        if (k <= i) s[t] = fma(rk, sm.D[i][k], s[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) sm.Z[j][i0 + 16 * t] = s[t];
+  }
+  __syncthreads();
   double* A = aug + (size_t)b * g.stride;
   const int ld = g.ld;
   {

@@ -10,12 +10,14 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayesianopttools_b200 import _lib
 from oracle import kriging_oracle as ko
+from oracle import longdouble_truth as lt
 
 ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 KERNELS = ["gaussian", "exponential", "matern32", "matern52"]
 worst = dict(nll=0.0, pred=0.0, ssqr=0.0)
-fails = 0
+fails = narb = 0
+arb = dict(nll=[], pred=[], ssqr=[])
 for case in range(ncases):
     n = int(rng.choice([rng.integers(2, 70), rng.integers(60, 140), rng.integers(120, 420), rng.integers(400, 900)]))
     d = int(rng.integers(1, 9))
@@ -67,18 +69,41 @@ for case in range(ncases):
                 bad_flags += 1
         mdl.close()
         worst["nll"] = max(worst["nll"], e_nll); worst["pred"] = max(worst["pred"], e_pred); worst["ssqr"] = max(worst["ssqr"], e_ssqr)
-        # 1e-9 is the parity bar on well-conditioned designs; candidates with cond(R) ~ 1e10 (nugget 1e-8, very
-        # smooth kernels) sit where LAPACK itself is 1e-9..1e-8 off a long-double evaluation
-        # (profiles/r01_accuracy_vs_longdouble.txt), so the sweep flags only differences beyond 1e-7
-        status = "ok" if (e_nll < 1e-7 and e_pred < 2e-8 and e_ssqr < 1e-6 and bad_flags == 0) else "FAIL"
-        if status == "ok" and e_nll >= 1e-9:
-            status = "ok(ill-conditioned)"
+        # 1e-9 is the parity bar.  Where the two FP64 paths differ by more (cond(R) ~ 1e10: nugget tuned down to 1e-8
+        # on smooth kernels), an 80-bit evaluation of the same formulas arbitrates: the GPU value passes when it is
+        # no further from it than 3x the LAPACK oracle's own distance (both are random rounding walks) or 1e-9.
+        status, extra = "ok", ""
+        if bad_flags:
+            status = "FAIL"
+        if e_nll >= 1e-9 and ok.any():
+            rel = np.where(ok, np.abs(nll - ref) / np.abs(ref), 0.0)
+            bw = int(np.argmax(rel))
+            t = lt.nll(xpop[bw], X, y, F, kernels=tuple(kern), trainvar=trainvar, fixed_nugget=-6.0)
+            eg, eo = abs(nll[bw] - t) / abs(t), abs(ref[bw] - t) / abs(t)
+            extra += f" | nll vs 80-bit: gpu {eg:.1e} lapack {eo:.1e}"
+            arb["nll"].append((eg, eo))
+            status = "FAIL" if eg > max(1e-9, 3 * eo) else ("ok(arbitrated)" if status == "ok" else status)
+        if (e_pred >= 1e-9 or e_ssqr >= 1e-9) and b is not None:
+            tf = lt.nll(xpop[b], X, y, F, kernels=tuple(kern), trainvar=trainvar, fixed_nugget=-6.0, full=True)
+            tp = lt.predict(xq, X, y, F, idx, tf, kernels=tuple(kern))
+            for k, e in (("pred", e_pred), ("ssqr", e_ssqr)):
+                sc = max(np.max(np.abs(tp[k])), 1e-300)
+                eg, eo = np.max(np.abs(outs[k] - tp[k])) / sc, np.max(np.abs(rp[k] - tp[k])) / sc
+                extra += f" | {k} vs 80-bit: gpu {eg:.1e} lapack {eo:.1e}"
+                arb[k].append((eg, eo))
+                if e >= 1e-9:
+                    status = "FAIL" if eg > max(1e-9, 3 * eo) else ("ok(arbitrated)" if status == "ok" else status)
         fails += status == "FAIL"
-        illc = globals().get("illc", 0) + (status == "ok(ill-conditioned)")
-        globals()["illc"] = illc
-        print(f"{status} {tag}: nll {e_nll:.1e} pred {e_pred:.1e} ssqr {e_ssqr:.1e} flags {bad_flags} notpd {int(np.sum(info != 0))}", flush=True)
+        narb += status == "ok(arbitrated)"
+        print(f"{status} {tag}: nll {e_nll:.1e} pred {e_pred:.1e} ssqr {e_ssqr:.1e} flags {bad_flags} notpd {int(np.sum(info != 0))}{extra}", flush=True)
     except Exception as ex:                      # noqa: BLE001
         fails += 1
         print(f"EXC {tag}: {type(ex).__name__}: {ex}", flush=True)
-print("worst:", worst, "ill-conditioned (1e-9 <= nll err < 1e-7):", globals().get("illc", 0), "failures:", fails)
+print("worst GPU-vs-LAPACK difference:", {k: f"{v:.1e}" for k, v in worst.items()}, "| cases beyond 1e-9 settled by the 80-bit evaluation:", narb,
+      "| failures:", fails)
+for k, v in arb.items():
+    if v:
+        a = np.array(v)
+        print(f"  {k}: {len(a)} arbitrated values; worst distance from the 80-bit value: gpu {a[:, 0].max():.1e}, lapack {a[:, 1].max():.1e}; "
+              f"gpu closer than lapack in {int(np.sum(a[:, 0] <= a[:, 1]))}")
 sys.exit(1 if fails else 0)
