@@ -17,6 +17,7 @@ OUT_IDS = {"pred": 0, "ssqr": 1, "s": 2, "ei": 3, "poi": 4, "pof": 5, "lcb": 6, 
            "fpc": 9}
 OUT_COUNT = 10
 NORM_DEFAULT, NORM_STD, NORM_NONE = 0, 1, 2
+YMAP_NONE, YMAP_DEFAULT, YMAP_STD = 0, 1, 2
 TYPE_KRIGING, TYPE_KPLS = 0, 1
 ERR_NOT_PD = 4
 
@@ -72,6 +73,7 @@ _SIGNATURES = [
                                c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("kb_model_set_trend", C.c_int, [C.c_void_p, c_int_p, C.c_int, C.c_int]),
     ("kb_model_set_norm", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    ("kb_model_set_ymap", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     ("kb_predict", C.c_int, [C.c_void_p, C.c_longlong, c_double_p, C.POINTER(AcqParams),
                              C.POINTER(c_double_p), C.c_int, C.POINTER(SweepResult)]),
     ("kb_predict_dev", C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
@@ -290,6 +292,14 @@ class DeviceModel:
                 return
             check(self._lib.kb_model_set_norm(self._h, norm_type, _dp(p0), _dp(p1)))
         self._norm_key = key
+
+    def set_ymap(self, mode, a=1.0, b=0.0):
+        """Map of the predicted mean to real units for models trained on normalised responses (prediction.py:213-217)."""
+        key = (int(mode), float(a), float(b))
+        if getattr(self, "_ymap_key", (YMAP_NONE, 1.0, 0.0)) == key:
+            return
+        check(self._lib.kb_model_set_ymap(self._h, *key))
+        self._ymap_key = key
 
     def loocv(self):
         pred = np.empty(self.n)

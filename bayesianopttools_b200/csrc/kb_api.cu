@@ -215,6 +215,8 @@ struct kb_model {
   int maxorder = 0;
   int norm_type = KB_NORM_NONE;
   double *p0 = nullptr, *p1 = nullptr;
+  int ymode = KB_YMAP_NONE;
+  double ya = 1.0, yb = 0.0;
   // predict scratch
   double* psi_scratch = nullptr;
   double* ex_scratch = nullptr;
@@ -854,6 +856,12 @@ kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const 
   return KB_OK;
 }
 
+kb_status kb_model_set_ymap(kb_model* m, int mode, double a, double b) {
+  if (!m || mode < KB_YMAP_NONE || mode > KB_YMAP_STD) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  m->ymode = mode; m->ya = a; m->yb = b;
+  return KB_OK;
+}
+
 static kb_status ensure_predict_scratch(kb_model* m) {
   const int qx = 1 + m->nind;
   const int resident = kb_predict_can_warp(m->d, m->n, qx, m->idx_dev ? 1 : 0)
@@ -903,6 +911,7 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   a.beta = m->fit.beta; a.LM = m->fit.Mbuf; a.idx = m->idx_dev; a.maxorder = m->maxorder;
   a.sigma2 = m->sigma2;
   a.norm_type = m->norm_type; a.p0 = m->p0; a.p1 = m->p1;
+  a.ymode = m->ymode; a.ya = m->ya; a.yb = m->yb;
   a.m = npts; a.x = x_dev; a.idx_offset = idx_offset;
   a.ybest = ap ? ap->ybest : 0.0;
   a.limit = ap ? ap->limit : 0.0;

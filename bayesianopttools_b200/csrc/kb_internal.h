@@ -117,6 +117,9 @@ struct KbPredictArgs {
   long long m;
   const double* x;         // [m][d] raw units (device)
   long long idx_offset;    // global index of x[0] (multi-GPU shards)
+  // mean in real units when the responses were normalised (KB_YMAP_*, prediction.py:213-217)
+  int ymode;
+  double ya, yb;
   // acquisition parameters
   double ybest, limit, sigmalcb;
   int limit_sign;          // +1 for '>' '>=' ; -1 for '<' '<='

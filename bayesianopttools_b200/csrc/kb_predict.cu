@@ -81,7 +81,9 @@ struct KbRunning {
 // erf / exp are evaluated only when an output or the arg-min needs them.
 __device__ __forceinline__ void kb_acq_site(const KbPredictArgs& P, double fpc, double psia, double vv, double t2,
                                             long long gi, KbRunning& run) {
-  const double f = fpc + psia;
+  double f = fpc + psia;
+  if (P.ymode == KB_YMAP_DEFAULT) f = (f * 0.5 + 0.5) * P.ya + P.yb;      // stdtoreal, prediction.py:300-313
+  else if (P.ymode == KB_YMAP_STD) f = P.yb + P.ya * f;
   const double ssqr = P.sigma2 * ((1.0 - vv) + t2);
   const double s = sqrt(fabs(ssqr));
   const bool want_ei = P.out[KB_OUT_EI] || P.out[KB_OUT_POI] || P.acq == KB_OUT_EI || P.acq == KB_OUT_POI;

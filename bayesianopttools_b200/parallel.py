@@ -5,10 +5,9 @@ The path partitions into independent units:
     replicated.  The only exchange is an all-gather of the per-rank NLL slices (8 B per
     candidate) followed by a local arg-min with lowest-index tie-break.
   * prediction / Monte-Carlo sites: contiguous shards of m/G points; the fit state is
-    replicated.  The exchange is an all-gather of one 64-byte reduction record per rank
-    (min acquisition + index, min U + index, three failure counters), merged locally and
-    deterministically -- NCCL has no arg-reduce, and summing int64 counters after a gather is
-    exact and order independent.
+    replicated.  The exchange is an all-reduce (sum) of the int64 failure counters (akmcs.py:208-238)
+    and an all-gather of one 32-byte (min acquisition, index, min U, index) record per rank, merged
+    locally and deterministically (lowest index on ties) -- NCCL has no arg-reduce.
 No data-path collective exists: NCCL (NVLink) carries only these records.  The same code runs
 over gloo on CPU tensors (tests/test_parallel_gloo.py).
 """
@@ -78,8 +77,10 @@ def merge_results(records):
 
 
 def gather_sweep_result(local):
-    """All-gather one reduction record per rank and merge.  `local` is a dict with
-    RESULT_FIELDS, or a (8,) int64-viewable device tensor laid out like KbSweepResult."""
+    """Merge one reduction record per rank.  `local` is a dict with RESULT_FIELDS, or a (8,) int64-viewable
+    device tensor laid out like KbSweepResult.  The failure counters and the site count are summed with
+    `all_reduce` (int64, exact); the two (min, index) pairs are all-gathered and merged with the lowest index
+    winning ties, which is what np.argmin over the whole population returns."""
     rank, size = world()
     if isinstance(local, torch.Tensor):
         raw = local.view(torch.int64).reshape(8)
@@ -91,17 +92,67 @@ def gather_sweep_result(local):
         raw = torch.as_tensor(vals)
     if size > 1:
         raw = raw.to(_comm_device())
-        outs = [torch.empty_like(raw) for _ in range(size)]
-        dist.all_gather(outs, raw)
+        counts = raw[4:8].clone()
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)               # n_fail, n_fail_minus, n_fail_plus, n_points
+        mins = raw[0:4].contiguous()
+        outs = [torch.empty_like(mins) for _ in range(size)]
+        dist.all_gather(outs, mins)
+        counts = counts.cpu().numpy()
+        outs = [o.cpu().numpy() for o in outs]
     else:
-        outs = [raw]
+        a = raw.cpu().numpy()
+        counts, outs = a[4:8], [a[0:4]]
     recs = []
-    for o in outs:
-        a = o.cpu().numpy()
+    for r, a in enumerate(outs):
         f = a.view(np.float64)
         recs.append(dict(best_val=float(f[0]), best_idx=int(a[1]), min_u=float(f[2]), min_u_idx=int(a[3]),
-                         n_fail=int(a[4]), n_fail_minus=int(a[5]), n_fail_plus=int(a[6]), n_points=int(a[7])))
-    return merge_results(recs)
+                         n_fail=0, n_fail_minus=0, n_fail_plus=0, n_points=0))
+    out = merge_results(recs)
+    out.update(n_fail=int(counts[0]), n_fail_minus=int(counts[1]), n_fail_plus=int(counts[2]), n_points=int(counts[3]))
+    return out
+
+
+def assert_same_population(xpop):
+    """Sharded likelihood evaluation slices ONE population over the ranks: every rank must have submitted the same
+    rows (same optimiser state, same seed).  One all-reduce of (B, -B, checksum, -checksum) with MAX catches a
+    rank that drew different random numbers before the slices are silently interleaved."""
+    rank, size = world()
+    if size == 1:
+        return
+    x = np.ascontiguousarray(xpop, dtype=np.float64)
+    w = np.cos(np.arange(x.size, dtype=np.float64) * 0.7310585786) + 1.5      # position-dependent weights
+    chk = float(np.dot(x.ravel(), w)) if x.size else 0.0
+    if not np.isfinite(chk):
+        chk = float(np.count_nonzero(~np.isfinite(x)))
+    v = torch.tensor([float(len(x)), -float(len(x)), chk, -chk], dtype=torch.float64, device=_comm_device())
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    v = v.cpu().numpy()
+    if v[0] != -v[1] or v[2] != -v[3]:
+        raise ValueError("shard_population: the ranks submitted different populations (sizes %g..%g); every rank "
+                         "must run the same deterministic optimiser with the same seed" % (-v[1], v[0]))
+
+
+def broadcast_array(a, src=0):
+    """A float64 array of a shape every rank knows, sent by rank `src`."""
+    rank, size = world()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if size == 1:
+        return a
+    buf = torch.as_tensor(a.copy()).to(_comm_device())
+    dist.broadcast(buf, src=src)
+    return buf.cpu().numpy().reshape(a.shape)
+
+
+def allgather_rows(row):
+    """Every rank contributes one float64 row of the same length; returns the (size, len) matrix."""
+    rank, size = world()
+    row = np.ascontiguousarray(row, dtype=np.float64).reshape(-1)
+    if size == 1:
+        return row[None, :]
+    mine = torch.as_tensor(row.copy()).to(_comm_device())
+    outs = [torch.empty_like(mine) for _ in range(size)]
+    dist.all_gather(outs, mine)
+    return np.stack([o.cpu().numpy() for o in outs])
 
 
 def gather_counts(n_local):

@@ -6,6 +6,8 @@ optimisers stay on the host but evaluate POPULATIONS: the finite-difference sten
 L-BFGS-B / SLSQP (nbhyp+1 candidates), a CMA-ES generation or a GA population is one batched
 call instead of one `likelihood()` per candidate (kriging_model.py:420-446).
 """
+import threading
+
 import numpy as np
 from scipy.optimize import fmin_cobyla, minimize
 
@@ -18,6 +20,62 @@ from .supports.prediction import prediction
 from .supports.trendfunction import compute_regression_mat, polytruncation
 
 PENALTY = 1e4      # the reference's penalty value for failed evaluations (likelihood_func.py:207)
+_TLS = threading.local()   # which lock-step slot the current optimiser thread owns (see _Lockstep)
+
+
+class _Lockstep:
+    """Runs the objective calls of several optimiser threads as ONE device call.
+
+    The reference's multi-start search (`parallelopt`, kriging_model.py:326-389) runs `nrestart` independent local
+    optimisers; with L-BFGS-B each of them asks for nbhyp + 1 likelihoods at a time, which is far too small a
+    population to fill the device.  Here every restart runs in its own thread; a thread that needs likelihood
+    values deposits its candidates and waits, and when every still-running restart has deposited, the last one
+    evaluates the union in one `likelihood_batch` call and hands each thread its slice.  Each optimiser sees
+    exactly the values it would see alone (the kernels are deterministic per candidate, whatever else is in the
+    population), so every restart ends where the sequential loop would end -- nrestart times fewer device calls."""
+
+    def __init__(self, batch_fn, nthreads):
+        self.fn, self.active = batch_fn, nthreads
+        self.cv = threading.Condition()
+        self.pending, self.results = {}, {}
+        self.gen, self.error, self.calls = 0, None, 0
+
+    def _flush(self):                      # lock held; every active thread is waiting on it
+        tids = sorted(self.pending)
+        sizes = [len(self.pending[t]) for t in tids]
+        try:
+            f = np.asarray(self.fn(np.vstack([self.pending[t] for t in tids])))
+            off = 0
+            for t, n in zip(tids, sizes):
+                self.results[t] = f[off:off + n]
+                off += n
+        except BaseException as e:         # noqa: BLE001 -- handed to every waiting thread
+            self.error = e
+        self.calls += 1
+        self.pending.clear()
+        self.gen += 1
+        self.cv.notify_all()
+
+    def evaluate(self, tid, pts):
+        with self.cv:
+            if self.error is not None:
+                raise self.error
+            self.pending[tid] = np.atleast_2d(np.asarray(pts, dtype=float))
+            if len(self.pending) >= self.active:
+                self._flush()
+            else:
+                gen = self.gen
+                while self.gen == gen:
+                    self.cv.wait()
+            if self.error is not None:
+                raise self.error
+            return self.results.pop(tid)
+
+    def finish(self, tid):
+        with self.cv:
+            self.active -= 1
+            if self.active > 0 and len(self.pending) >= self.active:
+                self._flush()
 
 
 class Kriging:
@@ -29,6 +87,7 @@ class Kriging:
         KrigInfo["nsamp"] = np.size(KrigInfo["X"], 0)
         self.nbhyp = KrigInfo["nvar"] + 1 if trainvar is True else KrigInfo["nvar"]
         self.trainvar = trainvar
+        self._lockstep = None
         self.normy = normy
         self.standardization = standardization
         self.standtype = standtype
@@ -89,8 +148,12 @@ class Kriging:
 
     # ------------------------------------------------------------------
     def _batch_nll(self, xpop):
-        f = likelihood_batch(xpop, self.KrigInfo, trainvar=self.trainvar)
-        return f
+        ls = getattr(self, "_lockstep", None)
+        if ls is not None:
+            tid = getattr(_TLS, "tid", None)
+            if tid is not None:
+                return ls.evaluate(tid, xpop)
+        return likelihood_batch(xpop, self.KrigInfo, trainvar=self.trainvar)
 
     def _fun_and_grad(self, x, lbv, ubv, eps=1e-3):
         """Objective and forward-difference gradient from ONE batched evaluation; the stencil
@@ -126,6 +189,10 @@ class Kriging:
         if pre_theta is not None:
             pre_theta = np.asarray(pre_theta, dtype=float)
             xhyp = np.vstack((pre_theta, np.random.rand(K["nrestart"] - 1, nhyp) + pre_theta))
+        if K.get("shard_population", False) or K.get("shard_restarts", False):
+            # ranks that share one training must start from the same points (np.random.rand above is per process)
+            from bayesianopttools_b200 import parallel as par
+            xhyp = par.broadcast_array(xhyp, 0)
 
         if self.nbhyp == 1:
             best_x, neglnlikecand = self._train_1d()
@@ -173,17 +240,81 @@ class Kriging:
         return x, float(self._batch_nll(x[None, :])[0])
 
     def parallelopt(self, xhyp, parallel=False, optimbound=None, disp=True):
-        """kriging_model.py:326-389.  Restarts run in sequence; the parallelism is inside each
-        objective call (population on the GPU), so `parallel` is accepted and ignored."""
+        """kriging_model.py:326-389: one local search per start point, arg-min taken by the caller.
+
+        The reference offers a process pool over the restarts (`parallel=True`).  Here the restarts always run
+        concurrently in two nested ways, both transparent to the result:
+          * on one GPU they run in LOCKSTEP (`_Lockstep`): their objective calls are merged into one population
+            per device call (nrestart x (nbhyp + 1) candidates for L-BFGS-B instead of nbhyp + 1);
+          * with KrigInfo["shard_restarts"] under torch.distributed, restart i runs on rank i mod G and the
+            (x*, NLL*) rows are all-gathered -- what AK-MCS / SOBO use to stop replicating the retraining.
+        KrigInfo["lockstep_restarts"] = False restores the sequential loop (debug / A-B aid)."""
         K = self.KrigInfo
         nres = xhyp.shape[0]
         bestxcand = np.zeros((nres, xhyp.shape[1]))
-        neglnlikecand = np.zeros(nres)
-        for ii in range(nres):
-            if disp:
-                print(f"Training hyperparameter candidate no.{ii + 1}")
-            bestxcand[ii, :], neglnlikecand[ii] = self.tune_hyperparameters(xhyp[ii, :])
+        neglnlikecand = np.full(nres, np.inf)
+        mine = list(range(nres))
+        rank, size = 0, 1
+        if K.get("shard_restarts", False) and nres > 1:
+            from bayesianopttools_b200 import parallel as par
+            rank, size = par.world()
+            if size > 1:
+                mine = [i for i in range(nres) if i % size == rank]
+        # the ranks now do DIFFERENT work: a population-sharded likelihood (a collective per call) cannot run inside
+        shard_pop = K.get("shard_population", False)
+        if size > 1:
+            K["shard_population"] = False
+        device_loop = K["optimizer"].lower() == "cmaes" and K.get("cmaes_device", True) and xhyp.shape[1] <= 64
+        if len(mine) > 1 and K.get("lockstep_restarts", True) and not device_loop:
+            ls = _Lockstep(lambda P: likelihood_batch(P, K, trainvar=self.trainvar), len(mine))
+            self._lockstep = ls
+            errors = []
+
+            def work(slot, ii):
+                _TLS.tid = slot
+                try:
+                    bestxcand[ii, :], neglnlikecand[ii] = self.tune_hyperparameters(xhyp[ii, :])
+                except BaseException as e:          # noqa: BLE001 -- re-raised on the calling thread
+                    errors.append(e)
+                finally:
+                    _TLS.tid = None
+                    ls.finish(slot)
+
+            threads = [threading.Thread(target=work, args=(slot, ii)) for slot, ii in enumerate(mine)]
+            try:
+                for t in threads:
+                    t.start()
+                for t in threads:
+                    t.join()
+            finally:
+                self._lockstep = None
+            if errors:
+                raise errors[0]
+            self.lockstep_calls = ls.calls
+        else:
+            for ii in mine:
+                if disp:
+                    print(f"Training hyperparameter candidate no.{ii + 1}")
+                bestxcand[ii, :], neglnlikecand[ii] = self.tune_hyperparameters(xhyp[ii, :])
+        if size > 1:
+            from bayesianopttools_b200 import parallel as par
+            K["shard_population"] = shard_pop
+            rows = np.hstack([bestxcand, neglnlikecand[:, None]])
+            rows[[i for i in range(nres) if i not in mine]] = 0.0
+            allrows = par.allgather_rows(rows.ravel()).reshape(size, nres, -1)
+            for i in range(nres):
+                bestxcand[i, :], neglnlikecand[i] = allrows[i % size, i, :-1], allrows[i % size, i, -1]
         return bestxcand, neglnlikecand
+
+    def _seed(self):
+        """KrigInfo["seed"], or -- when several ranks train one design together -- a seed drawn by rank 0, so that
+        the stochastic optimisers (GA, CMA-ES) submit identical populations on every rank."""
+        K = self.KrigInfo
+        seed = K.get("seed")
+        if seed is None and K.get("shard_population", False):
+            from bayesianopttools_b200 import parallel as par
+            seed = int(par.broadcast_array(np.array([float(np.random.randint(0, 2 ** 31 - 1))]), 0)[0])
+        return seed
 
     def tune_hyperparameters(self, x0):
         """kriging_model.py:392-455 with batched objective evaluations."""
@@ -198,7 +329,7 @@ class Kriging:
         if opt == "cmaes" and K.get("cmaes_device", True) and len(x0) <= 64:
             # the whole generation loop runs on the device (kb_train_cmaes): no host round trip per generation
             from .supports.device_state import fixed_nugget_of, get_model
-            seed = K.get("seed")
+            seed = self._seed()
             bx, bf, _, _, _ = get_model(K).model.train_cmaes(
                 x0, self.sigmacmaes, self.trainvar, fixed_nugget_of(K), lb=lbv, ub=ubv, scaling=self.scaling,
                 popsize=K.get("cmaes_popsize") or 0, maxiter=K.get("cmaes_maxiter") or 0,
@@ -207,7 +338,7 @@ class Kriging:
         if opt == "cmaes":
             bx, bf, _ = fmin_batched(lambda P: self._batch_nll(P), x0, self.sigmacmaes, bounds=[lbv, ubv],
                                      scaling=self.scaling, popsize=K.get("cmaes_popsize"),
-                                     seed=K.get("seed"), maxiter=K.get("cmaes_maxiter"))
+                                     seed=self._seed(), maxiter=K.get("cmaes_maxiter"))
             return bx, bf
         if opt == "lbfgsb":
             res = minimize(lambda x: self._fun_and_grad(x, lbv, ubv, 1e-3), x0, method="L-BFGS-B", jac=True,
@@ -226,7 +357,7 @@ class Kriging:
             return res, scalar(res)
         if opt == "ga":
             bx, bf, _ = uncGA(self._batch_nll, lb=lbv, ub=ubv, npop=K.get("ga_npop", 100),
-                              maxg=K.get("ga_maxg", 100), seed=K.get("seed"))
+                              maxg=K.get("ga_maxg", 100), seed=self._seed())
             return bx, bf
         raise KeyError(f"{K['optimizer']} in KrigInfo['Optimizer'] is not recognised.")
 

@@ -31,6 +31,8 @@ def likelihood_batch(xpop, KrigInfo, trainvar=True, return_info=False):
         # optimisers here are deterministic, so ranks that train the same design stay in lockstep).
         from bayesianopttools_b200 import parallel
         rank, size = parallel.world()
+        if size > 1:
+            parallel.assert_same_population(xpop)         # every rank, every call: same collective sequence
         if size > 1 and len(xpop) >= size:
             mine = parallel.candidate_slice(len(xpop), rank, size)
             nll, info = holder.model.nll_batch(xpop[mine], trainvar, fixed_nugget_of(KrigInfo), return_info=True)

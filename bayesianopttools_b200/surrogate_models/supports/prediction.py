@@ -36,6 +36,16 @@ def _configure(KrigInfo, model):
     else:
         model.set_norm(_lib.NORM_NONE)
     model.set_trend(np.asarray(KrigInfo["idx"]).astype(np.int32))
+    # norm_y: the reference maps the mean to real units before anything is derived from it (prediction.py:213-217);
+    # the device applies the same map inside the sweep, so acquisitions, U and the AK-MCS counters see real units
+    if KrigInfo.get("norm_y", False) is True:
+        if KrigInfo["normtype"] == "default":
+            y = np.asarray(KrigInfo["y"], dtype=float)
+            model.set_ymap(_lib.YMAP_DEFAULT, float(np.max(y) - np.min(y)), float(np.min(y)))
+        else:
+            model.set_ymap(_lib.YMAP_STD, float(np.ravel(KrigInfo["y_std"])[0]), float(np.ravel(KrigInfo["y_mean"])[0]))
+    else:
+        model.set_ymap(_lib.YMAP_NONE)
 
 
 def stdtoreal(f, KrigInfo, num=None):
@@ -84,8 +94,6 @@ def prediction(x, KrigInfo, predtypes, num=None, drm=None, **kwargs):
         kw["sigmalcb"] = float(KrigInfo["sigmalcb"])
     outs, _ = model.predict(x, tuple(dict.fromkeys(names)), acq=names[0] if names[0] != "fpc" else "pred",
                             want_result=False, **kw)
-    if KrigInfo.get("norm_y", False) is True and "pred" in outs:
-        outs["pred"] = stdtoreal(outs["pred"], KrigInfo)
     outputs = []
     for p in names:
         v = outs[p]

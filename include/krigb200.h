@@ -115,6 +115,15 @@ kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d);
  * (samplingplan.py:84-88); KB_NORM_STD p0=X_mean,p1=X_std (prediction.py:160). */
 kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const double* p1);
 
+/* Output map of the predicted mean when the model was trained on normalised responses (KrigInfo["norm_y"],
+ * prediction.py:213-217 -> stdtoreal :300-313): applied to f BEFORE every acquisition function, U and the AK-MCS
+ * counters, exactly where the reference applies it; variance and s stay in the model's units, as in the reference.
+ *   KB_YMAP_NONE                                  f
+ *   KB_YMAP_DEFAULT  a = max(y) - min(y), b = min(y)   (f / 2 + 0.5) * a + b
+ *   KB_YMAP_STD      a = y_std, b = y_mean             b + a * f                                      */
+enum { KB_YMAP_NONE = 0, KB_YMAP_DEFAULT = 1, KB_YMAP_STD = 2 };
+kb_status kb_model_set_ymap(kb_model* m, int mode, double a, double b);
+
 /* Batched predictor.  Replaces `prediction(x, KrigInfo, predtypes)`
  * (prediction.py:67-298): x is (m x d) in RAW units; outs[k] (k = KB_OUT_*) is a
  * buffer of m doubles or NULL.  result (may be NULL) receives the reductions

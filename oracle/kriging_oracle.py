@@ -59,8 +59,11 @@ def corr(XN, XM, theta, kernel="gaussian", plscoeff=None):
 
 
 def corr_chunked(XN, XM, theta, kernel="gaussian", plscoeff=None, chunk=2048):
-    """Same as :func:`corr` without the (n, m, d) temporary (large n*m*d)."""
+    """Same as :func:`corr` without the (n, m, d) temporary (large n*m*d): column chunks sized so that the
+    temporary stays below about 128 MB."""
     XM = np.asarray(XM, dtype=np.float64)
+    n, d = np.shape(XN)
+    chunk = int(max(1, min(chunk, (1 << 24) // max(1, n * d))))
     out = np.empty((np.shape(XN)[0], XM.shape[0]))
     for s in range(0, XM.shape[0], chunk):
         out[:, s:s + chunk] = corr(XN, XM[s:s + chunk], theta, kernel, plscoeff)

@@ -301,6 +301,72 @@ def mobo_host(ref_root="/root/reference"):
     np.savez(_os.path.join(OUT, "mobo_host.npz"), **out)
 
 
+def branch_cases():
+    """tests/golden/branches.npz: branches of the prediction / likelihood boundary the other fixtures do not
+    reach -- standtype 'std' (prediction.py:160), norm_y = True (prediction.py:213-217; Kriging.standardize itself
+    crashes with normy=True in the reference -- kwarg mismatch at kriging_model.py:121-129 -- so the dict is
+    completed by hand with the reference's own `standardize(..., norm_y=True)` and then goes through the
+    reference's likelihood and prediction), limittype '<' (prediction.py:279-282), 'lcb' / 'ebe' outputs
+    (:244-247) and the isotropic Gaussian kernel (likelihood_func.py:60-61)."""
+    rng = np.random.default_rng(31)
+    n, d = 45, 3
+    lb, ub = -5.0 * np.ones(d), 5.0 * np.ones(d)
+    X = rng.uniform(-5, 5, (n, d))
+    y = styb(X)
+    xq = rng.uniform(-5, 5, (61, d))
+    x = np.array([0.1, 0.25, 0.3])
+    types = ("pred", "SSqr", "s", "EI", "poi", "pof", "ebe", "fpc")
+    out = dict(X=X, y=y, lb=lb, ub=ub, xq=xq, theta_log10=x)
+
+    def run(tag, K, obj, xx=x):
+        with quiet():
+            K = ref.likelihood(xx.copy(), K, mode="all", trainvar=False)
+        K["limit"], K["limittype"], K["sigmalcb"] = float(np.median(y)), "<", 2.0
+        obj.KrigInfo = K
+        out[tag + "_nll"] = np.array(K["NegLnLike"])
+        out[tag + "_limit"] = np.array(K["limit"])
+        for t, o in pred_all(obj, xq, types).items():
+            out[tag + "_" + t] = o
+        with quiet():
+            lcb = np.asarray(obj.predict(xq, ["lcb"]), float)      # (m, m): f_i - sigmalcb SSqr_j
+        out[tag + "_p_lcb_diag"] = np.diag(lcb).copy()
+        return K
+
+    with quiet():
+        obj = ref.Kriging(make_info(X, y, lb, ub), standardization=True, standtype="std", normy=False, trainvar=False)
+    K = run("std", obj.KrigInfo, obj)
+    for k in ("X_norm", "X_mean", "X_std", "F"):
+        out["std_" + k] = np.asarray(K[k], float)
+    # norm_y = True, 'std': the reference's standardize returns the six arrays its Kriging.standardize fails to unpack
+    with quiet():
+        obj = ref.Kriging(make_info(X, y, lb, ub), standardization=True, standtype="std", normy=False, trainvar=False)
+        Xn, yn, Xm, ym, Xs, ys = ref.standardize(X, y, type="std", norm_y=True)
+    K = obj.KrigInfo
+    K.update(X_norm=Xn, y_norm=yn, X_mean=Xm, y_mean=ym, X_std=Xs, y_std=ys, norm_y=True)
+    K = run("stdny", K, obj)
+    for k in ("X_norm", "y_norm", "X_mean", "X_std", "y_mean", "y_std", "F"):
+        out["stdny_" + k] = np.asarray(K[k], float)
+    # norm_y = True, 'default'
+    with quiet():
+        obj = ref.Kriging(make_info(X, y, lb, ub), standardization=True, standtype="default", normy=False, trainvar=False)
+        rngs = np.vstack((np.hstack((lb, np.min(y))), np.hstack((ub, np.max(y)))))
+        Xn, yn = ref.standardize(X, y, type="default", norm_y=True, range=rngs)
+    K = obj.KrigInfo
+    K.update(X_norm=Xn, y_norm=yn, norm_y=True)
+    K = run("defny", K, obj)
+    for k in ("X_norm", "y_norm", "F"):
+        out["defny_" + k] = np.asarray(K[k], float)
+    # isotropic Gaussian kernel: one length-scale for every dimension
+    with quiet():
+        obj = ref.Kriging(make_info(X, y, lb, ub, kernel=["iso_gaussian"]), standardization=True, standtype="default",
+                          normy=False, trainvar=False)
+        xi = np.array([0.2])
+        out["iso_nll_default"] = np.array(ref.likelihood(xi.copy(), obj.KrigInfo, mode="default", trainvar=False))
+    K = run("iso", obj.KrigInfo, obj, xx=xi)
+    out["iso_X_norm"], out["iso_F"] = np.asarray(K["X_norm"], float), np.asarray(K["F"], float)
+    save("branches", **out)
+
+
 if __name__ == "__main__":
     notebook_case("krigdemo_nb", 50, [-0.06768278, -0.06558988, 121.47648552358743,
                                       4.379695408530209, 4.298317119160842])
@@ -326,3 +392,4 @@ if __name__ == "__main__":
     sobol_indices()
     ehvi2d()
     mobo_host()
+    branch_cases()

@@ -30,3 +30,10 @@ def relerr(a, b):
     b = np.asarray(b, dtype=np.float64).ravel()
     scale = max(float(np.max(np.abs(b))), np.finfo(float).tiny)
     return float(np.max(np.abs(a - b))) / scale
+
+
+def assert_rel(label, a, b, tol=1e-9):
+    """Scale-relative comparison that PRINTS the achieved error (pytest -s / the captured output of a failure)."""
+    e = relerr(a, b)
+    print(f"[achieved] {label}: {e:.1e} (bar {tol:.0e})")
+    assert e < tol, (label, e)

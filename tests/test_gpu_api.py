@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import load_golden, relerr
+from conftest import assert_rel, load_golden, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -29,18 +29,18 @@ def test_train_reproduces_notebook(name, capsys):
     assert np.array_equal(obj.KrigInfo["X_norm"], g["X_norm"])
     obj.train(disp=False)
     K = obj.KrigInfo
-    assert abs(K["NegLnLike"] - float(g["nll"])) / abs(float(g["nll"])) < 1e-8
+    assert abs(K["NegLnLike"] - float(g["nll"])) / abs(float(g["nll"])) < 1e-9
     assert np.allclose(K["Theta"], g["theta_log10"], atol=2e-5)
     assert K["U"].shape == g["U"].shape and K["BE"].shape == (1, 1) and K["SigmaSqr"].shape == (1, 1)
     err, pred = obj.loocvcalc(metrictype="rmse")
     assert pred.shape == (len(g["y"]), 1)
-    assert abs(err - float(g["loocv_rmse"])) / float(g["loocv_rmse"]) < 1e-5
+    assert abs(err - float(g["loocv_rmse"])) / float(g["loocv_rmse"]) < 1e-5     # (theta* of the two L-BFGS-B runs differ by 1e-6)
     xx = np.linspace(-5, 5, 100)
     gx, gy = np.meshgrid(xx, xx)
     grid = np.column_stack([gx.reshape(-1), gy.reshape(-1)])
     ygrid = obj.predict(grid, ["pred"])
     assert ygrid.shape == (10000, 1)
-    assert relerr(ygrid.ravel()[g["grid_idx"]], g["grid_pred_sub"]) < 1e-5
+    assert_rel("test_gpu_api.py:43 ygrid.ravel()[g['grid_idx']]", ygrid.ravel()[g["grid_idx"]], g["grid_pred_sub"], 1e-5)
     yact = 0.5 * np.sum(grid ** 4 - 16 * grid ** 2 + 5 * grid, axis=1)
     rmse = np.sqrt(np.mean((yact - ygrid.ravel()) ** 2))
     assert abs(rmse - float(g["rmse_grid"])) / float(g["rmse_grid"]) < 1e-5
@@ -70,9 +70,9 @@ def test_likelihood_and_prediction_shims_follow_reference_conventions():
     outs = obj.predict(g["xq"], ["pred", "SSqr", "s", "EI", "poi", "pof"])
     assert isinstance(outs, list) and outs[0].shape == (133, 1) and outs[1].shape == (1, 133)
     for o, k in zip(outs, ("pred", "ssqr", "s", "ei", "poi", "pof")):
-        assert relerr(o, g["p_" + k]) < 2e-8, k
+        assert_rel("shim predict " + k, o, g["p_" + k], 1e-9)
     one = obj.predict(g["xq"][5], "EI")
-    assert isinstance(one, float) and abs(one - g["p_ei"][5]) <= 2e-8 * np.max(np.abs(g["p_ei"]))
+    assert isinstance(one, float) and abs(one - g["p_ei"][5]) <= 1e-9 * np.max(np.abs(g["p_ei"]))
     with pytest.raises(ValueError):
         obj.predict(g["xq"][:2], ["nope"])
     with pytest.raises(ValueError):
@@ -101,7 +101,7 @@ def test_kpls_train_cmaes_and_predict():
     g = load_golden("kpls")
     K = _info(g, n_princomp=3, optimizer="cmaes", nrestart=1, cmaes_popsize=16, cmaes_maxiter=40, seed=3)
     obj = KPLS(K, standardization=True, standtype="default", normy=False, trainvar=False)
-    assert relerr(obj.KrigInfo["plscoeff"] ** 2, g["plscoeff"] ** 2) < 1e-9
+    assert_rel("test_gpu_api.py:104 obj.KrigInfo['plscoeff'] ** 2", obj.KrigInfo["plscoeff"] ** 2, g["plscoeff"] ** 2, 1e-9)
     obj.train(disp=False)
     Kt = obj.KrigInfo
     ref = ko.nll(Kt["Theta"], g["X_norm"], g["y"], g["F"], plscoeff=Kt["plscoeff"], n_princomp=3, full=True)
@@ -110,7 +110,8 @@ def test_kpls_train_cmaes_and_predict():
     pr = obj.predict(g["xq"], ["pred", "s"])
     out = ko.predict(ko.standardize_x(g["xq"], g["lb"], g["ub"]), g["X_norm"], g["y"], g["F"], g["idx"], ref,
                      plscoeff=Kt["plscoeff"])
-    assert relerr(pr[0], out["pred"]) < 1e-8 and relerr(pr[1], out["s"]) < 1e-7
+    assert_rel("kpls pred", pr[0], out["pred"], 1e-9)
+    assert_rel("kpls s", pr[1], out["s"], 1e-9)
 
 
 def test_akmcs_iteration0_matches_reference():
@@ -124,7 +125,7 @@ def test_akmcs_iteration0_matches_reference():
     ak = AKMCS(obj, dict(init_samp=g["pop"], maxupdate=2, problem="fourbranches"))
     ak.run(autoupdate=False, disp=False)
     assert ak.Gx.shape == (4000, 1) and ak.sigmaG.shape == (1, 4000)
-    assert relerr(ak.Gx, g["Gx"]) < 1e-6
+    assert_rel("test_gpu_api.py:127 ak.Gx", ak.Gx, g["Gx"], 1e-6)
     assert ak.Pf == float(g["Pf"])
     assert np.array_equal(ak.xnew, g["xnew"])
     assert abs(ak.stop_criteria - float(g["stop"])) < 1e-12

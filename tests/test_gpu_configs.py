@@ -9,12 +9,12 @@ C4 KPLS, C5 AK-MCS) and for the code paths those shapes switch on in the CUDA ke
 Sizes are cut so the numpy oracle finishes in seconds; the full-size shapes are covered through
 size-independent properties (sub-population equality, shard additivity of the AK-MCS counters).
 Tolerances as in test_gpu_parity.py: relative 1e-9 on NLL / beta / sigma^2, scale-relative 5e-9 on
-predictor outputs, identical indices and counters.
+predictor outputs, identical indices and counters.  (Round 2: every bar is 1e-9 unless the line says why not.)
 """
 import numpy as np
 import pytest
 
-from conftest import relerr
+from conftest import assert_rel, relerr
 from oracle import kriging_oracle as ko
 
 pytestmark = pytest.mark.gpu
@@ -55,8 +55,8 @@ def test_c3_trend_nll_beta_sigma(lib, n, d, order):
     for b in range(len(xpop)):
         ref = ko.nll(xpop[b], Xn, y, F, full=True)
         assert abs(nll[b] - ref["NegLnLike"]) / abs(ref["NegLnLike"]) < TOL, (b, nll[b], ref["NegLnLike"])
-        assert relerr(beta[b], ref["BE"]) < 1e-7, (b, relerr(beta[b], ref["BE"]))
-        assert abs(s2[b] - ref["SigmaSqr"]) / ref["SigmaSqr"] < 1e-8
+        assert_rel(f"c3 n={n} beta[{b}]", beta[b], ref["BE"], TOL)
+        assert_rel(f"c3 n={n} sigma2[{b}]", s2[b], ref["SigmaSqr"], TOL)
     mdl.close()
 
 
@@ -76,7 +76,7 @@ def test_c3_trend_fit_and_predict(lib):
     outs, _ = mdl.predict(xq, ("pred", "ssqr", "fpc"))
     ref = ko.predict(xq, Xn, y, F, idx, fit)
     for k in ("pred", "ssqr", "fpc"):
-        assert relerr(outs[k], ref[k]) < 5e-9, (k, relerr(outs[k], ref[k]))
+        assert_rel("c3 predict " + k, outs[k], ref[k], TOL)
     mdl.close()
 
 
@@ -148,7 +148,9 @@ def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
     ref = ko.predict(xq, Xn, y, F, np.zeros((1, d), int), fit, kernels=(kernel,), limit=0.2)
     ref["u"] = ref["U"]
     for k in names:
-        assert relerr(outs[k], ref[k]) < 2e-8, (k, relerr(outs[k], ref[k]))
+        # mean, variance and s at the north-star tolerance; EI / PoI / PoF / U divide by s, which near a training
+        # site of these smooth low-dimensional designs amplifies the 1e-10 of the variance (achieved: <= 1.3e-8)
+        assert_rel(f"n={n} d={d} {kernel} {k}", outs[k], ref[k], TOL if k in ("pred", "ssqr", "s") else 2e-8)
     assert res["min_u_idx"] == int(np.argmin(outs["u"]))
     assert res["n_fail"] == int(np.sum(outs["pred"] <= 0))
     assert res["n_fail_minus"] == int(np.sum(outs["pred"] - 1.96 * outs["s"] <= 0))
@@ -393,7 +395,7 @@ def test_wide_input_predictor_without_strip_staging(lib):
     outs, res = mdl.predict(xq, ("pred", "ssqr", "ei"), acq="ei", ybest=float(y.min()))
     p = ko.predict(xq, X, y, F, np.zeros((1, d), int), fit, kernels=("matern32",), ybest=float(y.min()))
     for k in ("pred", "ssqr", "ei"):
-        assert relerr(outs[k], p[k]) < 2e-8, k
+        assert_rel("d=150 " + k, outs[k], p[k], TOL)
     assert res["best_idx"] == int(np.argmin(p["ei"]))
     mdl.close()
     # d = 200 is the widest design a model accepts; wider ones are refused with a message, not a crash
@@ -414,7 +416,7 @@ def test_wide_input_predictor_without_strip_staging(lib):
     else:
         fitw = ko.nll(thw, Xw, yw, np.ones((40, 1)), full=True)
         pw = ko.predict(Xw[:7] + 0.01, Xw, yw, np.ones((40, 1)), np.zeros((1, 200), int), fitw)
-        assert relerr(outs["pred"], pw["pred"]) < 2e-8
+        assert_rel("d=200 pred", outs["pred"], pw["pred"], TOL)
     big.close()
 
 
@@ -451,7 +453,8 @@ def test_few_sites_predictor_matches_strip_kernel_and_oracle(lib, n, d, order, k
         for k in want:
             # tail probabilities and |f|/s near training sites amplify the 1e-13 differences of the summation order
             assert relerr(few[k], strip[k][:msites]) < (1e-7 if k in ("ei", "poi", "pof", "u") else 1e-9), (k, msites)
-        assert relerr(few["pred"], p["pred"][:msites]) < 2e-8 and relerr(few["ssqr"], p["ssqr"][:msites]) < 2e-8
+        assert_rel(f"few-sites {msites} pred", few["pred"], p["pred"][:msites], TOL)
+        assert_rel(f"few-sites {msites} ssqr", few["ssqr"], p["ssqr"][:msites], TOL)
         assert rf["best_idx"] == int(np.argmin(strip["ei"][:msites])) and rf["n_points"] == msites
         assert rf["n_fail"] == int(np.sum(strip["pred"][:msites] <= 0))
         assert rf["min_u_idx"] == int(np.argmin(strip["u"][:msites]))
@@ -484,7 +487,8 @@ def test_seated_right_hand_sides_at_their_limits(lib, n, nind, kernel):
     for b in range(0, B, max(1, B // 5)):
         ref = ko.nll(xpop[b], X, y, F, kernels=(kernel,), full=True)
         assert abs(nll[b] - ref["NegLnLike"]) <= TOL * max(1.0, abs(ref["NegLnLike"])), (b, nll[b], ref["NegLnLike"])
-        assert relerr(beta[b], ref["BE"]) < 1e-7 and abs(s2[b] - ref["SigmaSqr"]) / ref["SigmaSqr"] < 1e-8
+        assert_rel(f"seated n={n} beta[{b}]", beta[b], ref["BE"], TOL)
+        assert_rel(f"seated n={n} sigma2[{b}]", s2[b], ref["SigmaSqr"], TOL)
     # a duplicated LAST site with a vanishing nugget: the pivot test of the seated last tile
     Xd = X.copy()
     Xd[n - 1] = Xd[n - 2]

@@ -93,7 +93,9 @@ def test_nll_population_matches_reference(lib, name):
     assert np.all(info == 0)
     assert np.max(np.abs(nll - g["nll"]) / np.abs(g["nll"])) < TOL, (nll, g["nll"])
     beta, s2 = mdl.nll_extras(len(nll))
-    assert relerr(beta, g["BE"]) < 1e-8
+    print(f"[achieved] {name}: nll {np.max(np.abs(nll - g['nll']) / np.abs(g['nll'])):.1e} beta {relerr(beta, g['BE']):.1e} "
+          f"sigma2 {relerr(s2, g['sigma2']):.1e}")
+    assert relerr(beta, g["BE"]) < TOL
     assert relerr(s2, g["sigma2"]) < TOL
     # a second call re-uses the workspace (flag epochs) and must reproduce bit-for-bit
     nll2 = mdl.nll_batch(g["xpop"], kw["trainvar"], kw["fixed_nugget"])
@@ -117,10 +119,15 @@ def test_notebook_golden_fit_and_predict(lib, name):
     mdl.set_norm(lib.NORM_DEFAULT, g["lb"], g["ub"])
     outs, res = mdl.predict(g["xq"], ("pred", "ssqr", "s", "ei", "poi"), acq="ei",
                             ybest=float(np.min(g["y"])))
+    print(f"[achieved] {name}: " + " ".join(f"{k} {relerr(outs[k], g['p_' + k]):.1e}" for k in outs))
     for k in ("pred", "ssqr", "s", "ei", "poi"):
-        assert relerr(outs[k], g["p_" + k]) < 5e-9, (k, relerr(outs[k], g["p_" + k]))
+        assert relerr(outs[k], g["p_" + k]) < TOL, (k, relerr(outs[k], g["p_" + k]))
     assert res["best_idx"] == int(np.argmin(g["p_ei"]))
     assert res["n_points"] == len(g["xq"])
+    # leave-one-out predictions at this fixed theta against the reference's n refits (krigloocv2.py:7-33)
+    lo = mdl.loocv()
+    print(f"[achieved] {name}: loocv {relerr(lo, g['loocv_pred']):.1e}")
+    assert relerr(lo, g["loocv_pred"]) < TOL
     mdl.close()
 
 
@@ -134,8 +141,9 @@ def test_predict_matches_reference(lib, name):
     names = ("pred", "ssqr", "s", "ei", "poi", "pof")
     outs, res = mdl.predict(g["xq"], names, acq="pred", ybest=float(np.min(g["y"])),
                             limit=float(g["limit"]), limit_sign=1)
-    for k in names:
-        assert relerr(outs[k], g["p_" + k]) < 2e-8, (name, k, relerr(outs[k], g["p_" + k]))
+    print(f"[achieved] {name}: " + " ".join(f"{k} {relerr(outs[k], g['p_' + k]):.1e}" for k in names))
+    for k in names:        # every site of the fixture, north-star tolerance (mean, variance and what derives from them)
+        assert relerr(outs[k], g["p_" + k]) < TOL, (name, k, relerr(outs[k], g["p_" + k]))
     assert res["best_idx"] == int(np.argmin(g["p_pred"]))
     mdl.close()
 
@@ -157,8 +165,9 @@ def test_predict_with_trend_matches_oracle(lib, name):
     xq = rng.uniform(-5, 5, (77, g["X"].shape[1]))
     outs, _ = mdl.predict(xq, ("pred", "ssqr", "fpc"))
     ref = ko.predict(ko.standardize_x(xq, g["lb"], g["ub"]), g["X_norm"], g["y"], g["F"], g["idx"], fit)
+    print(f"[achieved] {name}: " + " ".join(f"{k} {relerr(outs[k], ref[k]):.1e}" for k in ("pred", "ssqr", "fpc")))
     for k in ("pred", "ssqr", "fpc"):
-        assert relerr(outs[k], ref[k]) < 5e-9, (k, relerr(outs[k], ref[k]))
+        assert relerr(outs[k], ref[k]) < TOL, (k, relerr(outs[k], ref[k]))
     mdl.close()
 
 
@@ -169,7 +178,7 @@ def test_akmcs_reductions_match_reference(lib):
     mdl.set_norm(lib.NORM_DEFAULT, g["lb"], g["ub"])
     outs, res = mdl.predict(g["pop"], ("pred", "s", "u"), acq="u")
     assert relerr(outs["pred"], g["Gx"]) < TOL
-    assert relerr(outs["s"], g["sigmaG"]) < 1e-8
+    assert relerr(outs["s"], g["sigmaG"]) < TOL
     assert res["n_fail"] == int(g["n_fail"])
     assert res["n_fail_minus"] == int(g["n_fail_minus"])
     assert res["n_fail_plus"] == int(g["n_fail_plus"])
@@ -197,20 +206,21 @@ def test_nll_not_positive_definite_is_flagged_not_fatal(lib):
 
 
 def test_nll_c2_size_properties(lib):
-    """BASELINE config 2 shape (n=1000, d=10, B=64): a seeded subset vs the oracle plus
+    """BASELINE configs[1] on the bench's OWN design and population (bench.py: n=1000, d=10, Styblinski-Tang,
+    64 candidates log10(theta) ~ U(-1, 1), seed 2): every candidate against the oracle, plus the
     size-independent properties (determinism, permutation equivariance over the population)."""
-    rng = np.random.default_rng(1)
-    n, d, B = 1000, 10, 64
-    X = rng.uniform(-1, 1, (n, d))
-    y = 0.5 * np.sum((5 * X) ** 4 - 16 * (5 * X) ** 2 + 5 * (5 * X), axis=1)
-    F = np.ones((n, 1))
-    xpop = np.random.default_rng(2).uniform(-0.3, 0.7, (B, d))
+    import bench
+    _, X, y, F = bench.make_design()
+    xpop = bench.make_population()
+    B = len(xpop)
     mdl = lib.DeviceModel(X, y, F, ["gaussian"])
     nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
     assert np.all(info == 0)
-    for b in (0, 17, 63):
-        ref = ko.nll(xpop[b], X, y, F)
-        assert abs(nll[b] - ref) / abs(ref) < TOL, (b, nll[b], ref)
+    ref = np.array([ko.nll(xpop[b], X, y, F) for b in range(B)])
+    err = np.abs(nll - ref) / np.abs(ref)
+    print(f"[achieved] C2 bench population: worst nll {err.max():.1e} over {B} candidates")
+    assert err.max() < TOL, (int(np.argmax(err)), err.max())
+    assert int(np.argmin(nll)) == int(np.argmin(ref))
     perm = np.random.default_rng(3).permutation(B)
     nll_p = mdl.nll_batch(xpop[perm], False, -6.0)
     assert np.array_equal(nll_p, nll[perm])
@@ -234,8 +244,9 @@ def test_predict_c2_size_vs_oracle(lib):
     outs, res = mdl.predict(xq, ("pred", "ssqr", "ei"), acq="ei", ybest=float(y.min()))
     sub = np.concatenate([np.arange(0, 300), np.arange(m - 300, m)])
     ref = ko.predict(xq[sub], X, y, F, np.zeros((1, d), int), fit)
+    print("[achieved] C2 predictor: " + " ".join(f"{k} {relerr(outs[k][sub], ref[k]):.1e}" for k in ("pred", "ssqr", "ei")))
     for k in ("pred", "ssqr", "ei"):
-        assert relerr(outs[k][sub], ref[k]) < 5e-9, (k, relerr(outs[k][sub], ref[k]))
+        assert relerr(outs[k][sub], ref[k]) < TOL, (k, relerr(outs[k][sub], ref[k]))
     assert res["best_idx"] == int(np.argmin(outs["ei"]))
     assert res["n_fail"] == int(np.sum(outs["pred"] <= 0))
     mdl.close()
@@ -299,15 +310,17 @@ def test_tiny_and_tile_boundary_designs(lib, n, d):
         outs, _ = mdl.predict(xq, ("pred", "ssqr"), acq="pred")
         fit = ko.nll(xpop[0], X, y, F, kernels=("matern52",), full=True)
         p = ko.predict(xq, X, y, F, np.zeros((1, d), int), fit, kernels=("matern52",))
-        assert relerr(outs["pred"], p["pred"]) < 2e-8 and relerr(outs["ssqr"], p["ssqr"]) < 2e-8
+        assert relerr(outs["pred"], p["pred"]) < TOL and relerr(outs["ssqr"], p["ssqr"]) < TOL
     mdl.close()
 
 
 def test_stress_population_over_the_whole_hyperparameter_box(lib):
-    """SURVEY C2 stress set: log10(theta) ~ U(-5, 5) at n = 400 -- from R = I (tiny length-scales) to a
-    matrix of ones plus the nugget (cond ~ n / nugget = 4e8).  Flags agree with LAPACK; the values agree
-    to 1e-9 on the well-conditioned half and to 1e-6 on the near-singular one (both paths are then
-    1e-8-ish away from a long-double evaluation, DESIGN.md 'Accuracy beyond the parity bar')."""
+    """SURVEY C2 stress set: log10(theta) ~ U(-5, 5) at n = 400 -- from R = I (tiny length-scales) to a matrix of
+    ones plus the nugget (cond ~ n / nugget = 4e8).  Not-PD flags agree with LAPACK and every value agrees to
+    1e-9 -- except where cond(R) makes two correct FP64 evaluations differ by more: there an 80-bit evaluation of
+    the same formula (oracle/longdouble_truth.py) arbitrates, and the GPU value must be no further from it than
+    3x LAPACK's own distance."""
+    from oracle import longdouble_truth as lt
     rng = np.random.default_rng(9)
     n, d, B = 400, 6, 48
     X = rng.uniform(-1, 1, (n, d))
@@ -316,7 +329,7 @@ def test_stress_population_over_the_whole_hyperparameter_box(lib):
     xpop = rng.uniform(-5, 5, (B, d))
     mdl = lib.DeviceModel(X, y, F, ["gaussian"])
     nll, info = mdl.nll_batch(xpop, False, -6.0, return_info=True)
-    worst_good, worst_bad, nbad = 0.0, 0.0, 0
+    worst, narb = 0.0, 0
     for b in range(B):
         try:
             ref = ko.nll(xpop[b], X, y, F)
@@ -325,9 +338,13 @@ def test_stress_population_over_the_whole_hyperparameter_box(lib):
             continue
         assert info[b] == 0
         err = abs(nll[b] - ref) / max(1.0, abs(ref))
-        if np.min(xpop[b]) > 0.5:                 # every length-scale above ~3x the design width
-            worst_bad, nbad = max(worst_bad, err), nbad + 1
+        if err >= TOL:
+            t = lt.nll(xpop[b], X, y, F)
+            eg, eo = abs(nll[b] - t) / max(1.0, abs(t)), abs(ref - t) / max(1.0, abs(t))
+            narb += 1
+            print(f"[achieved] stress candidate {b}: gpu-vs-lapack {err:.1e}; vs 80-bit: gpu {eg:.1e} lapack {eo:.1e}")
+            assert eg <= max(TOL, 3 * eo), (b, eg, eo)
         else:
-            worst_good = max(worst_good, err)
-    assert worst_good < 1e-9 and worst_bad < 1e-6, (worst_good, worst_bad, nbad)
+            worst = max(worst, err)
+    print(f"[achieved] stress population: worst {worst:.1e} on {B - narb} candidates, {narb} arbitrated")
     mdl.close()
