@@ -38,16 +38,31 @@
 #include "kb_internal.h"
 #include "kb_diag.cuh"
 
-#define KB_KC 32        // K chunk (doubles) per pipeline stage
-#define KB_STAGES 3
-#define KB_LDK 36       // padded row stride of a 64 x KC chunk
+// K chunk (doubles) per pipeline stage and stage count, per task shape (compile-time, -D overridable for A/B builds).
+// tools/ubench/kloop.cu runs the K loops alone on the real access stream (no dependencies, no epilogues; operands from
+// HBM or L2 make no difference): 128-row tasks 32 wide x 2 stages reach 32.0 TFLOP/s of the 37.1 peak, 16 wide x 3 stages
+// 34.2, with the copies compiled out 35.6 (profiles/r02_ubench_kloop.txt).  Inside the factorisation the two rings are
+// equal within noise (n=1000: 1.118 vs 1.135 ms, n=2000: 6.63 vs 6.66 ms): the tasks are not K-loop-throughput bound
+// (DESIGN 5c), so the wider chunk with fewer barriers stays.
+#ifndef KB_KC128
+#define KB_KC128 32     // 128-row tasks (MODE 4)
+#define KB_NS128 2
+#endif
+#ifndef KB_KC64
+#define KB_KC64 32      // 64-row, PRE and thin tasks (MODE 0, 1, 2)
+#define KB_NS64 3
+#endif
 
-// One ring of 384 chunk rows: three stages of (64 A rows + 64 B rows) for the 64-row tasks, or two
-// stages of (128 A rows + 64 B rows) for the 128-row tasks.  Epilogue tiles and the chain worker's
-// three tiles alias it.
-#define KB_RING_ROWS 384
+// One ring of 384 x 36 doubles: the pipeline stages of the K loop (rows padded by 4 doubles: row stride == 4 mod 16
+// doubles for KC = 16 and 32, conflict-free fragment loads).  Epilogue tiles and the chain worker's three tiles alias it.
+#define KB_RING_DOUBLES (384 * 36)
+#ifndef KB_EARLY_CLAIM
+#define KB_EARLY_CLAIM 0
+#endif
+static_assert(KB_NS128 * (128 + 64) * (KB_KC128 + 4) <= KB_RING_DOUBLES && KB_NS64 * (64 + 64) * (KB_KC64 + 4) <= KB_RING_DOUBLES,
+              "pipeline stages must fit in the ring");
 struct KbCholSmem {
-  double ring[KB_RING_ROWS][KB_LDK];
+  double ring[KB_RING_DOUBLES];
   int4 tdesc;
   int task;
   int ready;
@@ -55,7 +70,7 @@ struct KbCholSmem {
   int rf[8];          // chain worker: refinement flag of the last finished tile of each home candidate
   int knext[8];       // chain worker: next step of each home candidate
 };
-static_assert(sizeof(double) * KB_RING_ROWS * KB_LDK >= sizeof(double) * (3 * KB_TILE * KB_LDC + KB_DIAG_SCRATCH),
+static_assert(sizeof(double) * KB_RING_DOUBLES >= sizeof(double) * (3 * KB_TILE * KB_LDC + KB_DIAG_SCRATCH),
               "three padded tiles and the exchange scratch must fit in the pipeline ring");
 
 __device__ __forceinline__ unsigned long long kb_globaltimer() {
@@ -273,7 +288,7 @@ struct KbCholArgs {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& sm, int b, int k, int slot,
                                               unsigned long long* stamps) {
-  double* raw = &sm.ring[0][0];
+  double* raw = &sm.ring[0];
   double (*C2)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw);
   double (*C1)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw + KB_TILE * KB_LDC);
   double (*Dk)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw + 2 * KB_TILE * KB_LDC);
@@ -549,33 +564,38 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
                                          unsigned need2, double (&acc)[4][4][2]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
-  constexpr int CPT = KB_TILE / KB_KC;      // chunks per tile column
-  constexpr int NS = (MODE == 4) ? 2 : 3;   // pipeline stages
+  constexpr int KC = (MODE == 4) ? KB_KC128 : KB_KC64;     // chunk width
+  constexpr int LDK = KC + 4;                              // padded row stride of a chunk row
+  constexpr int CPT = KB_TILE / KC;                        // chunks per tile column
+  constexpr int NS = (MODE == 4) ? KB_NS128 : KB_NS64;     // pipeline stages
   constexpr int AROWS = (MODE == 4) ? 128 : 64;
-  constexpr int SROWS = AROWS + 64;         // ring rows per stage
+  constexpr int SROWS = AROWS + 64;                        // ring rows per stage
+  constexpr int UPR = KC / 2;                              // 16-byte units per chunk row
   const int c_begin = k0 * CPT, c_end = k1 * CPT;
 
   auto load_chunk = [&](int c, int stage) {
-    const int col0 = c * KB_KC;
-    double (*as)[KB_LDK] = &sm.ring[stage * SROWS];
-    double (*bs)[KB_LDK] = &sm.ring[stage * SROWS + AROWS];
+    const int col0 = c * KC;
+    double* as = &sm.ring[stage * SROWS * LDK];
+    double* bs = as + AROWS * LDK;
     if (MODE == 2) {
-      const int row = tid >> 4, seg = (tid & 15) * 2;
-      kb_cp_async16(&as[row][seg], Arow + (size_t)row * ld + col0 + seg);
+      if (tid < 16 * UPR) {
+        const int row = tid / UPR, seg = (tid % UPR) * 2;
+        kb_cp_async16(&as[row * LDK + seg], Arow + (size_t)row * ld + col0 + seg);
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < (AROWS * KB_KC / 2) / KB_THREADS; ++j) {
+      for (int j = 0; j < (AROWS * UPR) / KB_THREADS; ++j) {
         const int idx = tid + j * KB_THREADS;
-        const int row = idx >> 4, seg = (idx & 15) * 2;
-        kb_cp_async16(&as[row][seg], Arow + (size_t)row * ld + col0 + seg);
+        const int row = idx / UPR, seg = (idx % UPR) * 2;
+        kb_cp_async16(&as[row * LDK + seg], Arow + (size_t)row * ld + col0 + seg);
       }
     }
     if (!same) {
 #pragma unroll
-      for (int j = 0; j < (KB_TILE * KB_KC / 2) / KB_THREADS; ++j) {
+      for (int j = 0; j < (KB_TILE * UPR) / KB_THREADS; ++j) {
         const int idx = tid + j * KB_THREADS;
-        const int row = idx >> 4, seg = (idx & 15) * 2;
-        kb_cp_async16(&bs[row][seg], Brow + (size_t)row * ld + col0 + seg);
+        const int row = idx / UPR, seg = (idx % UPR) * 2;
+        kb_cp_async16(&bs[row * LDK + seg], Brow + (size_t)row * ld + col0 + seg);
       }
     }
   };
@@ -611,11 +631,11 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
       kb_cp_async_commit();
     };
     const int stg = (c - c_begin) % NS;
-    const double (*as)[KB_LDK] = &sm.ring[stg * SROWS];
-    const double (*bs)[KB_LDK] = same ? as : &sm.ring[stg * SROWS + AROWS];
+    const double (*as)[LDK] = reinterpret_cast<const double (*)[LDK]>(&sm.ring[stg * SROWS * LDK]);
+    const double (*bs)[LDK] = same ? as : as + AROWS;
     if (MODE == 2) {
 #pragma unroll
-      for (int ks = 0; ks < KB_KC / 4; ++ks) {
+      for (int ks = 0; ks < KC / 4; ++ks) {
         const double a0 = as[gq][ks * 4 + tq], a1 = as[8 + gq][ks * 4 + tq];
         const double bf = bs[warp * 8 + gq][ks * 4 + tq];
         kb_dmma(acc[0][0][0], acc[0][0][1], a0, bf);
@@ -624,7 +644,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
       }
     } else if (MODE == 4) {
 #pragma unroll
-      for (int ks = 0; ks < KB_KC / 4; ++ks) {
+      for (int ks = 0; ks < KC / 4; ++ks) {
         double af[4], bf[4];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) af[mi] = as[wr * 32 + mi * 8 + gq][ks * 4 + tq];
@@ -638,7 +658,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
       }
     } else {
 #pragma unroll
-      for (int ks = 0; ks < KB_KC / 4; ++ks) {
+      for (int ks = 0; ks < KC / 4; ++ks) {
         double af[2], bf[4];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) af[mi] = as[wr * 16 + mi * 8 + gq][ks * 4 + tq];
@@ -699,7 +719,7 @@ __device__ __forceinline__ void kb_dinv_land() {
 }
 
 __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& sm) {
-  double (*Cs)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.ring[0][0]);
+  double (*Cs)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(&sm.ring[0]);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3, wr = warp >> 1, wc = warp & 1;
   const int NT = P.g.NT, ld = P.g.ld, nb = P.g.nb;
@@ -778,6 +798,15 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
       kb_kloop<0>(sm, Arow, Brow, ti == tkc, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
     }
     if (P.trace && tid == 0) tr2 = kb_globaltimer();
+#if KB_EARLY_CLAIM
+    // the next ticket is claimed as the K loop ends (every thread copied this task's descriptor long ago), so the
+    // atomic's and the descriptor's round trips run under the epilogue
+    if (tid == 32) {
+      const int nx = atomicAdd(&P.ctl[0], 1);
+      sm.task = nx;
+      if (nx < P.ntasks) sm.tdesc = P.tasks[nx];
+    }
+#endif
 
     if (is_pre) {
       // C1 = A[r,r-1] - acc (full tile), C2 = A[r,r] - acc2 (lower 8x8 blocks), both in place
@@ -931,11 +960,13 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
         if (two) kb_flag_release(&fl[ti + 1], tkc + 1);
       }
     }
+#if !KB_EARLY_CLAIM
     if (tid == 32) {
       const int nx = atomicAdd(&P.ctl[0], 1);
       sm.task = nx;
       if (nx < P.ntasks) sm.tdesc = P.tasks[nx];
     }
+#endif
     if (P.trace && tid == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

@@ -148,6 +148,48 @@ def nll(x, X, y, F, kernels=("gaussian",), fixed_nugget=-6.0, trainvar=False,
                 alpha=_trsv(L.T, rt, lower=False), M=M, ZF=ZF)
 
 
+def nll_reference_cost(x, X, y, F, kernels=("gaussian",), fixed_nugget=-6.0, trainvar=False):
+    """The same value as `nll`, computed with the reference's OWN operation sequence so that timing it gives the
+    cost of the unmodified reference on this host (BASELINE.md section 3 asks for that figure next to the fair one):
+    per-dimension (n, n, nvar) distance stack as kernelfunc.py:36-47 builds it, the `eigvals` positive-definiteness
+    print-check (likelihood_func.py:172-173), the Cholesky factor (:175) and the six dense `numpy.linalg.solve`
+    calls on the triangular factors (:183-193; the reference imports `solve` as `mldivide`).  Ordinary / universal
+    Kriging, no KPLS.  Timing aid for bench.py's CPU arms only; `tests/test_oracle_golden.py` pins it to `nll`."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    F = np.asarray(F, dtype=np.float64).reshape(X.shape[0], -1)
+    n, nvar = X.shape
+    hp = decode_hyper(x, nvar, len(kernels), fixed_nugget, trainvar)
+    Psi = np.zeros((n, n))
+    for kname, w in zip(kernels, hp["wgkf"]):
+        stack = np.empty((n, n, nvar))
+        for j in range(nvar):
+            dj = np.abs(X[:, j][:, None] - X[:, j][None, :])
+            stack[:, :, j] = (dj ** 2) / hp["theta"][j] ** 2 if kname in ("gaussian", "iso_gaussian") else dj / hp["theta"][j]
+        if kname in ("gaussian", "iso_gaussian"):
+            Psi += w * np.exp(-0.5 * np.sum(stack, 2))
+        elif kname == "exponential":
+            Psi += w * np.exp(-np.sum(stack, 2))
+        elif kname == "matern32":
+            Psi += w * np.prod(1 + np.sqrt(3) * stack, 2) * np.exp(-np.sqrt(3) * np.sum(stack, 2))
+        else:
+            Psi += w * np.prod(1 + np.sqrt(5) * stack + (5 / 3) * stack ** 2, 2) * np.exp(-np.sqrt(5) * np.sum(stack, 2))
+    R = Psi + np.eye(n) * hp["eps"]
+    np.any(np.linalg.eigvals(R) < 0)                                  # :172 (general, non-symmetric eigen-solver)
+    U = np.linalg.cholesky(R).T                                       # :175-176
+    lndet = 2.0 * np.sum(np.log(np.abs(np.diag(U))))
+    a = np.linalg.solve(U, np.linalg.solve(U.T, y))                   # :183-184  R^-1 y  (two LU solves)
+    Bm = np.linalg.solve(U, np.linalg.solve(U.T, F))                  # :185-186  R^-1 F
+    BE = np.linalg.solve(F.T @ Bm, F.T @ a)                           # :187-189
+    r = y - F @ BE
+    c = np.linalg.solve(U, np.linalg.solve(U.T, r))                   # :192-193
+    if trainvar:
+        s2 = hp["sigma2"]
+        return float(0.5 * lndet + n / 2 * np.log(2 * np.pi) + n / 2 * np.log(s2) + (r.T @ c)[0, 0] / (2 * s2))
+    s2 = (r.T @ c)[0, 0] / n
+    return float((n / 2) * np.log(s2) + 0.5 * lndet)
+
+
 def nll_batch(xpop, X, y, F, **kw):
     """Population form: one NLL per row of xpop; +inf where R is not PD."""
     out = np.empty(len(xpop))

@@ -123,3 +123,18 @@ def test_exi2d_restatement_matches_the_reference_fixture():
         ref = g["ref%d" % c]
         assert np.all(ref >= 0) and np.any(ref > 0)
         assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-12
+
+
+def test_reference_cost_restatement_gives_the_reference_values():
+    """`nll_reference_cost` (bench.py's "unmodified reference" CPU figure) walks the reference's own operation
+    sequence -- eigvals check, six LU solves, (n, n, d) distance stack -- and must return what the unmodified
+    reference returned for the golden cases (likelihood_func.py:168-213)."""
+    for case in ("ok_gaussian", "ok_matern52", "ok_exponential", "ok_matern32", "ok_gaussian_trainvar",
+                 "ok_gaussian_tunednugget", "ok_composite_tn_tv", "trend2"):
+        g = load_golden(case)
+        kw = _case_kwargs(g)
+        for x, want in zip(g["xpop"], g["nll"]):
+            if not np.isfinite(want):
+                continue
+            got = ko.nll_reference_cost(x, g["X_norm"], g["y"], g["F"], **kw)
+            assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (case, got, want)

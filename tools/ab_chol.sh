@@ -5,7 +5,8 @@ for rep in 1 2; do
   for v in "" "$@"; do
     lib=bayesianopttools_b200/csrc/libkrigb200${v:+_$v}.so
     echo "== ${v:-product} rep $rep" >> $out
-    KRIGB200_LIB=$PWD/$lib timeout 120 python tools/quick_perf.py nll1000 >> $out 2>&1
-    KRIGB200_LIB=$PWD/$lib timeout 120 python tools/quick_perf.py nll2000 >> $out 2>&1
+    for c in nll1000 nll2000 nll1000b8 c3; do
+      KRIGB200_LIB=$PWD/$lib timeout 120 python tools/quick_perf.py $c >> $out 2>&1
+    done
   done
 done

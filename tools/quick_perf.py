@@ -100,6 +100,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pred1000":
         predict_case(1000, 10, 1 << 20)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "nll1000b8":
+        nll_case(1000, 10, 8)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "nll1000":
         nll_case(1000, 10, 64)
         sys.exit(0)
