@@ -78,6 +78,87 @@ class _Lockstep:
                 self._flush()
 
 
+def lbfgsb_lockstep(batch_nll, x0s, lbv, ubv, eps=1e-3, maxcor=10, ftol=2.2204460492503131e-09, gtol=1e-5,
+                    maxiter=15000, maxls=20):
+    """`scipy.optimize.minimize(method="L-BFGS-B", jac=True)` for several start points at once, on ONE thread.
+
+    scipy's driver (`_minimize_lbfgsb`, scipy/optimize/_lbfgsb_py.py) is a reverse-communication loop around
+    `_lbfgsb.setulb`: the routine hands back an x and asks for (f, g).  Here every restart owns its own `setulb`
+    state; each round advances every unfinished restart to its next (f, g) request, evaluates the forward-difference
+    stencils of ALL of them in one `batch_nll` call (nrestart x (nbhyp + 1) candidates) and feeds the values back.
+    Arguments, evaluation points and values are exactly those of the sequential scipy call, so each restart ends at
+    the bit-identical point (tests/test_gpu_branches.py::test_lockstep_restarts_equal_the_sequential_search); the
+    thread rendezvous of `_Lockstep` (0.3 ms per round against 0.1 ms of device call on small designs) is gone.
+    Returns (x*, f*) rows and the number of device calls."""
+    from scipy.optimize import _lbfgsb
+    x0s = np.atleast_2d(np.asarray(x0s, dtype=float))
+    R, n = x0s.shape
+    lbv, ubv = np.asarray(lbv, dtype=float), np.asarray(ubv, dtype=float)
+    idt = np.int32
+    factr = ftol / np.finfo(float).eps
+
+    def stencils(xs):
+        """(f, g) at every x of xs from one population: scipy's '2-point' rule with bounds (the step flips where
+        x + eps leaves the box), PENALTY for failed evaluations -- the arithmetic of Kriging._fun_and_grad."""
+        blocks, hs = [], []
+        for x in xs:
+            h = np.full(n, eps)
+            flip = (x + h > ubv) & (x - h >= lbv)
+            h[flip] = -eps
+            blocks.append(np.vstack([x[None, :], x[None, :] + np.diag(h)]))
+            hs.append(h)
+        f = np.asarray(batch_nll(np.vstack(blocks)))
+        f = np.where(np.isfinite(f), f, PENALTY)
+        out = []
+        for i, (pts, x) in enumerate(zip(blocks, xs)):
+            fi = f[i * (n + 1):(i + 1) * (n + 1)]
+            dx = (pts[1:, :] - x[None, :])[np.arange(n), np.arange(n)]
+            out.append((float(fi[0]), (fi[1:] - fi[0]) / dx))
+        return out
+
+    st = []
+    for r in range(R):
+        x = np.array(np.clip(x0s[r], lbv, ubv), dtype=np.float64)
+        st.append(dict(x=x, x_eval=None, f=np.array(0.0, dtype=np.float64), g=np.zeros(n), nit=0, done=False,
+                       wa=np.zeros(2 * maxcor * n + 5 * n + 11 * maxcor * maxcor + 8 * maxcor), iwa=np.zeros(3 * n, dtype=idt),
+                       task=np.zeros(2, dtype=idt), ln_task=np.zeros(2, dtype=idt), lsave=np.zeros(4, dtype=idt),
+                       isave=np.zeros(44, dtype=idt), dsave=np.zeros(29), cache=None))
+    nbd = np.full(n, 2, dtype=idt)
+    calls = 1
+    # scipy's ScalarFunction evaluates (f, g) at the clipped start point when it is built and answers the routine's
+    # first request from that cache
+    for s_, fg in zip(st, stencils([s_["x"].copy() for s_ in st])):
+        s_["cache"] = (s_["x"].copy(), fg)
+    while True:
+        pending = []
+        for s_ in st:
+            while not s_["done"]:
+                s_["g"] = s_["g"].astype(np.float64)
+                _lbfgsb.setulb(maxcor, s_["x"], lbv, ubv, nbd, s_["f"], s_["g"], factr, gtol, s_["wa"], s_["iwa"],
+                               s_["task"], s_["lsave"], s_["isave"], s_["dsave"], maxls, s_["ln_task"])
+                t0 = s_["task"][0]
+                if t0 == 3:
+                    cx, cfg = s_["cache"]
+                    if np.array_equal(cx, s_["x"]):
+                        s_["f"], s_["g"] = cfg[0], cfg[1]
+                        continue
+                    pending.append(s_)
+                    break
+                elif t0 == 1:
+                    s_["nit"] += 1
+                    if s_["nit"] >= maxiter:
+                        s_["task"][0], s_["task"][1] = 5, 504
+                else:
+                    s_["done"] = True
+        if not pending:
+            break
+        calls += 1
+        for s_, fg in zip(pending, stencils([s_["x"].copy() for s_ in pending])):
+            s_["cache"] = (s_["x"].copy(), fg)
+            s_["f"], s_["g"] = fg[0], fg[1]
+    return np.array([s_["x"] for s_ in st]), np.array([float(s_["f"]) for s_ in st]), calls
+
+
 class Kriging:
     """See the reference docstring (kriging_model.py:16-52) for the KrigInfo keys."""
 
@@ -265,7 +346,13 @@ class Kriging:
         if size > 1:
             K["shard_population"] = False
         device_loop = K["optimizer"].lower() == "cmaes" and K.get("cmaes_device", True) and xhyp.shape[1] <= 64
-        if len(mine) > 1 and K.get("lockstep_restarts", True) and not device_loop:
+        if mine and K["optimizer"].lower() == "lbfgsb" and K.get("lockstep_restarts", True):
+            # L-BFGS-B: every restart's reverse-communication state on this thread, one population per round
+            bx, bf, self.lockstep_calls = lbfgsb_lockstep(
+                lambda P: likelihood_batch(P, K, trainvar=self.trainvar), xhyp[mine, :],
+                np.asarray(K["lbhyp"], dtype=float), np.asarray(K["ubhyp"], dtype=float))
+            bestxcand[mine, :], neglnlikecand[mine] = bx, bf
+        elif len(mine) > 1 and K.get("lockstep_restarts", True) and not device_loop:
             ls = _Lockstep(lambda P: likelihood_batch(P, K, trainvar=self.trainvar), len(mine))
             self._lockstep = ls
             errors = []

@@ -14,9 +14,8 @@ with the inputs resident in HBM; `e2e` is the same metric through the reference-
 Two more blocks ride in the same JSON line:
   `sharded`  STRONG scaling of the splits BASELINE names, at every N: one fixed 64-candidate population split
              b mod N (configs[1]); one fixed 1e8-site Monte-Carlo population split N ways and 20 AK-MCS updates
-             through the AKMCS class with the retraining spread over the ranks (configs[4]); Kriging.train at
-             the configs[2] shape (n=4000, d=20, 231 regressors) with the restarts / stencils spread over the
-             ranks.  Results are compared with a one-GPU evaluation by rank 0 inside the run.
+             through the AKMCS class (configs[4]); Kriging.train at the configs[2] shape (n=4000, d=20, 231
+             regressors) with the lock-step stencil populations of its restarts spread over the ranks.  Results are compared with a one-GPU evaluation by rank 0 inside the run.
   `configs`  (N = 1 only) device-timed throughput + roofline + sampled CPU baseline at the other shapes:
              n=2000 B=64 (the north-star Cholesky target), C3, C4 (KPLS), C5 sweeps n=40 / n=120 / d=40.
 
@@ -434,7 +433,7 @@ def akmcs_run(n_order, maxupdate, shard, cx):
     y = evaluate(X, type="fourbranches")
     K = initkriginfo("single")
     K.update(X=X, y=y, nvar=2, problem="fourbranches", nsamp=12, nrestart=5, ub=ub, lb=lb, optimizer="lbfgsb",
-             kernel=["gaussian"], nugget=-6, shard_restarts=bool(shard))
+             kernel=["gaussian"], nugget=-6)
     krig = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
     krig.train(disp=False)
     pop = mcpopgen_device(type="gaussian", ndim=2, n_order=n_order, n_coeff=1, stddev=1, mean=0, seed=1, shard=shard)
@@ -466,8 +465,10 @@ def akmcs_run(n_order, maxupdate, shard, cx):
 
 def sharded_akmcs(cx, n_order=8, updates=20):
     """configs[4]: ONE 1e8-site Philox population split N ways, resident per GPU; per update one all-reduce of the
-    int64 failure counters + all-gather of the (min U, index) records, the new site broadcast by its owner, the
-    five restarts of the retraining spread over the ranks (KrigInfo['shard_restarts'])."""
+    int64 failure counters + all-gather of the (min U, index) records, the new site broadcast by its owner.  Every
+    rank retrains the 12..32-point model from identical inputs (the five L-BFGS-B restarts advance in lock-step, one
+    15-candidate population per round): a round is one ~0.1 ms latency-bound device call whatever the population, so
+    spreading the restarts over the ranks (KrigInfo['shard_restarts']) would add a collective and save nothing."""
     shard = cx.world > 1
     akmcs_run(5, 2, shard, cx)                    # warm-up: pools, graphs, communicator
     hist, t, t_sweep = akmcs_run(n_order, updates, shard, cx)
@@ -480,7 +481,8 @@ def sharded_akmcs(cx, n_order=8, updates=20):
            "sites_per_s": hist["nsamp"] * (nupd + 1) / t, "Pf": hist["Pf"], "cov": hist["cov"],
            "stop_criterion": hist["stop"], "fail_counters_last": list(hist["counters"][-1][:3]),
            "exchange": "per update: all_reduce(int64[4]) + all_gather of one 32-byte (min, index) record, 16-byte "
-                       "site broadcast, all-gather of the restart results"}
+                       "site broadcast; the retraining is replicated (serial part of the loop: ~35 dependent "
+                       "L-BFGS-B rounds of one latency-bound device call each)"}
     if shard:
         same = None
         if cx.rank == 0:
@@ -496,8 +498,8 @@ def c3_design(n=4000, d=20, seed=11):
     varies on the scale of the box, so the likelihood optimum is INTERIOR to the log10(theta) box."""
     rng = np.random.default_rng(seed)
     X = rng.uniform(-1, 1, (n, d))
-    w = np.linspace(0.5, 1.5, d)
-    y = np.sum(np.sin(2.5 * w * X) + 0.15 * (w * X) ** 3, axis=1) + 0.5 * np.sin(X[:, 0] * X[:, 1] * 3)
+    w = np.linspace(0.8, 1.25, d)
+    y = np.sum(np.sin(4.0 * w * X) + 0.15 * (w * X) ** 3, axis=1) + 0.5 * np.sin(X[:, 0] * X[:, 1] * 3)
     return X, y.reshape(-1, 1)
 
 
@@ -506,12 +508,11 @@ def sharded_train_c3(cx, n=4000, d=20):
     from bayesianopttools_b200.surrogate_models.supports.initinfo import initkriginfo
     X, y = c3_design(n, d)
     K = initkriginfo("single")
-    K.update(X=X, y=y, lb=-np.ones(d), ub=np.ones(d), nrestart=max(2, min(8, cx.world)) if cx.world > 1 else 2,
+    K.update(X=X, y=y, lb=-np.ones(d), ub=np.ones(d), nrestart=2,
              kernel=["gaussian"], nugget=-6, TrendOrder=2, optimizer="lbfgsb", nvar=d, nsamp=n, problem="c3")
-    K["nrestart"] = 2
     if cx.world > 1:
         K["shard_population"] = True             # the 2 x 21-candidate lock-step stencil is split b mod N
-    krig = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False, lb=-2, ub=1)
+    krig = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False, lb=-2, ub=2)
     from bayesianopttools_b200.surrogate_models.supports.likelihood_func import likelihood_batch
     likelihood_batch(np.zeros((2 * (d + 1), d)), K, trainvar=False)      # warm-up: workspace, task queue
     cx.barrier()
@@ -524,7 +525,7 @@ def sharded_train_c3(cx, n=4000, d=20):
                        "restarts in lock-step (42-candidate stencils), candidates b mod N" % (n, d, K["F"].shape[1]),
            "train_s": t, "device_calls": int(getattr(krig, "lockstep_calls", 0)), "nll": float(K["NegLnLike"]),
            "log10_theta_min_max": [float(th.min()), float(th.max())],
-           "interior_optimum": bool(th.min() > -2 + 1e-6 and th.max() < 1 - 1e-6),
+           "interior_optimum": bool(th.min() > -2 + 1e-6 and th.max() < 2 - 1e-6),
            "theta_checksum": float(np.dot(th, np.cos(np.arange(d))))}
     K["_kb"].drop()
     return out
@@ -615,16 +616,24 @@ def cfg_sweep(cx, peak, hbm, fp64_peak, name, n, d, m, acq, cpu_m=20000, reps=3,
     if d >= 10 and n >= 500:
         y = styb(5 * X[:, :10])
         th = np.full(d, 0.3)
+    elif d > 4:                                     # hidimenRA (testcase/RA/testcase.py:81-88): g = d + 0.6 sqrt(d) - sum x
+        X = rng.uniform(0.4, 1.6, (n, d))
+        y = d + 3 * 0.2 * np.sqrt(d) - np.sum(X, axis=1)
+        th = np.full(d, 0.9)
     else:                                           # AK-MCS shapes: a limit state that changes sign over the population
-        y = (d + 3 * 0.2 * np.sqrt(d) - np.sum(2.5 * X, axis=1)) if d > 4 else np.sum(X ** 2, axis=1) - 0.5
-        th = np.full(d, 0.6 if d > 4 else -0.2)
+        y = np.sum(X ** 2, axis=1) - 0.5
+        th = np.full(d, -0.2)
     F = np.ones((n, 1))
     mdl = _lib.DeviceModel(X, y, F, ["gaussian"])
     mdl.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
     mdl.set_norm(_lib.NORM_NONE)
     mdl.set_stream(torch.cuda.current_stream().cuda_stream)
-    pts = _lib.DevicePoints.generate(m, d, dist="gaussian", mean=0.0, stddev=0.4, seed=9) if acq == "u" else \
-        _lib.DevicePoints.generate(m, d, dist="random", lb=-np.ones(d), ub=np.ones(d), seed=9)
+    if acq == "u" and d > 4:
+        pts = _lib.DevicePoints.generate(m, d, dist="lognormal", mean=1.0, stddev=0.2, seed=9)
+    elif acq == "u":
+        pts = _lib.DevicePoints.generate(m, d, dist="gaussian", mean=0.0, stddev=0.4, seed=9)
+    else:
+        pts = _lib.DevicePoints.generate(m, d, dist="random", lb=-np.ones(d), ub=np.ones(d), seed=9)
     res = {}
 
     def go():
@@ -689,7 +698,7 @@ def run_configs(cx):
         lambda: cfg_sweep(cx, peak, hbm, fp64, "sweep n=2000 d=10, 1e6 sites (EI)", 2000, 10, 1_000_000, "ei", cpu_m=4000),
         lambda: cfg_sweep(cx, peak, hbm, fp64, "C5 AK-MCS U sweep n=40 d=2, 1e8 sites", 40, 2, 100_000_000, "u"),
         lambda: cfg_sweep(cx, peak, hbm, fp64, "C5 AK-MCS late model n=120 d=2, 1e8 sites", 120, 2, 100_000_000, "u"),
-        lambda: cfg_sweep(cx, peak, hbm, fp64, "C5 hidimenRA-like n=100 d=40, 2e7 sites", 100, 40, 20_000_000, "u"),
+        lambda: cfg_sweep(cx, peak, hbm, fp64, "C5 hidimenRA n=100 d=40 (lognormal population), 2e7 sites", 100, 40, 20_000_000, "u"),
     ]
     for j in jobs:
         try:

@@ -189,3 +189,39 @@ def test_cmaes_restatement_minimises_known_functions():
     g = lambda X: np.where(X[:, 0] > 0.5, np.inf, np.sum((X + 0.2) ** 2, axis=1))
     r = cmaes_oracle.run(g, np.zeros(3), 1.0, seed=4, maxiter=200)
     assert np.isfinite(r["best_f"]) and r["best_x"][0] <= 0.5 and r["best_f"] < 1e-8
+
+
+def test_lockstep_lbfgsb_driver_equals_scipy_restart_by_restart():
+    """`lbfgsb_lockstep` drives scipy's reverse-communication routine for all restarts on one thread and evaluates
+    their stencils as one population per round (kriging_model.py:358-368, :430 of the reference run the restarts one
+    after another): every restart must end at scipy.optimize.minimize's bit-identical (x*, f*), including a start
+    point outside the box and one that converges to a different basin."""
+    from scipy.optimize import minimize
+    from bayesianopttools_b200.surrogate_models.kriging_model import lbfgsb_lockstep
+    rng = np.random.default_rng(0)
+    n = 6
+    lb, ub = -3 * np.ones(n), 2 * np.ones(n)
+    A = rng.normal(size=(n, n))
+    A = A @ A.T + np.eye(n)
+
+    def batch(P):
+        return np.array([0.5 * p @ A @ p + np.sum(np.sin(3 * p)) + 0.1 * np.sum(p ** 4) for p in P])
+
+    def fg(x, eps=1e-3):
+        h = np.full(n, eps)
+        flip = (x + h > ub) & (x - h >= lb)
+        h[flip] = -eps
+        pts = np.vstack([x[None, :], x[None, :] + np.diag(h)])
+        f = batch(pts)
+        dx = (pts[1:, :] - x[None, :])[np.arange(n), np.arange(n)]
+        return float(f[0]), (f[1:] - f[0]) / dx
+
+    x0s = rng.uniform(-3, 2, (7, n))
+    x0s[3] = ub + 0.5
+    bx, bf, calls = lbfgsb_lockstep(batch, x0s, lb, ub)
+    nfev = []
+    for r in range(len(x0s)):
+        res = minimize(fg, x0s[r], method="L-BFGS-B", jac=True, bounds=np.column_stack((lb, ub)))
+        assert np.array_equal(res.x, bx[r]) and res.fun == bf[r], r
+        nfev.append(res.nfev)
+    assert calls == max(nfev)          # one population per round: as many device calls as the longest restart needs
