@@ -67,6 +67,7 @@ struct KbCholSmem {
   int task;
   int ready;
   int misc[6];
+  unsigned long long poll_ns;   // trace aid: time thread 0 spent polling progress words inside this task's K loop
   int rf[8];          // chain worker: refinement flag of the last finished tile of each home candidate
   int knext[8];       // chain worker: next step of each home candidate
 };
@@ -252,6 +253,70 @@ __device__ __noinline__ void kb_refined_solve_thin(double (*Cs)[KB_LDC], double 
   for (int mi = 0; mi < 2; ++mi)
     *reinterpret_cast<double2*>(&Xg[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
         make_double2(o[mi][0] + dl[mi][0], o[mi][1] + dl[mi][1]);
+}
+
+// ... and for the first 8 * nmi rows of a tile (short tasks, nmi <= 7): warp w owns column block w.
+__device__ __noinline__ void kb_refined_solve_short(double (*Cs)[KB_LDC], double (*Bs)[KB_LDC], const double* Wg,
+                                                    const double* Lg, int ldl, double* Xg, int ld, int nmi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int kmax = 2 * (warp + 1);
+  double o[7][2];
+#pragma unroll
+  for (int mi = 0; mi < 7; ++mi) o[mi][0] = o[mi][1] = 0.0;
+  for (int ks = 0; ks < kmax; ++ks) {
+    const double bf = Bs[warp * 8 + gq][ks * 4 + tq];
+#pragma unroll
+    for (int mi = 0; mi < 7; ++mi)
+      if (mi < nmi) kb_dmma(o[mi][0], o[mi][1], Cs[mi * 8 + gq][ks * 4 + tq], bf);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 7; ++mi)
+    if (mi < nmi)
+      *reinterpret_cast<double2*>(&Xg[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) = make_double2(o[mi][0], o[mi][1]);
+  __syncthreads();
+  kb_load_tile_async(Bs, Lg, ldl);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+  {
+    double p[7][2];
+#pragma unroll
+    for (int mi = 0; mi < 7; ++mi) p[mi][0] = p[mi][1] = 0.0;
+    for (int ks = 0; ks < kmax; ++ks) {
+      const double bf = Bs[warp * 8 + gq][ks * 4 + tq];
+#pragma unroll
+      for (int mi = 0; mi < 7; ++mi)
+        if (mi < nmi) kb_dmma(p[mi][0], p[mi][1], __ldcg(&Xg[(size_t)(mi * 8 + gq) * ld + ks * 4 + tq]), bf);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 7; ++mi)
+      if (mi < nmi) {
+        double2 v = *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]);
+        v.x -= p[mi][0];
+        v.y -= p[mi][1];
+        *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]) = v;
+      }
+  }
+  __syncthreads();
+  kb_load_tile_async(Bs, Wg, KB_TILE);
+  kb_cp_async_commit();
+  kb_cp_async_wait<0>();
+  __syncthreads();
+  double dl[7][2];
+#pragma unroll
+  for (int mi = 0; mi < 7; ++mi) dl[mi][0] = dl[mi][1] = 0.0;
+  for (int ks = 0; ks < kmax; ++ks) {
+    const double bf = Bs[warp * 8 + gq][ks * 4 + tq];
+#pragma unroll
+    for (int mi = 0; mi < 7; ++mi)
+      if (mi < nmi) kb_dmma(dl[mi][0], dl[mi][1], Cs[mi * 8 + gq][ks * 4 + tq], bf);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 7; ++mi)
+    if (mi < nmi)
+      *reinterpret_cast<double2*>(&Xg[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
+          make_double2(o[mi][0] + dl[mi][0], o[mi][1] + dl[mi][1]);
 }
 
 // pivots of a diagonal tile spanning more than this ratio (as max L_ii / min L_ii) switch its column to
@@ -556,6 +621,10 @@ __device__ __forceinline__ void kb_chain_worker(const KbCholArgs& P, KbCholSmem&
 //               MODE 2: thin task: A = 16 rows, B 64 rows, warp w owns column block w
 //               MODE 4: 128-row task (two tile rows i, i+1 against one B row): 32 x 32 per warp,
 //                       16 DMMA per 8 fragment loads, two pipeline stages
+//               MODE 5: short task: the LAST tile row of R when it holds at most 56 live rows (n mod 64 sites plus
+//                       the seated right-hand sides): A = the first 8 * need2 rows only, warp w owns column block w
+//                       (need2 DMMA per need2 + 1 fragment loads).  n = 2000: 24 of 64 rows, n = 1000: 48 -- the
+//                       padding rows of that tile row were 5 % / 3 % of the whole factorisation.
 // ---------------------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restrict__ Arow,
@@ -580,6 +649,11 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
     if (MODE == 2) {
       if (tid < 16 * UPR) {
         const int row = tid / UPR, seg = (tid % UPR) * 2;
+        kb_cp_async16(&as[row * LDK + seg], Arow + (size_t)row * ld + col0 + seg);
+      }
+    } else if (MODE == 5) {
+      for (int idx = tid; idx < (int)need2 * 8 * UPR; idx += KB_THREADS) {
+        const int row = idx / UPR, seg = (idx % UPR) * 2;
         kb_cp_async16(&as[row * LDK + seg], Arow + (size_t)row * ld + col0 + seg);
       }
     } else {
@@ -611,6 +685,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
     const bool poll = (cn < c_end) && (pn >= ready_cols);
     if (poll && tid == 0) {
       int ra, rb, rc;
+      const unsigned long long tp0 = kb_globaltimer();
       while (true) {
         ra = kb_flag_acquire(fa);
         rb = kb_flag_acquire(fb);
@@ -618,6 +693,7 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
         if (ra > pn && rb > pn && rc > pn) break;
         __nanosleep(64);
       }
+      sm.poll_ns += kb_globaltimer() - tp0;
       ra = ra < rb ? ra : rb;
       sm.ready = ra < rc ? ra : rc;
     }
@@ -640,6 +716,18 @@ __device__ __forceinline__ void kb_kloop(KbCholSmem& sm, const double* __restric
         const double bf = bs[warp * 8 + gq][ks * 4 + tq];
         kb_dmma(acc[0][0][0], acc[0][0][1], a0, bf);
         kb_dmma(acc[1][0][0], acc[1][0][1], a1, bf);
+        if (ks == 0) refill();
+      }
+    } else if (MODE == 5) {
+#pragma unroll
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        const double bf = bs[warp * 8 + gq][ks * 4 + tq];
+        double af[7];
+#pragma unroll
+        for (int mi = 0; mi < 7; ++mi) af[mi] = as[mi * 8 + gq][ks * 4 + tq];      // (rows past the live ones: stale, unused)
+#pragma unroll
+        for (int mi = 0; mi < 7; ++mi)
+          if (mi < (int)need2) kb_dmma(acc[mi & 3][mi >> 2][0], acc[mi & 3][mi >> 2][1], af[mi], bf);
         if (ks == 0) refill();
       }
     } else if (MODE == 4) {
@@ -739,12 +827,15 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
     const int b = T.x, ti = T.y, tkc = T.z, type = T.w & 0xff, kstart = T.w >> 8;
     unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
     if (P.trace && tid == 0) tr0 = kb_globaltimer();
+    if (tid == 0) sm.poll_ns = 0;
     double* A = P.aug + (size_t)b * P.g.stride;
     int* fl = P.prog + (size_t)b * NT;
     const bool is_pre = (type == KB_TASK_PRE || type == KB_TASK_PRE_A);
     const bool is_schur = (type == KB_TASK_SCHUR || type == KB_TASK_SCHUR_THIN || type == KB_TASK_SCHUR_THIN_A);
     const bool thin = (type == KB_TASK_THIN || type == KB_TASK_SCHUR_THIN || type == KB_TASK_SCHUR_THIN_A);
     const bool two = (type == KB_TASK_OFF2);
+    const bool shortrow = (type == KB_TASK_OFFS);
+    const int nmi = (P.g.n - (nb - 1) * KB_TILE + (P.g.seated ? P.g.q : 0) + 7) >> 3;    // live 8-row blocks of the last tile row
     const int brow = is_pre ? ti - 1 : tkc;
     const int kend = (type == KB_TASK_PRE_A) ? ti - 2
                      : (is_pre ? ti - 1 : (type == KB_TASK_SCHUR_THIN_A ? nb - 1 : (tkc < nb ? tkc : nb)));
@@ -756,7 +847,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
     const int* fb = &fl[brow];
     // the tile(s) this task updates are read once, after the K loop: pull them towards L2 now
     {
-      const int nrows = thin ? 16 : (two ? 128 : 64);
+      const int nrows = thin ? 16 : (two ? 128 : (shortrow ? nmi * 8 : 64));
       const int lines = (is_pre ? 8 : 4);          // 128-byte lines per row (PRE touches two tiles)
       for (int e = tid; e < nrows * lines; e += KB_THREADS) {
         const double* p = Atile + (size_t)(e / lines) * ld + (e % lines) * 16;
@@ -794,6 +885,8 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
       kb_kloop<2>(sm, Arow, Brow, false, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
     } else if (two) {
       kb_kloop<4>(sm, Arow, Brow, false, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
+    } else if (shortrow) {
+      kb_kloop<5>(sm, Arow, Brow, false, ld, kstart, kend, fa, fa2, fb, ready_cols, (unsigned)nmi, acc);
     } else {
       kb_kloop<0>(sm, Arow, Brow, ti == tkc, ld, kstart, kend, fa, fa2, fb, ready_cols, 0u, acc);
     }
@@ -874,6 +967,39 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
             *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) =
                 make_double2(o[mi][0], o[mi][1]);
         }
+      }
+    } else if (shortrow) {
+      // 8 nmi x 64 strip of the last tile row; warp w owns column block w (the rows below stay the zeros the
+      // correlation build wrote: identity padding)
+      double (*Ds)[KB_LDC] = Cs + KB_TILE;
+      kb_dinv_issue(P, sm, Ds, &fl[tkc], b, tkc);
+#pragma unroll
+      for (int mi = 0; mi < 7; ++mi)
+        if (mi < nmi) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]));
+          *reinterpret_cast<double2*>(&Cs[mi * 8 + gq][warp * 8 + 2 * tq]) =
+              make_double2(v.x - acc[mi & 3][mi >> 2][0], v.y - acc[mi & 3][mi >> 2][1]);
+        }
+      kb_dinv_land();
+      if (P.trace && tid == 0) tr3 = kb_globaltimer();
+      if (KB_REFINE_ON && Ds[0][KB_TILE - 1] != 0.0) {
+        kb_refined_solve_short(Cs, Ds, P.dinv + ((size_t)b * nb + tkc) * (KB_TILE * KB_TILE),
+                               A + (size_t)tkc * KB_TILE * ld + (size_t)tkc * KB_TILE, ld, Atile, ld, nmi);
+      } else {
+        double o[7][2];
+#pragma unroll
+        for (int mi = 0; mi < 7; ++mi) o[mi][0] = o[mi][1] = 0.0;
+        const int kmax = 2 * (warp + 1);
+        for (int ks = 0; ks < kmax; ++ks) {
+          const double bf = Ds[warp * 8 + gq][ks * 4 + tq];
+#pragma unroll
+          for (int mi = 0; mi < 7; ++mi)
+            if (mi < nmi) kb_dmma(o[mi][0], o[mi][1], Cs[mi * 8 + gq][ks * 4 + tq], bf);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 7; ++mi)
+          if (mi < nmi)
+            *reinterpret_cast<double2*>(&Atile[(size_t)(mi * 8 + gq) * ld + warp * 8 + 2 * tq]) = make_double2(o[mi][0], o[mi][1]);
       }
     } else if (two) {
       // 128 x 64: C = A[i..i+1, k] - acc -> shared, one triangular multiply for both tile rows
@@ -973,7 +1099,7 @@ __device__ __forceinline__ void kb_bulk_worker(const KbCholArgs& P, KbCholSmem& 
       unsigned long long* t = P.trace + (size_t)tk * 8;
       t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = tr3; t[4] = kb_globaltimer();
       t[5] = ((unsigned long long)b << 40) | ((unsigned long long)ti << 24) | ((unsigned long long)tkc << 8) | type;
-      t[6] = smid; t[7] = blockIdx.x;
+      t[6] = smid | (sm.poll_ns << 16); t[7] = blockIdx.x;
     }
   }
 }
@@ -1092,13 +1218,19 @@ void kb_chol_build_tasks(const KbAugGeom& g, int B, int num_ctas, std::vector<in
   };
   const int rhs0 = g.nb, id0 = g.nb + g.sb;
   const bool thin_rhs = (g.sb == 1 && g.q <= 16);
+  // the last tile row of R as short tasks when at most 56 of its rows are live (sites + seated right-hand sides)
+  static const char* short_env = getenv("KB_CHOL_SHORT");       // debug aid: 0 = off
+  const int live_last = g.n - (g.nb - 1) * KB_TILE + (g.seated ? g.q : 0);
+  const bool short_last = live_last <= 56 && !(short_env && atoi(short_env) == 0);
+  const int last_type = short_last ? KB_TASK_OFFS : KB_TASK_OFF;
   for (int k = 0; k < g.nb; ++k) {
-    if (k + 2 < g.nb) emit({{k + 2, k, KB_TASK_OFF}});
+    if (k + 2 < g.nb) emit({{k + 2, k, (k + 2 == g.nb - 1) ? last_type : KB_TASK_OFF}});
     std::vector<T3> seg;
     // remaining tile rows of R and the full right-hand-side rows, two tile rows per task
     {
       std::vector<int> rows;
-      for (int i = k + 3; i < g.nb; ++i) rows.push_back(i);
+      for (int i = k + 3; i < g.nb - (short_last ? 1 : 0); ++i) rows.push_back(i);
+      if (short_last && k + 3 <= g.nb - 1) seg.push_back({g.nb - 1, k, KB_TASK_OFFS});
       if (!thin_rhs)
         for (int i = rhs0; i < id0; ++i) rows.push_back(i);
       size_t r = 0;

@@ -13,7 +13,7 @@
 
 // Bulk tile task kinds of the Cholesky task graph (kb_chol.cu); task.w = kind | first K tile column << 8.
 enum { KB_TASK_CHAIN = 0, KB_TASK_OFF = 1, KB_TASK_SCHUR = 2, KB_TASK_PRE = 3, KB_TASK_THIN = 4,
-       KB_TASK_SCHUR_THIN = 5, KB_TASK_OFF2 = 6, KB_TASK_PRE_A = 7, KB_TASK_SCHUR_THIN_A = 8 };
+       KB_TASK_SCHUR_THIN = 5, KB_TASK_OFF2 = 6, KB_TASK_PRE_A = 7, KB_TASK_SCHUR_THIN_A = 8, KB_TASK_OFFS = 9 };
 #define KB_CHOL_CTL_WORDS (8 + 1024)
 
 // Geometry of one augmented matrix  [ R ; rhs rows ]  (row-major, lower tiles only).

@@ -63,6 +63,42 @@ def gather_population_nll(local_nll, B):
     return full, best
 
 
+def gather_sharded_nll(local_nll, local_info, xpop):
+    """ONE all-gather per sharded likelihood call: every rank contributes its NLL slice, its info flags and a
+    (population size, checksum) pair of the population it was handed; the slices are put back into candidate order
+    and the pairs are compared -- every rank must have submitted the same rows (same optimiser state, same seed),
+    otherwise the slices of different populations would be interleaved silently.  Returns (nll[B], info[B])."""
+    rank, size = world()
+    B = len(xpop)
+    local = np.asarray(local_nll, dtype=np.float64)
+    info = np.asarray(local_info)
+    if size == 1:
+        return local, info
+    x = np.ascontiguousarray(xpop, dtype=np.float64)
+    w = np.cos(np.arange(x.size, dtype=np.float64) * 0.7310585786) + 1.5      # position-dependent weights
+    chk = float(np.dot(x.ravel(), w)) if x.size else 0.0
+    if not np.isfinite(chk):
+        chk = float(np.count_nonzero(~np.isfinite(x)))
+    per = (B + size - 1) // size
+    row = np.full(2 * per + 2, np.inf)
+    row[:len(local)] = local
+    row[per:per + len(info)] = info
+    row[2 * per], row[2 * per + 1] = float(B), chk
+    mine = torch.as_tensor(row).to(_comm_device())
+    out = torch.empty(size * len(row), dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    rows = out.cpu().numpy().reshape(size, len(row))
+    if np.any(rows[:, 2 * per] != float(B)) or np.any(rows[:, 2 * per + 1] != chk):
+        raise ValueError("shard_population: the ranks submitted different populations (sizes %s); every rank must run "
+                         "the same deterministic optimiser with the same seed" % sorted(set(rows[:, 2 * per].tolist())))
+    full, flags = np.full(B, np.inf), np.zeros(B, dtype=info.dtype if info.size else np.int32)
+    for r in range(size):
+        idx = candidate_slice(B, r, size)
+        full[idx] = rows[r, :len(idx)]
+        flags[idx] = rows[r, per:per + len(idx)].astype(flags.dtype)
+    return full, flags
+
+
 def merge_results(records):
     """Deterministic merge of per-shard sweep records (dicts with RESULT_FIELDS)."""
     out = dict(records[0])

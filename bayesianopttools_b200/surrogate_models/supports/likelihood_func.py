@@ -31,16 +31,14 @@ def likelihood_batch(xpop, KrigInfo, trainvar=True, return_info=False):
         # optimisers here are deterministic, so ranks that train the same design stay in lockstep).
         from bayesianopttools_b200 import parallel
         rank, size = parallel.world()
-        if size > 1:
-            parallel.assert_same_population(xpop)         # every rank, every call: same collective sequence
         if size > 1 and len(xpop) >= size:
             mine = parallel.candidate_slice(len(xpop), rank, size)
             nll, info = holder.model.nll_batch(xpop[mine], trainvar, fixed_nugget_of(KrigInfo), return_info=True)
-            full, _ = parallel.gather_population_nll(nll, len(xpop))
-            if not return_info:
-                return full
-            flags, _ = parallel.gather_population_nll(info.astype(np.float64), len(xpop))
-            return full, flags.astype(info.dtype)
+            # one collective per call: NLL slices, info flags and the same-population check together
+            full, flags = parallel.gather_sharded_nll(nll, info, xpop)
+            return (full, flags) if return_info else full
+        if size > 1:
+            parallel.assert_same_population(xpop)         # every rank, every call: same collective sequence
     return holder.model.nll_batch(xpop, trainvar, fixed_nugget_of(KrigInfo), return_info=return_info)
 
 

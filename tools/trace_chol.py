@@ -12,7 +12,7 @@ meta = raw[:, 5]
 b, ti, tk, ty = (meta >> 40).astype(int), ((meta >> 24) & 0xffff).astype(int), ((meta >> 8) & 0xffff).astype(int), (meta & 0xff).astype(int)
 end = T[:, 4].max()
 print("records", len(raw), "span %.1f us" % end)
-names = {0: "CHAIN", 1: "OFF", 2: "SCHUR", 3: "PRE", 4: "THIN", 5: "SCHURT", 6: "OFF2", 7: "PRE_A"}
+names = {0: "CHAIN", 1: "OFF", 2: "SCHUR", 3: "PRE", 4: "THIN", 5: "SCHURT", 6: "OFF2", 7: "PRE_A", 8: "SCHURTA", 9: "OFFS"}
 for code, name in names.items():
     m = ty == code
     if not m.any():
@@ -22,11 +22,13 @@ for code, name in names.items():
     dw = np.where(T[m, 3] > 0, T[m, 3] - T[m, 2], 0)
     epi = T[m, 4] - np.where(T[m, 3] > 0, T[m, 3], T[m, 2])
     tot = T[m, 4] - T[m, 0]
+    pollus = (raw[m, 6] >> np.uint64(16)).astype(np.int64) / 1e3 if code != 0 else np.zeros(m.sum())
     print(f"{name:6s} n={m.sum():5d} total {tot.sum()/1e3:8.2f} ms-CTA | mean us: depwait {dep.mean():6.2f} gemm {gemm.mean():6.2f} "
           f"diagwait {dw.mean():6.2f} epilogue {epi.mean():6.2f} | sums ms: dep {dep.sum()/1e3:.2f} gemm {gemm.sum()/1e3:.2f} "
-          f"dw {dw.sum()/1e3:.2f} epi {epi.sum()/1e3:.2f}")
+          f"dw {dw.sum()/1e3:.2f} epi {epi.sum()/1e3:.2f} | polling inside the K loop: {pollus.sum()/1e3:.2f} ms, mean {pollus.mean():.2f} us, tasks with > 5 us: {(pollus > 5).sum()}")
 bulk = ty != 0
 slots = np.unique(raw[bulk, 7])
+raw6 = raw[:, 6] & np.uint64(0xffff)
 busy = (T[bulk, 4] - T[bulk, 0]).sum()
 print("bulk CTAs", len(slots), "busy fraction %.2f" % (busy / (end * len(slots))))
 cb = int(sys.argv[2]) if len(sys.argv) > 2 else 0
