@@ -112,11 +112,14 @@ def merge_results(records):
     return out
 
 
-def gather_sweep_result(local):
+def gather_sweep_result(local, payload=None):
     """Merge one reduction record per rank.  `local` is a dict with RESULT_FIELDS, or a (8,) int64-viewable
     device tensor laid out like KbSweepResult.  The failure counters and the site count are summed with
     `all_reduce` (int64, exact); the two (min, index) pairs are all-gathered and merged with the lowest index
-    winning ties, which is what np.argmin over the whole population returns."""
+    winning ties, which is what np.argmin over the whole population returns.
+    `payload`: a float64 row every rank attaches to its (min U, index) record -- the coordinates of its own best
+    site -- so that the winner's row arrives with the same all-gather (no separate broadcast); the merged dict
+    then carries it as "min_u_payload"."""
     rank, size = world()
     if isinstance(local, torch.Tensor):
         raw = local.view(torch.int64).reshape(8)
@@ -126,25 +129,38 @@ def gather_sweep_result(local):
         vals[[1, 3, 4, 5, 6, 7]] = [local[k] for k in ("best_idx", "min_u_idx", "n_fail", "n_fail_minus",
                                                        "n_fail_plus", "n_points")]
         raw = torch.as_tensor(vals)
+    npay = 0 if payload is None else int(np.size(payload))
+    pays = None
     if size > 1:
         raw = raw.to(_comm_device())
         counts = raw[4:8].clone()
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)               # n_fail, n_fail_minus, n_fail_plus, n_points
         mins = raw[0:4].contiguous()
-        outs = [torch.empty_like(mins) for _ in range(size)]
-        dist.all_gather(outs, mins)
+        if npay:
+            pay = torch.as_tensor(np.ascontiguousarray(payload, dtype=np.float64).reshape(-1).view(np.int64).copy())
+            mins = torch.cat([mins, pay.to(mins.device)])
+        out = torch.empty(size * mins.numel(), dtype=torch.int64, device=mins.device)
+        dist.all_gather_into_tensor(out, mins)
         counts = counts.cpu().numpy()
-        outs = [o.cpu().numpy() for o in outs]
+        rows = out.cpu().numpy().reshape(size, -1)
+        outs = [rows[r, 0:4] for r in range(size)]
+        if npay:
+            pays = [rows[r, 4:].view(np.float64) for r in range(size)]
     else:
         a = raw.cpu().numpy()
         counts, outs = a[4:8], [a[0:4]]
+        if npay:
+            pays = [np.asarray(payload, dtype=np.float64).reshape(-1)]
     recs = []
     for r, a in enumerate(outs):
-        f = a.view(np.float64)
+        f = np.ascontiguousarray(a).view(np.float64)
         recs.append(dict(best_val=float(f[0]), best_idx=int(a[1]), min_u=float(f[2]), min_u_idx=int(a[3]),
                          n_fail=0, n_fail_minus=0, n_fail_plus=0, n_points=0))
     out = merge_results(recs)
     out.update(n_fail=int(counts[0]), n_fail_minus=int(counts[1]), n_fail_plus=int(counts[2]), n_points=int(counts[3]))
+    if pays is not None:
+        win = [r for r, q in enumerate(recs) if q["min_u_idx"] == out["min_u_idx"] and q["min_u"] == out["min_u"]][0]
+        out["min_u_payload"] = np.array(pays[win], dtype=np.float64)
     return out
 
 

@@ -7,10 +7,11 @@ counts.  Here one fused launch returns pred, s and the reductions: #{G<=0},
 
 Several GPUs (BASELINE configs[4]): under torch.distributed every rank holds
 one contiguous shard of the Monte-Carlo population as its `init_samp`, resident on its GPU across
-all updates.  Per update each rank sweeps its shard; one 64-byte record per rank is all-gathered
-(the three failure counters are summed, min U is merged with the lowest whole-population index on
-ties, `parallel.gather_sweep_result`), the rank that owns the new site broadcasts its d
-coordinates, and every rank retrains the (small) model redundantly from identical inputs.
+all updates.  Per update each rank sweeps its shard; the three int64 failure counters are summed with one
+all-reduce, and one all-gather carries every rank's (min U, index) record together with the d coordinates
+of its own lowest-U site (merged with the lowest whole-population index on ties,
+`parallel.gather_sweep_result`), so the new site arrives without a separate broadcast; every rank retrains
+the (small) model redundantly from identical inputs.
 """
 import time
 
@@ -65,10 +66,11 @@ class AKMCS:
             res = dict(res)
             res["min_u_idx"] += self._offset          # indices of the whole population
             res["best_idx"] += self._offset
-            res = parallel.gather_sweep_result(res)
-            owner, local = parallel.owner_of(res["min_u_idx"], self._counts)
-            row = self.init_samp[local, :] if owner == self._rank else None
-            xnew = parallel.broadcast_row(row, owner, self.krigobj.KrigInfo["nvar"])
+            # every rank attaches the coordinates of its own lowest-U site: the winner's arrive with the records
+            mine = int(res["min_u_idx"]) - self._offset
+            row = self.init_samp[mine, :] if 0 <= mine < self.nsamp_local else np.zeros(self.krigobj.KrigInfo["nvar"])
+            res = parallel.gather_sweep_result(res, payload=np.asarray(row, dtype=float))
+            xnew = res.pop("min_u_payload")
         else:
             xnew = self.init_samp[res["min_u_idx"], :]
         self._res = res

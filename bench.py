@@ -480,9 +480,10 @@ def sharded_akmcs(cx, n_order=8, updates=20):
            "sweep_ms_per_update": 1e3 * t_sweep / (nupd + 1), "retrain_and_host_ms_per_update": 1e3 * (t - t_sweep) / max(1, nupd),
            "sites_per_s": hist["nsamp"] * (nupd + 1) / t, "Pf": hist["Pf"], "cov": hist["cov"],
            "stop_criterion": hist["stop"], "fail_counters_last": list(hist["counters"][-1][:3]),
-           "exchange": "per update: all_reduce(int64[4]) + all_gather of one 32-byte (min, index) record, 16-byte "
-                       "site broadcast; the retraining is replicated (serial part of the loop: ~35 dependent "
-                       "L-BFGS-B rounds of one latency-bound device call each)"}
+           "exchange": "per update: all_reduce(int64[4]) of the failure counters + ONE all_gather of the 32-byte "
+                       "(min, index) records with each rank's best site attached (no separate broadcast); the "
+                       "retraining is replicated (serial part of the loop: ~35 dependent L-BFGS-B rounds of one "
+                       "latency-bound device call each)"}
     if shard:
         same = None
         if cx.rank == 0:
