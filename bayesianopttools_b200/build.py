@@ -12,8 +12,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libkrigb200.so")
-SOURCES = ["kb_corr.cu", "kb_chol.cu", "kb_gls.cu", "kb_predict.cu", "kb_rng.cu", "kb_ehvi.cu", "kb_cmaes.cu", "kb_small.cu", "kb_peak.cu", "kb_api.cu"]
-HEADERS = ["kb_common.cuh", "kb_internal.h", "kb_diag.cuh", "kb_philox.cuh", os.path.join("..", "..", "include", "krigb200.h")]
+SOURCES = ["kb_corr.cu", "kb_chol.cu", "kb_gls.cu", "kb_predict.cu", "kb_rng.cu", "kb_ehvi.cu", "kb_cmaes.cu", "kb_small.cu", "kb_peak.cu", "kb_pools.cu", "kb_api.cu", "kb_api_predict.cu", "kb_api_train.cu"]
+HEADERS = ["kb_common.cuh", "kb_internal.h", "kb_diag.cuh", "kb_philox.cuh", "kb_api_internal.h", os.path.join("..", "..", "include", "krigb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
