@@ -59,6 +59,9 @@
 #ifndef KB_EARLY_CLAIM
 #define KB_EARLY_CLAIM 0
 #endif
+#ifndef KB_CHOL_GROUPS_DEFAULT
+#define KB_CHOL_GROUPS_DEFAULT 1     // candidate groups of the staggered queue (kb_chol_stagger)
+#endif
 static_assert(KB_NS128 * (128 + 64) * (KB_KC128 + 4) <= KB_RING_DOUBLES && KB_NS64 * (64 + 64) * (KB_KC64 + 4) <= KB_RING_DOUBLES,
               "pipeline stages must fit in the ring");
 struct KbCholSmem {
@@ -1209,11 +1212,35 @@ size_t kb_chol_sync_words(const KbAugGeom& g, int B) {
 // Bulk task queue: every dependency precedes its user.  Column k holds the tile tasks (i,k),
 // i >= k+2 (the sub-diagonal tile belongs to the chain), with the tile the chain needs next
 // (k+2,k) and the PRE task of row k+2 first.
+// Candidate groups and their stagger.  Every candidate walks the same column sequence; with all of them in
+// lock-step the first and the last columns of the factorisation (little bulk work per chain step) leave the bulk
+// CTAs waiting for the chain workers.  The population is therefore dealt into `groups` groups and group j enters the
+// queue `stagger` tile columns after group j-1: one group's thin columns overlap another group's wide ones.  Any
+// interleaving keeps the queue's invariant (every dependency of a task is earlier in the queue), because tasks of
+// different candidates are independent and each candidate's own order is unchanged.
+static void kb_chol_stagger(const KbAugGeom& g, int B, int* groups, int* stagger) {
+  static const char* g_env = getenv("KB_CHOL_GROUPS");          // debug aids
+  static const char* s_env = getenv("KB_CHOL_STAGGER");
+  int ng = 1, st = 0;
+  if (g.nb >= 8 && B >= 32) { ng = KB_CHOL_GROUPS_DEFAULT; st = g.nb / (2 * ng) > 0 ? g.nb / (2 * ng) : 1; }
+  if (g_env && atoi(g_env) > 0) ng = atoi(g_env);
+  if (s_env && atoi(s_env) >= 0) st = atoi(s_env);
+  if (ng > B) ng = B;
+  if (ng <= 1 || st <= 0) { ng = 1; st = 0; }
+  *groups = ng;
+  *stagger = st;
+}
+
 void kb_chol_build_tasks(const KbAugGeom& g, int B, int num_ctas, std::vector<int4>& out) {
   out.clear();
   struct T3 { int i, k, type; };
+  int ngroups = 1, stagger = 0;
+  kb_chol_stagger(g, B, &ngroups, &stagger);
+  // group j = candidates [B j / ngroups, B (j + 1) / ngroups): the chain workers' home candidates (b = worker + j *
+  // workers) then fall into different groups
+  int b_lo = 0, b_hi = B;
   auto emit = [&](const std::vector<T3>& seg) {
-    for (int b = 0; b < B; ++b)
+    for (int b = b_lo; b < b_hi; ++b)
       for (const T3& t : seg) out.push_back(make_int4(b, t.i, t.k, t.type));
   };
   const int rhs0 = g.nb, id0 = g.nb + g.sb;
@@ -1223,7 +1250,16 @@ void kb_chol_build_tasks(const KbAugGeom& g, int B, int num_ctas, std::vector<in
   const int live_last = g.n - (g.nb - 1) * KB_TILE + (g.seated ? g.q : 0);
   const bool short_last = live_last <= 56 && !(short_env && atoi(short_env) == 0);
   const int last_type = short_last ? KB_TASK_OFFS : KB_TASK_OFF;
-  for (int k = 0; k < g.nb; ++k) {
+  // tile column k of the current group (k == nb: the Schur tiles behind the last column)
+  auto emit_column = [&](int k) {
+    if (k == g.nb) {
+      std::vector<T3> seg;
+      for (int kk = rhs0; kk < id0; ++kk)
+        for (int i = kk; i < id0; ++i)
+          seg.push_back({i, kk, thin_rhs ? (KB_TASK_SCHUR_THIN | (g.nb >= 3 ? (g.nb - 1) << 8 : 0)) : KB_TASK_SCHUR});
+      emit(seg);
+      return;
+    }
     if (k + 2 < g.nb) emit({{k + 2, k, (k + 2 == g.nb - 1) ? last_type : KB_TASK_OFF}});
     std::vector<T3> seg;
     // remaining tile rows of R and the full right-hand-side rows, two tile rows per task
@@ -1254,10 +1290,13 @@ void kb_chol_build_tasks(const KbAugGeom& g, int B, int num_ctas, std::vector<in
     // time the pool gets here its inputs (PRE_A of the previous column, the chain's L[k+1,k]) are
     // in, so it never parks a CTA, and the chain still runs a good part of a column ahead.
     if (k + 2 < g.nb) emit({{k + 2, k, KB_TASK_PRE | (k << 8)}});
-  }
-  std::vector<T3> seg;
-  for (int kk = rhs0; kk < id0; ++kk)
-    for (int i = kk; i < id0; ++i)
-      seg.push_back({i, kk, thin_rhs ? (KB_TASK_SCHUR_THIN | (g.nb >= 3 ? (g.nb - 1) << 8 : 0)) : KB_TASK_SCHUR});
-  emit(seg);
+  };
+  for (int slot = 0; slot <= g.nb + stagger * (ngroups - 1); ++slot)
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const int k = slot - stagger * grp;
+      if (k < 0 || k > g.nb) continue;
+      b_lo = (int)((long long)B * grp / ngroups);
+      b_hi = (int)((long long)B * (grp + 1) / ngroups);
+      emit_column(k);
+    }
 }

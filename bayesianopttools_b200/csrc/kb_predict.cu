@@ -571,26 +571,39 @@ kb_predict_kernel(KbPredictArgs P) {
 #define PW_LDP 36          // padded psi row: 32 sites + 4 (== 4 mod 16 -> conflict-free B fragments)
 #define PW_MAXD 8           // widest design of the 8-warp kernel (128 registers per thread)
 #define PW_MAXD_WIDE 16     // ... of the 4-warp kernel (255 registers per thread): runtime-d loop
+#define PW_MAXD_XWIDE 40    // ... of its extra-wide build (hidimenRA, testcase/RA/testcase.py:81-88: 40 inputs): the lane's
+                            // 40 coordinates still live in registers, two correlation chains per lane
 
 // Up to 64 training sites: 8 warps per CTA, L^-1 as a full k-major matrix, two CTAs per SM.  65 .. 128 sites:
 // 4 warps per CTA (one per SM sub-partition), L^-1 packed as its lower 8x8 blocks, one CTA per SM -- the psi
 // tiles of the warps (n8 x 36 doubles each) are what fills the shared memory.
 static int kb_predict_warp_nw(int n8, int d) { return (n8 <= 64 && d <= PW_MAXD) ? 8 : 4; }
+// Rows of the shared copy of the design (and entries of the weight vectors): the width the kernel build that serves d
+// columns is compiled for.  Runtime-d builds pad to 8 / 16 / 24 / 32 / 40 with zero rows and zero weights, so their
+// dimension loop carries no predicate at all (a per-dimension `dim < d` branch kept the chains of a lane from
+// interleaving: the d = 40 sweep ran at 35 % of the FP64 issue rate).
+__host__ __device__ __forceinline__ int kb_pw_rows(int d) {
+  return d <= 3 ? d : (d <= 8 ? 8 : (d <= 16 ? 16 : ((d + 7) & ~7)));
+}
 static size_t kb_predict_warp_at_doubles(int n8, int nw) {
   const int nrb = n8 >> 3;
   return nw == 8 ? (size_t)n8 * (n8 + 4) : (size_t)(nrb * (nrb + 1) / 2) * 64;
 }
 size_t kb_predict_warp_smem_bytes(int d, int n8, int qx) {
   const int nw = kb_predict_warp_nw(n8, d);
-  return sizeof(double) * ((size_t)d * n8 + 2 * (size_t)d + (size_t)qx * n8 + kb_predict_warp_at_doubles(n8, nw) +
+  const int dr = kb_pw_rows(d);
+  return sizeof(double) * ((size_t)dr * n8 + 2 * (size_t)dr + (size_t)qx * n8 + kb_predict_warp_at_doubles(n8, nw) +
                            nw * (size_t)n8 * PW_LDP + 8 * 32) + sizeof(KbSweepResult) * 8 + 64;
 }
 bool kb_predict_can_warp(int d, int n, int qx, int nind_trend) {
   const int n8 = (n + 7) & ~7;
   static const char* big_env = getenv("KB_PW_BIG");       // debug aid: KB_PW_BIG=0 keeps n > 64 on the CTA kernel
   const int nmax = (big_env && atoi(big_env) == 0) ? 64 : 128;
-  const int dmax = (big_env && atoi(big_env) == 0) ? PW_MAXD : PW_MAXD_WIDE;
-  return n8 <= nmax && d <= dmax && nind_trend == 0 && qx == 2 &&
+  static const char* xw_env = getenv("KB_PW_XWIDE");   // debug aid: KB_PW_XWIDE=0 keeps d > 16 on the CTA kernel
+  const int dmax = (big_env && atoi(big_env) == 0) ? PW_MAXD
+                   : ((xw_env && atoi(xw_env) == 0) ? PW_MAXD_WIDE : PW_MAXD_XWIDE);
+  // (from 4 columns up a group's 32 d raw coordinates are transposed through one warp's n8 x PW_LDP psi tile)
+  return n8 <= nmax && d <= dmax && nind_trend == 0 && qx == 2 && (d < 4 || 32 * d <= n8 * PW_LDP) &&
          kb_predict_warp_smem_bytes(d, n8, qx) + 1024 <= 227 * 1024;
 }
 int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
@@ -600,31 +613,46 @@ int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
 // D > 0: the design has exactly D columns (compile-time: the per-dimension weights live in registers, no
 // predicated dimension loop); D = 0: any d <= PW_MAXD.  U = correlation chains in flight per lane.
 // The triangular product takes the 8-row blocks in pairs (6 fragment loads per 8 DMMA instead of 10).
-template <int MASK, int D, int U, int NW>
+template <int MASK, int D, int U, int NW, int DW>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
 kb_predict_warp_kernel(KbPredictArgs P) {
   constexpr bool PACKED = (NW != 8);       // L^-1 as lower 8x8 blocks [rb (rb + 1) / 2 + kb][k % 8][row % 8]
   constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int DD = D ? D : (NW == 8 ? PW_MAXD : PW_MAXD_WIDE);
+  // DD: the width this build is compiled for.  The runtime-d builds (DW = 8, 16, 24, 32, 40 = kb_pw_rows(d)) see
+  // zero rows and zero weights beyond d: no predicate in the dimension loop.  (The host sizes the shared memory for
+  // kb_pw_rows(d) >= DD rows.)
+  constexpr int DD = D ? D : DW;
+  // single-kernel designs: the weight of a dimension is folded into the coordinates once (x sqrt(gw) for the Gaussian,
+  // x / theta otherwise), which leaves a subtract and an FMA (or add) per pair and dimension instead of three
+  constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8);
   const int n = P.n, d = D ? D : P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
   KbSweepResult* red = reinterpret_cast<KbSweepResult*>(smem_raw);
   double* swk = reinterpret_cast<double*>(smem_raw + sizeof(KbSweepResult) * 8);   // [4] (+4 pad)
-  double* XTs = swk + 8;                    // [d][n8]
-  double* sgw = XTs + (size_t)d * n8;       // [d]
-  double* sith = sgw + d;                   // [d]
-  double* exts = sith + d;                  // [2][n8]  alpha | R^-1 1
+  double* XTs = swk + 8;                    // [DD][n8]
+  double* sgw = XTs + (size_t)DD * n8;      // [DD]
+  double* sith = sgw + DD;                  // [DD]
+  double* exts = sith + DD;                 // [2][n8]  alpha | R^-1 1
   double* ATs = exts + 2 * (size_t)n8;      // [n8][n8 + 4]  k-major L^-1, or its packed lower blocks
   double* psiAll = ATs + (PACKED ? (size_t)((n8 >> 3) * ((n8 >> 3) + 1) / 2) * 64 : (size_t)n8 * lda);  // [NW][n8][PW_LDP]
   double* vvAll = psiAll + NW * (size_t)n8 * PW_LDP;   // [NW warps][32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
 
-  for (int e = tid; e < d * n8; e += NTH) {
+  for (int e = tid; e < DD * n8; e += NTH) {
     const int dim = e / n8, k = e - dim * n8;
-    XTs[e] = (k < n) ? P.XT[(size_t)dim * P.n_pad + k] : 0.0;
+    double v = 0.0;
+    if (dim < d && k < n) {
+      v = P.XT[(size_t)dim * P.n_pad + k];
+      if (PRE) v *= (MASK == 1) ? sqrt(P.gw[dim]) : P.ith[dim];
+    }
+    XTs[e] = v;
   }
-  for (int e = tid; e < d; e += NTH) { sgw[e] = P.gw[e]; sith[e] = P.ith[e]; }
+  for (int e = tid; e < DD; e += NTH) {
+    // pre-scaled builds keep the coordinate scale of each dimension in sgw
+    sgw[e] = (e < d) ? (PRE ? ((MASK == 1) ? sqrt(P.gw[e]) : P.ith[e]) : P.gw[e]) : 0.0;
+    sith[e] = (e < d) ? P.ith[e] : 0.0;
+  }
   if (tid < 4) swk[tid] = P.wk[tid];
   for (int e = tid; e < 2 * n8; e += NTH) {
     const int j = e / n8, k = e - j * n8;
@@ -652,32 +680,73 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   const int nrb = n8 >> 3;
   KbRunning run;
   kb_run_init(run);
-  double rgw[DD], rith[DD];                 // D > 0: per-dimension weights in registers
+  // per-dimension weights in registers for the narrow builds (the wide ones read them from shared memory); with
+  // pre-scaled coordinates rgw holds the scale of the site coordinates and rith is unused
+  constexpr bool WREG = (D > 0) || (PRE && DD <= 16);
+  double rgw[WREG ? DD : 1], rith[WREG ? DD : 1];
+  if (WREG) {
 #pragma unroll
-  for (int dim = 0; dim < DD; ++dim) {
-    rgw[dim] = (D && dim < d) ? sgw[dim] : 0.0;
-    rith[dim] = (D && dim < d) ? sith[dim] : 0.0;
+    for (int dim = 0; dim < DD; ++dim) {
+      rgw[dim] = sgw[dim];
+      rith[dim] = sith[dim];
+    }
   }
 
   const long long ngroups = (P.m + 31) / 32;
-  for (long long grp = (long long)blockIdx.x * NW + warp; grp < ngroups; grp += (long long)gridDim.x * NW) {
+  // The raw coordinates of the warp's NEXT 32 sites are requested right after the psi phase, when xv is dead, and land
+  // during the triangular product: with one or two warps per SM sub-partition nothing else hides that global-memory
+  // latency (ncu, n = 100, d = 40: 27 % of the warps' samples sat on the first use of these loads).  From 4 columns up
+  // the 32 d doubles of the group are read as ONE contiguous block (lane l takes elements l, l + 32, ...: full lines per
+  // request instead of 32 sectors of 32 different rows) and transposed through the warp's own psi tile, which is idle
+  // between the product of one group and the psi phase of the next.
+  constexpr bool COAL = (DD >= 4);
+  double xv[DD];
+  auto load_raw = [&](long long g) {
+    if (COAL) {
+      const long long base = g * 32 * d, total = P.m * (long long)d;
+#pragma unroll
+      for (int j = 0; j < DD; ++j) {
+        const long long e = base + j * 32 + lane;
+        xv[j] = (j < d && e < total) ? P.x[e] : 0.0;
+      }
+    } else {
+      const long long st = g * 32 + lane;
+#pragma unroll
+      for (int dim = 0; dim < DD; ++dim) xv[dim] = (dim < d && st < P.m) ? P.x[(size_t)st * d + dim] : 0.0;
+    }
+  };
+  const long long gstride = (long long)gridDim.x * NW;
+  if ((long long)blockIdx.x * NW + warp < ngroups) load_raw((long long)blockIdx.x * NW + warp);
+  for (long long grp = (long long)blockIdx.x * NW + warp; grp < ngroups; grp += gstride) {
     const long long site = grp * 32 + lane;
     const bool valid = site < P.m;
     // ---- this lane's site, standardised ------------------------------------
-    double xv[DD];
+    if (COAL) {
+      double* stg = &psiW[0][0];                 // 32 d <= n8 * PW_LDP doubles (kb_predict_can_warp)
 #pragma unroll
-    for (int dim = 0; dim < DD; ++dim) {
-      double v = 0.0;
-      if (dim < d && valid) {
-        v = P.x[(size_t)site * d + dim];
-        if (P.norm_type == KB_NORM_DEFAULT) {
+      for (int j = 0; j < DD; ++j)
+        if (j < d) stg[j * 32 + lane] = xv[j];
+      __syncwarp();
+#pragma unroll
+      for (int dim = 0; dim < DD; ++dim) xv[dim] = (dim < d) ? stg[lane * d + dim] : 0.0;
+      __syncwarp();
+    }
+    // (sites past the end hold zeros: whatever the maps below make of them stays in their own lane and is dropped)
+    if (P.norm_type == KB_NORM_DEFAULT) {
+#pragma unroll
+      for (int dim = 0; dim < DD; ++dim)
+        if (dim < d) {
           const double lo = P.p0[dim], hi = P.p1[dim];
-          v = ((v - lo) / (hi - lo) - 0.5) * 2.0;
-        } else if (P.norm_type == KB_NORM_STD) {
-          v = (v - P.p0[dim]) / P.p1[dim];
+          xv[dim] = ((xv[dim] - lo) / (hi - lo) - 0.5) * 2.0;
         }
-      }
-      xv[dim] = v;
+    } else if (P.norm_type == KB_NORM_STD) {
+#pragma unroll
+      for (int dim = 0; dim < DD; ++dim)
+        if (dim < d) xv[dim] = (xv[dim] - P.p0[dim]) / P.p1[dim];
+    }
+    if (PRE) {
+#pragma unroll
+      for (int dim = 0; dim < DD; ++dim) xv[dim] *= WREG ? rgw[dim] : sgw[dim];
     }
     // ---- psi column of this site; psi' alpha and 1' R^-1 psi on the way --------
     double ex0 = 0.0, ex1 = 0.0;
@@ -696,8 +765,10 @@ kb_predict_warp_kernel(KbPredictArgs P) {
       for (int dim = 0; dim < DD; ++dim) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (D) kb_pair_dim(acc[u], xv[dim] - XTs[dim * n8 + k + u], rgw[dim], rith[dim], MASK);
-          else if (dim < d) kb_pair_dim(acc[u], xv[dim] - XTs[dim * n8 + k + u], sgw[dim], sith[dim], MASK);
+          const double diff = xv[dim] - XTs[dim * n8 + k + u];
+          if (PRE) kb_pair_dim_scaled(acc[u], diff, MASK);
+          else if (WREG) kb_pair_dim(acc[u], diff, rgw[dim], rith[dim], MASK);
+          else kb_pair_dim(acc[u], diff, sgw[dim], sith[dim], MASK);
         }
       }
 #pragma unroll
@@ -713,6 +784,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
       }
     }
     __syncwarp();
+    if (grp + gstride < ngroups) load_raw(grp + gstride);
     // ---- v = L^-1 psi for the 32 sites, keep the column sums of squares --------
     double sq[4][2];
 #pragma unroll
@@ -840,27 +912,28 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
     default: { constexpr int M_ = 15; CALL; } break;                     \
   }
 
-template <int MASK, int D, int U, int NW>
+template <int MASK, int D, int U, int NW, int DW>
 static cudaError_t kb_predict_warp_launch_w(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U, NW>,
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U, NW, DW>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_warp_kernel<MASK, D, U, NW><<<grid, NW * 32, smem, st>>>(a);
+  kb_predict_warp_kernel<MASK, D, U, NW, DW><<<grid, NW * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
-template <int MASK, int D, int U>
+template <int MASK, int D, int U, int DW = 8>
 static cudaError_t kb_predict_warp_launch_v(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  if (((a.n + 7) & ~7) <= 64 && a.d <= PW_MAXD) return kb_predict_warp_launch_w<MASK, D, U, 8>(st, a, grid, smem);
+  if (((a.n + 7) & ~7) <= 64 && a.d <= PW_MAXD) return kb_predict_warp_launch_w<MASK, D, U, 8, DW>(st, a, grid, smem);
   // one warp per SM sub-partition: twice the correlation chains per lane (registers are plentiful at 128
   // threads; measured +3 % at d = 2, +17 % at d = 6)
-  return kb_predict_warp_launch_w<MASK, D, 2 * U, 4>(st, a, grid, smem);
+  return kb_predict_warp_launch_w<MASK, D, 2 * U, 4, DW>(st, a, grid, smem);
 }
-// The kernel is compiled for every design width it serves (1 .. PW_MAXD; the reliability problems AK-MCS
-// sweeps are 2-D); KB_PW_D=0 forces the runtime-d variant (debug aid).
+// The kernel is compiled for every design width it serves exactly (1 .. PW_MAXD; the reliability problems AK-MCS
+// sweeps are 2-D) and, beyond that, for the padded widths 8 / 16 / 24 / 32 / 40 (kb_pw_rows); KB_PW_D=0 forces the
+// padded runtime-d build for narrow designs too (debug aid).
 template <int MASK>
 static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
   static const char* env_d = getenv("KB_PW_D");
-  const int dsel = (env_d && atoi(env_d) == 0) ? 0 : a.d;
+  const int dsel = (env_d && atoi(env_d) == 0 && a.d > 3) ? 0 : a.d;
   switch (dsel) {
     case 1: return kb_predict_warp_launch_v<MASK, 1, 4>(st, a, grid, smem);
     case 2: return kb_predict_warp_launch_v<MASK, 2, 4>(st, a, grid, smem);
@@ -877,7 +950,17 @@ static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& 
       default: break;
     }
   }
-  return kb_predict_warp_launch_v<MASK, 0, 2>(st, a, grid, smem);
+  // padded runtime-d builds.  A lane's chains are serial over the dimensions (one dependent FMA per dimension), and
+  // with one warp per SM sub-partition nothing else hides that latency: a pass over U pairs issues for 4 U DD cycles
+  // while each chain needs DD FMA latencies, so U = 8 for the single-kernel builds (the composite kernel issues four
+  // times the work per dimension and keeps U = 2 .. 4 within its registers).
+  switch (kb_pw_rows(a.d)) {
+    case 8: return kb_predict_warp_launch_v<MASK, 0, (MASK == 15 ? 2 : 4), 8>(st, a, grid, smem);
+    case 16: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 4 : 8), 4, 16>(st, a, grid, smem);
+    case 24: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, 24>(st, a, grid, smem);
+    case 32: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, 32>(st, a, grid, smem);
+    default: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, PW_MAXD_XWIDE>(st, a, grid, smem);
+  }
 }
 
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {

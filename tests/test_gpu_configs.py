@@ -127,7 +127,11 @@ def test_population_larger_than_chain_workers(lib):
                                         (50, 6, "exponential"), (16, 7, "matern52"),
                                         (120, 2, "gaussian"), (72, 8, "exponential"), (96, 4, "matern32"),
                                         (128, 1, "matern52"), (104, 7, "gaussian"),
-                                        (100, 12, "gaussian"), (64, 16, "matern32"), (128, 10, "exponential")])
+                                        (100, 12, "gaussian"), (64, 16, "matern32"), (128, 10, "exponential"),
+                                        # 17 .. 40 columns: the extra-wide warp-autonomous build (hidimenRA is d = 40);
+                                        # (128, 40) does not fit the shared memory and stays on the resident CTA kernel
+                                        (100, 40, "gaussian"), (60, 17, "matern52"), (96, 33, "exponential"),
+                                        (40, 40, "matern32"), (128, 40, "gaussian"), (104, 24, "gaussian")])
 def test_resident_and_streaming_predictor_agree_with_oracle(lib, n, d, kernel):
     """The three predictor variants around their switch-over points: warp-autonomous (n <= 64, d <= 8;
     two CTAs/SM up to n = 40, one above), shared-memory resident (n_pad <= 128) and streaming
