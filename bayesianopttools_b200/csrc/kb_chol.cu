@@ -59,6 +59,9 @@
 #ifndef KB_EARLY_CLAIM
 #define KB_EARLY_CLAIM 0
 #endif
+#ifndef KB_CHOL_HELPERS_DEFAULT
+#define KB_CHOL_HELPERS_DEFAULT 3    // bulk CTAs run chain steps at the start (1) and at the end (2) of the launch
+#endif
 #ifndef KB_CHOL_GROUPS_DEFAULT
 #define KB_CHOL_GROUPS_DEFAULT 1     // candidate groups of the staggered queue (kb_chol_stagger)
 #endif
@@ -71,8 +74,9 @@ struct KbCholSmem {
   int ready;
   int misc[6];
   unsigned long long poll_ns;   // trace aid: time thread 0 spent polling progress words inside this task's K loop
-  int rf[8];          // chain worker: refinement flag of the last finished tile of each home candidate
-  int knext[8];       // chain worker: next step of each home candidate
+  int knext[8];       // chain worker: next step of each home candidate, as far as this worker knows
+  unsigned long long argbuf[48];   // copy of the kernel arguments for the out-of-line chain step (the kernel's own
+                                   // parameter block stays in the constant bank for the inlined tile tasks)
 };
 static_assert(sizeof(double) * KB_RING_DOUBLES >= sizeof(double) * (3 * KB_TILE * KB_LDC + KB_DIAG_SCRATCH),
               "three padded tiles and the exchange scratch must fit in the pipeline ring");
@@ -338,8 +342,10 @@ struct KbCholArgs {
   int* prog;          // [B][NT]  number of final leading tile columns of each tile row
   int* pre;           // [B][nb]  1 once the PRE task of tile row r has written C1, C2
   int* pre_a;         // [B][nb]  1 once the early part (tile columns < r-2) of that PRE task is in
-  int* ctl;           // [0] bulk queue head, [1] chain-SM tickets, [2] finished chains,
+  int* ctl;           // [0] bulk queue head, [1] chain-SM tickets, [2] finished chains, [3] helper tickets,
                       // [8 + smid] CTA arrivals per SM, [8 + 512 + smid] chain-SM id + 1 or -1
+  int* cstate;        // [B]  chain state of each candidate: 2 k = step k is next, 2 k + 1 = a CTA is running step k
+  int helpers;        // bulk CTAs lend a hand with chain steps at both ends of the launch (kb_chain_helper)
   const int4* tasks;
   int ntasks;
   int B;
@@ -354,7 +360,7 @@ struct KbCholArgs {
 // Chain worker: critical path of its home candidates, round robin, never blocks on a step
 // that is not ready.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& sm, int b, int k, int slot,
+__device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& sm, int b, int k,
                                               unsigned long long* stamps) {
   double* raw = &sm.ring[0];
   double (*C2)[KB_LDC] = reinterpret_cast<double (*)[KB_LDC]>(raw);
@@ -381,7 +387,7 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
     // L[k,k-1] = C1 Dinv_{k-1}^T  -> shared (in place) and global, published at once
     double acc[4][4][2];
     double* Tsub = Tkk - KB_TILE;
-    if (KB_REFINE_ON && sm.rf[slot] != 0) {              // set by this worker's previous step on the same candidate
+    if (KB_REFINE_ON && Dk[0][KB_TILE - 1] != 0.0) {     // flag planted in the stored inverse by the previous step
       // ill-conditioned diagonal tile k-1: residual-corrected solve (writes shared C1 and global Tsub)
       kb_refined_solve<2>(C1, Dk, P.dinv + ((size_t)b * P.g.nb + (k - 1)) * (KB_TILE * KB_TILE),
                           Tkk - (size_t)KB_TILE * ld - KB_TILE, ld, Tsub, ld, C1);
@@ -555,7 +561,6 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
       hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     rf_tile = (P.force_refine > 0 || (P.force_refine == 0 && hi > KB_REFINE_RATIO * lo)) ? 1 : 0;
-    if (lane == 0) sm.rf[slot] = rf_tile;      // this worker's next step on the same candidate reads it
   }
   double* Dg = P.dinv + ((size_t)b * P.g.nb + k) * (KB_TILE * KB_TILE);
   for (int e = tid; e < KB_TILE * KB_TILE / 2; e += KB_THREADS) {
@@ -574,47 +579,126 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
   if (tid == 0) kb_flag_release(&fl[k], k + 1);
 }
 
+// One chain step of candidate b if it is due and nobody else is on it.  With helpers on, the state of a candidate's
+// chain lives in ONE global word, cstate[b] = 2 k (step k is next, nobody on it) or 2 k + 1 (a CTA is running step k),
+// claimed with a compare-and-swap, so that any CTA may run a step: the dedicated chain workers walk their home
+// candidates, and bulk CTAs with nothing else to do help at both ends of the launch (kb_chain_helper), where the
+// chains, not the tile pool, are the critical path.  Without helpers (small populations: every candidate has a worker
+// of its own and the launch is bound by the chain steps' latency) the owner keeps the step in shared memory (khint >= 0
+// is then the step itself) and a step costs one flag round trip, as it always did.
+// kmax: only steps below it (the start-up helpers stop after step 1).  Returns 1 if a step was run, 0 otherwise;
+// *kdone = the candidate's next step afterwards, as far as this CTA knows.
+__device__ __noinline__ int kb_chain_try(const KbCholArgs& P, KbCholSmem& sm, int b, int kmax, int khint, int* kdone) {
+  const int tid = threadIdx.x, nb = P.g.nb;
+  const bool locked = (P.helpers != 0);
+  __syncthreads();
+  if (tid == 0) {
+    int k = khint, go = 0;
+    if (locked) {
+      // the state word and the PRE flag of the step we expect travel together (one round trip when the hint holds)
+      const int hint = khint < nb ? khint : nb - 1;
+      const int pre_hint = (hint <= 1) ? 1 : kb_flag_acquire(&P.pre[(size_t)b * nb + hint]);
+      const int st = kb_flag_acquire(&P.cstate[b]);
+      k = st >> 1;
+      if (!(st & 1) && k < nb && k < kmax) {
+        const int pre_ok = (k <= 1) ? 1 : (k == hint ? pre_hint : kb_flag_acquire(&P.pre[(size_t)b * nb + k]));
+        if (pre_ok != 0 && atomicCAS(&P.cstate[b], 2 * k, 2 * k + 1) == 2 * k) {
+          __threadfence();                                 // acquire side of the previous holder's release
+          go = 1;
+        }
+      }
+    } else if (k < nb && k < kmax) {
+      go = (k <= 1) ? 1 : (kb_flag_acquire(&P.pre[(size_t)b * nb + k]) != 0);
+    }
+    sm.misc[2] = k;
+    sm.ready = go;
+  }
+  __syncthreads();
+  const int k = sm.misc[2];
+  if (kdone) *kdone = k;
+  if (sm.ready == 0) return 0;
+  unsigned long long tr0 = 0;
+  if (P.trace && tid == 0) tr0 = kb_globaltimer();
+  unsigned long long* trec = P.trace ? P.trace + ((size_t)P.ntasks + (size_t)b * nb + k) * 8 : nullptr;
+  kb_chain_step(P, sm, b, k, trec);
+  if (P.trace && tid == 0) {
+    // chain record: start | tiles loaded | sub-diagonal tile published | factor start | end | meta | factor end
+    trec[0] = tr0; trec[4] = kb_globaltimer();
+    trec[5] = ((unsigned long long)b << 40) | ((unsigned long long)k << 24) | ((unsigned long long)k << 8) | 0;
+    trec[7] = blockIdx.x;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (locked) kb_flag_release(&P.cstate[b], 2 * (k + 1));        // cumulative over the CTA barrier above
+    if (k + 1 == nb) atomicAdd(&P.ctl[2], 1);
+  }
+  if (kdone) *kdone = k + 1;
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// Chain worker: critical path of its home candidates, round robin, never blocks on a step
+// that is not ready.
+// ---------------------------------------------------------------------------
 __device__ __forceinline__ void kb_chain_worker(const KbCholArgs& P, KbCholSmem& sm, int wid, int nworkers) {
-  const int tid = threadIdx.x;
-  const int nb = P.g.nb;
-  // home candidates b = wid + j * nworkers (at most 8: the host sizes chain_sms for it); the next step of each
-  // lives in shared memory so that the round-robin loop stays ROLLED: one copy of the (large) step in the
-  // instruction stream instead of eight
-  int nhome = 0;
-  for (int b = wid; b < P.B; b += nworkers) ++nhome;
+  // home candidates b = wid + j * nworkers (at most 8: the host sizes chain_sms for it); the next step of each, as
+  // far as this worker knows, lives in shared memory and the loop stays ROLLED: one copy of the (large) step in the
+  // instruction stream
+  const int tid = threadIdx.x, nb = P.g.nb;
   if (tid < 8) sm.knext[tid] = 0;
   __syncthreads();
-  int done = 0;
-  while (done < nhome) {
-    bool progressed = false;
+  while (true) {
+    bool progressed = false, all_done = true;
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       const int b = wid + j * nworkers;
       if (b >= P.B) break;
-      const int k = sm.knext[j];
-      if (k >= nb) continue;
-      __syncthreads();
-      if (tid == 0) sm.ready = (k <= 1) ? 1 : kb_flag_acquire(&P.pre[(size_t)b * nb + k]);
-      __syncthreads();
-      if (sm.ready == 0) continue;
-      unsigned long long tr0 = 0;
-      if (P.trace && tid == 0) tr0 = kb_globaltimer();
-      unsigned long long* trec = P.trace ? P.trace + ((size_t)P.ntasks + (size_t)b * nb + k) * 8 : nullptr;
-      kb_chain_step(P, sm, b, k, j, trec);
-      if (P.trace && tid == 0) {
-        // chain record: start | tiles loaded | sub-diagonal tile published | factor start | end | meta | factor end
-        trec[0] = tr0; trec[4] = kb_globaltimer();
-        trec[5] = ((unsigned long long)b << 40) | ((unsigned long long)k << 24) | ((unsigned long long)k << 8) | 0;
-        trec[7] = blockIdx.x;
-      }
-      if (tid == 0) sm.knext[j] = k + 1;
-      __syncthreads();
-      if (k + 1 == nb) ++done;
-      progressed = true;
+      const int kh = sm.knext[j];
+      if (kh >= nb) continue;
+      int kd = kh;
+      if (kb_chain_try(P, sm, b, 0x7fffffff, kh, &kd)) progressed = true;
+      if (tid == 0) sm.knext[j] = kd;
+      if (kd < nb) all_done = false;
     }
+    __syncthreads();
+    if (all_done) break;
     if (!progressed) __nanosleep(200);
   }
-  if (tid == 0) atomicAdd(&P.ctl[2], nhome);
+}
+
+// Bulk CTA lending a hand.  phase 0 (start of the launch, before its first tile task): steps 0 and 1 of ONE candidate --
+// they depend on nothing, and 2 B of them on the few chain workers used to keep the whole tile pool waiting for its
+// first inverted diagonal blocks.  phase 1 (tile queue exhausted): any step of any candidate until every chain is done;
+// by then the chains are all that is left and the dedicated workers (two per SM, sharing one FP64 pipe) are the slow
+// way to run them.
+__device__ __forceinline__ void kb_chain_helper(const KbCholArgs& P, KbCholSmem& sm, int phase) {
+  const int tid = threadIdx.x;
+  if (phase == 0) {
+    __syncthreads();
+    if (tid == 0) sm.misc[3] = atomicAdd(&P.ctl[3], 1);
+    __syncthreads();
+    const int t = sm.misc[3];
+    if (t >= P.B) return;
+    // candidates from the far end first: the dedicated workers start with b = worker id
+    const int b = P.B - 1 - t;
+    if (kb_chain_try(P, sm, b, 2, 0, nullptr)) kb_chain_try(P, sm, b, 2, 1, nullptr);
+    return;
+  }
+  int start = blockIdx.x % P.B;
+  while (true) {
+    __syncthreads();
+    if (tid == 0) sm.misc[3] = kb_flag_acquire(&P.ctl[2]);
+    __syncthreads();
+    if (sm.misc[3] >= P.B) break;
+    bool progressed = false;
+#pragma unroll 1
+    for (int i = 0; i < P.B; ++i) {
+      int b = start + i;
+      if (b >= P.B) b -= P.B;
+      if (kb_chain_try(P, sm, b, 0x7fffffff, P.g.nb - 1, nullptr)) { progressed = true; start = b; break; }
+    }
+    if (!progressed) __nanosleep(300);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1112,6 +1196,10 @@ kb_chol_kernel(KbCholArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KbCholSmem& sm = *reinterpret_cast<KbCholSmem*>(smem_raw);
   const int tid = threadIdx.x;
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&P);
+    if (tid < (int)((sizeof(KbCholArgs) + 7) / 8)) sm.argbuf[tid] = src[tid];
+  }
   // ---- role: the first chain_sms SMs to start a CTA host the chain workers ----
   if (tid == 0) {
     unsigned smid;
@@ -1132,17 +1220,26 @@ kb_chol_kernel(KbCholArgs P) {
   }
   __syncthreads();
   const int role = sm.misc[0], slot = sm.misc[1];
+  static_assert(sizeof(KbCholArgs) <= sizeof(sm.argbuf), "argument copy does not fit");
+  KbCholArgs& Ps = *reinterpret_cast<KbCholArgs*>(sm.argbuf);
   if (role > 0) {
     if (slot < P.chain_wps) {
-      kb_chain_worker(P, sm, (role - 1) * P.chain_wps + slot, P.chain_sms * P.chain_wps);
+      kb_chain_worker(Ps, sm, (role - 1) * P.chain_wps + slot, P.chain_sms * P.chain_wps);
     } else {
       // spare CTA on a chain SM: stay off the FP64 pipe until every chain has finished
       if (tid == 0)
         while (kb_flag_acquire(&P.ctl[2]) < P.B) __nanosleep(500);
       __syncthreads();
     }
+    kb_bulk_worker(P, sm);
+    return;
   }
+  // bulk SM: its first CTA helps the chains before its first and after its last tile task (one helper per SM: a
+  // second one would share the FP64 pipe)
+  const bool helper = P.helpers && slot == 0;
+  if (helper && (P.helpers & 1)) kb_chain_helper(Ps, sm, 0);
   kb_bulk_worker(P, sm);
+  if (helper && (P.helpers & 2)) kb_chain_helper(Ps, sm, 1);
 }
 
 cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* aug, double* dinv,
@@ -1159,6 +1256,7 @@ cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* a
   P.prog = sync_words + KB_CHOL_CTL_WORDS;
   P.pre = P.prog + (size_t)B * g.NT;
   P.pre_a = P.pre + (size_t)B * g.nb;
+  P.cstate = P.pre_a + (size_t)B * g.nb;
   static const char* refine_env = getenv("KB_CHOL_REFINE");       // debug aid: 1 everywhere, 0 nowhere
   P.force_refine = refine_env ? (atoi(refine_env) > 0 ? 1 : -1) : 0;
   P.tasks = tasks; P.ntasks = ntasks; P.B = B; P.info = info;
@@ -1178,6 +1276,10 @@ cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* a
   while (csm * wps * 8 < B) ++csm;
   P.chain_sms = csm;
   P.chain_wps = wps;
+  // helpers only where a chain worker serves several candidates: with a worker per candidate the launch is bound by
+  // the latency of the chain steps themselves and the claim protocol would only add to it
+  static const char* help_env = getenv("KB_CHOL_HELPERS");      // debug aid: bit 0 start-up helpers, bit 1 drain helpers
+  P.helpers = help_env ? atoi(help_env) : ((B > csm * wps) ? KB_CHOL_HELPERS_DEFAULT : 0);
   int grid = num_sms * 2;
   static const char* grid_env = getenv("KB_CHOL_CTAS_PER_SM");   // debug aid: 1 or 2
   if (grid_env && atoi(grid_env) == 1) { grid = num_sms; P.chain_wps = 1; }
@@ -1206,7 +1308,7 @@ cudaError_t kb_launch_chol(cudaStream_t st, const KbAugGeom& g, int B, double* a
 }
 
 size_t kb_chol_sync_words(const KbAugGeom& g, int B) {
-  return (size_t)KB_CHOL_CTL_WORDS + (size_t)B * g.NT + 2 * (size_t)B * g.nb;
+  return (size_t)KB_CHOL_CTL_WORDS + (size_t)B * g.NT + 2 * (size_t)B * g.nb + (size_t)B;
 }
 
 // Bulk task queue: every dependency precedes its user.  Column k holds the tile tasks (i,k),
