@@ -472,56 +472,54 @@ __device__ __forceinline__ void kb_chain_step(const KbCholArgs& P, KbCholSmem& s
   kb_diag_factor_inverse(C2, Dk, xch, &P.info[b], k * KB_TILE);
   if (seated_last) {
     __syncthreads();
-    {
-      // Z[j][i] = sum_{t <= i} Y[j][t] Linv[i][t]  (i < nv): four interleaved dot products per thread
-      const int j = tid >> 4, i0 = tid & 15;
-      double z[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int t = 0; t < nv; ++t) {
-        const double yt = Yb[j][t];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + 16 * u;
-          if (t <= i && i < nv) z[u] = fma(yt, Dk[i][t], z[u]);
-        }
+    // Z = Y Linv^T, one step of residual correction (as kb_refined_solve; always: 16 rows cost nothing):
+    //   r = Y - Z L^T,  Z += r Linv^T
+    // as three 16 x 64 x 64 triangular DMMA products -- warp w owns column block w and stops at the diagonal, as in the
+    // thin tile tasks (scalar dot-product loops here used to make the last chain step 12 us longer than the others).
+    // Yb rows 0..15 = Y, 16..31 = Z, 32..47 = r; columns >= nv of Z and r are kept at zero.
+    const int ncb = (nv + 7) >> 3, kmaxw = 2 * (warp + 1), c0 = warp * 8 + 2 * tq;
+    if (warp < ncb) {
+      double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      for (int ks = 0; ks < kmaxw; ++ks) {
+        const double bf = Dk[warp * 8 + gq][ks * 4 + tq];
+        kb_dmma(o[0][0], o[0][1], Yb[gq][ks * 4 + tq], bf);
+        kb_dmma(o[1][0], o[1][1], Yb[8 + gq][ks * 4 + tq], bf);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) Yb[16 + j][i0 + 16 * u] = z[u];
+      for (int mi = 0; mi < 2; ++mi)
+        *reinterpret_cast<double2*>(&Yb[16 + mi * 8 + gq][c0]) = make_double2(o[mi][0], o[mi][1]);
     }
     __syncthreads();
-    {
-      // one step of residual correction (as kb_refined_solve; always: 16 rows cost nothing):
-      //   r = Y - Z L^T  (rows 32..47 of Yb),   Z += r Linv^T
-      const int j = tid >> 4, i0 = tid & 15;
-      double rr[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rr[u] = (i0 + 16 * u < nv) ? Yb[j][i0 + 16 * u] : 0.0;
-      for (int i = 0; i < nv; ++i) {
-        const double zi = Yb[16 + j][i];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = i0 + 16 * u;
-          if (i <= c && c < nv) rr[u] = fma(-zi, C2[c][i], rr[u]);
-        }
+    if (warp < ncb) {
+      double pr[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      const int row = warp * 8 + gq;
+      for (int ks = 0; ks < kmaxw; ++ks) {
+        const int col = ks * 4 + tq;
+        const double bf = (col <= row) ? C2[row][col] : 0.0;      // only the lower triangle of the factor is valid
+        kb_dmma(pr[0][0], pr[0][1], Yb[16 + gq][col], bf);
+        kb_dmma(pr[1][0], pr[1][1], Yb[24 + gq][col], bf);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) Yb[32 + j][i0 + 16 * u] = rr[u];
+      for (int mi = 0; mi < 2; ++mi) {
+        const double2 yv = *reinterpret_cast<const double2*>(&Yb[mi * 8 + gq][c0]);
+        *reinterpret_cast<double2*>(&Yb[32 + mi * 8 + gq][c0]) =
+            make_double2(c0 < nv ? yv.x - pr[mi][0] : 0.0, c0 + 1 < nv ? yv.y - pr[mi][1] : 0.0);
+      }
     }
     __syncthreads();
-    {
-      const int j = tid >> 4, i0 = tid & 15;
-      double z[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) z[u] = Yb[16 + j][i0 + 16 * u];
-      for (int t = 0; t < nv; ++t) {
-        const double rt = Yb[32 + j][t];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + 16 * u;
-          if (t <= i && i < nv) z[u] = fma(rt, Dk[i][t], z[u]);
-        }
+    if (warp < ncb) {
+      double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      for (int ks = 0; ks < kmaxw; ++ks) {
+        const double bf = Dk[warp * 8 + gq][ks * 4 + tq];
+        kb_dmma(o[0][0], o[0][1], Yb[32 + gq][ks * 4 + tq], bf);
+        kb_dmma(o[1][0], o[1][1], Yb[40 + gq][ks * 4 + tq], bf);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) Yb[16 + j][i0 + 16 * u] = z[u];
+      for (int mi = 0; mi < 2; ++mi) {
+        const double2 zv = *reinterpret_cast<const double2*>(&Yb[16 + mi * 8 + gq][c0]);
+        *reinterpret_cast<double2*>(&Yb[16 + mi * 8 + gq][c0]) =
+            make_double2(c0 < nv ? zv.x + o[mi][0] : 0.0, c0 + 1 < nv ? zv.y + o[mi][1] : 0.0);
+      }
     }
     __syncthreads();
     {

@@ -97,7 +97,9 @@ cudaError_t kb_launch_transpose_pad(cudaStream_t st, const double* X, int n, int
 // 64x64 correlation tile.  Thread (tr = tid/16, tc = tid%16) owns rows
 // tr*4 + a (a<4) and columns 2*tc + 32*a2 + e (a2<2, e<2).
 // ---------------------------------------------------------------------------
-template <int MASK>
+// PRE: single-kernel design whose staged coordinates were already multiplied by the dimension's weight (sqrt(gw) for the
+// Gaussian, 1/theta otherwise; kb_pair_dim_scaled): two FP64 operations per pair and dimension instead of three.
+template <int MASK, bool PRE = false>
 __device__ __forceinline__ void kb_corr_tile(const double* __restrict__ sXi, const double* __restrict__ sXj,
                                              int d, const double* __restrict__ sgw,
                                              const double* __restrict__ sith, const double* __restrict__ swk,
@@ -123,8 +125,13 @@ __device__ __forceinline__ void kb_corr_tile(const double* __restrict__ sXi, con
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int a2 = 0; a2 < 2; ++a2) {
-        kb_pair_dim(acc[a][a2][0], xi[a] - xj[a2].x, gw, ith, MASK);
-        kb_pair_dim(acc[a][a2][1], xi[a] - xj[a2].y, gw, ith, MASK);
+        if (PRE) {
+          kb_pair_dim_scaled(acc[a][a2][0], xi[a] - xj[a2].x, MASK);
+          kb_pair_dim_scaled(acc[a][a2][1], xi[a] - xj[a2].y, MASK);
+        } else {
+          kb_pair_dim(acc[a][a2][0], xi[a] - xj[a2].x, gw, ith, MASK);
+          kb_pair_dim(acc[a][a2][1], xi[a] - xj[a2].y, gw, ith, MASK);
+        }
       }
   }
 #pragma unroll
@@ -182,15 +189,27 @@ kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ 
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
     while (ti * (ti + 1) / 2 > t) --ti;
     const int tj = t - ti * (ti + 1) / 2;
+    // single-kernel designs: the staged coordinates are multiplied by the candidate's per-dimension weight once
+    // (128 d products per tile), which takes one of the three FP64 operations out of the 4096 d pair-dimension steps
+    constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8);
     for (int i = threadIdx.x; i < m.d; i += blockDim.x) {
-      sgw[i] = hp.gw[(size_t)b * m.d + i];
-      sith[i] = hp.ith[(size_t)b * m.d + i];
+      const double gwv = hp.gw[(size_t)b * m.d + i], ithv = hp.ith[(size_t)b * m.d + i];
+      sgw[i] = PRE ? ((MASK == 1) ? sqrt(gwv) : ithv) : gwv;
+      sith[i] = ithv;
     }
     if (threadIdx.x < 4) swk[threadIdx.x] = hp.wk[b * 4 + threadIdx.x];
     kb_stage_x_tiles(m.XT, m.n_pad, ti, m.XT, m.n_pad, tj, m.d, sX, bar);
     __syncthreads();
+    if (PRE) {
+      for (int e = threadIdx.x; e < 2 * m.d * KB_TILE; e += blockDim.x) {
+        int dim = e / KB_TILE;
+        if (dim >= m.d) dim -= m.d;
+        sX[e] *= sgw[dim];
+      }
+      __syncthreads();
+    }
     double out[4][2][2];
-    kb_corr_tile<MASK>(sX, sX + m.d * KB_TILE, m.d, sgw, sith, swk, out);
+    kb_corr_tile<MASK, PRE>(sX, sX + m.d * KB_TILE, m.d, sgw, sith, swk, out);
     const double eps = hp.eps[b];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
