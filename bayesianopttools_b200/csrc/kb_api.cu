@@ -304,6 +304,7 @@ void kb_model_destroy(kb_model* m) {
   free_ws(m->fit);
   kb_dev_free(m->XT); kb_dev_free(m->y); kb_dev_free(m->F); kb_dev_free(m->pls); kb_dev_free(m->kpls_dtiles); kb_dev_free(m->kernel_ids_dev);
   kb_dev_free(m->AT); kb_dev_free(m->rt); kb_dev_free(m->dense_tmp); kb_dev_free(m->idx_dev); kb_dev_free(m->p0);
+  kb_dev_free(m->LT); kb_dev_free(m->spread_dev);
   kb_dev_free(m->p1); kb_dev_free(m->psi_scratch); kb_dev_free(m->ex_scratch); kb_dev_free(m->partials);
   kb_dev_free(m->result_dev); kb_dev_free(m->results_dev); kb_dev_free(m->few_scratch);
   g_pinned.put(m->pin_small, m->pin_small_bytes);
@@ -529,9 +530,12 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
   s = run_pipeline(m, m->fit, 1, nbhyp, m->fit.xpop, trainvar, fixed_nugget_log10, m->fit.nll, m->rt);
   if (s != KB_OK) return s;
   CK(kb_launch_fit_extract(m->stream, g, m->fit.aug, m->rt, m->AT, m->ldat));
-  g_launches += 1;
-  double h_nll = 0.0, h_s2 = 0.0, h_nug = 0.0, h_wk[4];
+  if (!m->spread_dev) CK(kb_dev_malloc(&m->spread_dev, sizeof(double) * 2));
+  CK(kb_launch_diag_spread(m->stream, g, m->fit.aug, m->spread_dev));
+  g_launches += 2;
+  double h_nll = 0.0, h_s2 = 0.0, h_nug = 0.0, h_wk[4], h_spread[2] = {1.0, 1.0};
   int h_info = 0;
+  CK(cudaMemcpyAsync(h_spread, m->spread_dev, sizeof(double) * 2, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaMemcpyAsync(&h_nll, m->fit.nll, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaMemcpyAsync(&h_s2, m->fit.sigma2, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaMemcpyAsync(&h_nug, m->fit.hp.nugget, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -542,6 +546,29 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
   if (h_info != 0)
     KB_FAIL(KB_ERR_NOT_PD, "Matrix is not positive definite (pivot %d); the reference raises LinAlgError at "
             "likelihood_func.py:175", h_info);
+  // Pivots reaching down to the nugget (diag L spanning more than KB_PRED_REFINE_SPREAD: dense low-dimensional designs
+  // with smooth kernels) make the predictor's product with the EXPLICIT inverse 5-30x less accurate than the
+  // reference's triangular solve (profiles/r02_emulate_predictor.txt, tools/emulate_predictor.py; below that spread the
+  // two agree to rounding).  Such fits keep a k-major copy of the factor and the sweeps correct the product with one
+  // residual step, v = v0 + W (psi - L v0), at three times the tile stream -- on the strip kernel, whatever the size.
+  // KB_PRED_REFINE = 0 / 1 forces it off / on (debug aid).
+  {
+    static const char* ref_env = getenv("KB_PRED_REFINE");
+    const bool ill = h_spread[0] > 0.0 && h_spread[1] > KB_PRED_REFINE_SPREAD * h_spread[0];
+    const int refine = ref_env ? (atoi(ref_env) > 0 ? 1 : 0) : (ill ? 1 : 0);
+    if (refine) {
+      if (!m->LT) CK(kb_dev_malloc(&m->LT, sizeof(double) * (size_t)g.n_pad * m->ldat));
+      CK(kb_launch_fit_extract_factor(m->stream, g, m->fit.aug, m->LT, m->ldat));
+      // ... and alpha, R^-1 F (formed with the explicit inverse) get one residual step against the factor
+      double* res = nullptr;
+      CK(kb_dev_malloc(&res, sizeof(double) * (size_t)g.q * g.n_pad));
+      CK(kb_launch_fit_refine_extra(m->stream, g, m->fit.aug, m->rt, m->AT, m->LT, m->ldat, res));
+      CK(cudaStreamSynchronize(m->stream));
+      kb_dev_free(res);
+      g_launches += 3;
+    }
+    m->pred_refine = refine;
+  }
   m->sigma2 = h_s2;
   if (sigma2) *sigma2 = h_s2;
   if (nll) *nll = h_nll;

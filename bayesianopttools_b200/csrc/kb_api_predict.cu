@@ -5,10 +5,15 @@
 extern "C" {
 static kb_status ensure_predict_scratch(kb_model* m) {
   const int qx = 1 + m->nind;
-  const int resident = kb_predict_can_warp(m->d, m->n, qx, m->idx_dev ? 1 : 0)
-                           ? 2
-                           : (kb_predict_can_reside(m->d, m->n_pad, qx, m->idx_dev ? 1 : 0) ? 1 : 0);
-  if (m->ex_scratch && resident == m->pred_resident) return KB_OK;
+  // Ill-conditioned fits (kb_fit_state): designs the warp-autonomous kernel serves (n <= 128, ordinary Kriging: the
+  // AK-MCS population sweeps) take its blocked-substitution builds, everything else the strip kernel with the
+  // residual-corrected product (never the few-sites or the resident CTA kernels, which multiply by the explicit inverse).
+  const bool warp_ok = kb_predict_can_warp(m->d, m->n, qx, m->idx_dev ? 1 : 0);
+  const int refine = m->pred_refine ? 1 : 0;
+  const int resident = warp_ok ? 2 : (refine ? 0 : (kb_predict_can_reside(m->d, m->n_pad, qx, m->idx_dev ? 1 : 0) ? 1 : 0));
+  if (m->ex_scratch && resident == m->pred_resident && m->pred_refine_scratch == refine) return KB_OK;
+  CK(cudaStreamSynchronize(m->stream));
+  m->pred_refine_scratch = refine;
   kb_dev_free(m->psi_scratch); kb_dev_free(m->ex_scratch); kb_dev_free(m->partials);
   m->psi_scratch = m->ex_scratch = nullptr; m->partials = nullptr;
   m->pred_resident = resident;
@@ -30,7 +35,9 @@ static kb_status ensure_predict_scratch(kb_model* m) {
     KB_FAIL(KB_ERR_CUDA, "the predictor keeps one 64-site strip and a 16-site training tile per dimension in shared "
                          "memory: d = %d does not fit (limit about 180)", m->d);
   const size_t strip = kb_predict_strip(resident != 0);
-  if (!resident) CK(kb_dev_malloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip));
+  // (refine: a second strip per CTA holds v0)
+  if (!resident)
+    CK(kb_dev_malloc(&m->psi_scratch, sizeof(double) * (size_t)m->pred_grid * m->n_pad * strip * (refine ? 2 : 1)));
   CK(kb_dev_malloc(&m->ex_scratch, sizeof(double) * (size_t)m->pred_grid * qx * strip));
   CK(kb_dev_malloc(&m->partials, sizeof(KbSweepResult) * m->pred_grid));
   return KB_OK;
@@ -63,13 +70,15 @@ kb_status kb_predict_dev(kb_model* m, long long npts, const double* x_dev, long 
   a.psi_scratch = m->psi_scratch; a.ex_scratch = m->ex_scratch; a.qx = 1 + m->nind; a.partials = m->partials;
   a.resident = m->pred_resident;
   a.stage_x = m->pred_stage_x;
+  a.refine = m->pred_refine_scratch;        // (decided in ensure_predict_scratch)
+  a.LT = m->LT;
   // a handful of sites on a large model: spread the single strip over n_pad / 64 CTAs
   static const char* few_env = getenv("KB_PREDICT_FEW");            // debug aid: 0 disables
   const int few_ny = npts <= (long long)KB_FEW_MAX * KB_FEW_MAX_SLICES ? kb_predict_few_slices(npts) : 0;
   // the scratch grows with the slice count; cap it at 256 MB (many regressors on a large design)
   const bool few_fits = few_ny > 0 &&
                         kb_predict_few_scratch_doubles(m->n_pad, a.qx, few_ny) * sizeof(double) <= (256u << 20);
-  if (few_fits && m->pred_resident == 0 && !(few_env && atoi(few_env) == 0)) {
+  if (few_fits && m->pred_resident == 0 && !a.refine && !(few_env && atoi(few_env) == 0)) {
     if (few_ny > m->few_slices) {
       CK(cudaStreamSynchronize(m->stream));
       kb_dev_free(m->few_scratch);

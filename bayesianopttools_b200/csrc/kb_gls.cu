@@ -289,6 +289,90 @@ __global__ void kb_fit_extract_kernel(KbAugGeom g, const double* __restrict__ au
   }
 }
 
+// min / max of the factor's diagonal over the real rows (one warp): the predictor's product with the EXPLICIT inverse
+// loses accuracy against a triangular solve once the pivots reach down to the nugget (kb_api.cu: kb_fit_state).
+__global__ void kb_diag_spread_kernel(KbAugGeom g, const double* __restrict__ aug, double* __restrict__ out2) {
+  double lo = __longlong_as_double(0x7ff0000000000000LL), hi = 0.0;
+  for (int i = threadIdx.x; i < g.n; i += 32) {
+    const double v = aug[(size_t)i * g.ld + i];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (threadIdx.x == 0) { out2[0] = lo; out2[1] = hi; }
+}
+cudaError_t kb_launch_diag_spread(cudaStream_t st, const KbAugGeom& g, const double* aug, double* out2) {
+  kb_diag_spread_kernel<<<1, 32, 0, st>>>(g, aug, out2);
+  return cudaGetLastError();
+}
+
+// Ill-conditioned fits: one residual step on the extra columns of the fit state (alpha = R^-1 (y - F BE) and R^-1 F, the
+// vectors behind the predictor's mean and its trend term), which kb_fit_extract_kernel forms as W^T v with the explicit
+// inverse:  x1 = x0 + W^T (v - L^T x0).  Two launches (phase 0: res = v - L^T x0, phase 1: x1 = x0 + W^T res), one warp per
+// row k, every column j < q in turn; res is [q][n_pad] scratch.
+__global__ void kb_fit_refine_extra_kernel(KbAugGeom g, const double* __restrict__ aug, const double* __restrict__ rt,
+                                           double* __restrict__ AT, const double* __restrict__ LT, int ldat,
+                                           double* __restrict__ res, int phase) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= g.n) return;
+  const int ld = g.ld, n = g.n;
+  const size_t rhs0 = (size_t)g.nb * KB_TILE;
+  for (int j = 0; j < g.q; ++j) {
+    double s = 0.0;
+    if (phase == 0) {
+      const double* v = (j == 0) ? rt : (aug + (rhs0 + j) * ld);
+      const double* Lk = LT + (size_t)k * ldat;                  // Lk[i] = L[i][k]
+      for (int i = (k & ~31) + lane; i < n; i += 32)
+        if (i >= k) s = fma(Lk[i], AT[(size_t)i * ldat + g.n_pad + j], s);
+      s = kb_warp_sum(s);
+      if (lane == 0) res[(size_t)j * g.n_pad + k] = v[k] - s;
+    } else {
+      const double* Ek = AT + (size_t)k * ldat;                  // Ek[i] = W[i][k]
+      const double* r = res + (size_t)j * g.n_pad;
+      for (int i = (k & ~31) + lane; i < n; i += 32)
+        if (i >= k) s = fma(Ek[i], r[i], s);
+      s = kb_warp_sum(s);
+      if (lane == 0) AT[(size_t)k * ldat + g.n_pad + j] += s;
+    }
+  }
+}
+cudaError_t kb_launch_fit_refine_extra(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
+                                       double* AT, const double* LT, int ldat, double* res) {
+  const int wpb = 8;
+  for (int phase = 0; phase < 2; ++phase) {
+    kb_fit_refine_extra_kernel<<<(g.n + wpb - 1) / wpb, wpb * 32, 0, st>>>(g, aug, rt, AT, LT, ldat, res, phase);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// k-major copy of the factor for the residual-corrected predictor: LT[k][i] = L[i][k] (i >= k, both real), 0 elsewhere.
+// 32 x 32 tiles through shared memory (coalesced on both sides).
+__global__ void kb_fit_extract_factor_kernel(KbAugGeom g, const double* __restrict__ aug, double* __restrict__ LT, int ldat) {
+  __shared__ double t[32][33];
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, k = k0 + threadIdx.x;
+    t[r][threadIdx.x] = (i < g.n && k < g.n && k <= i) ? aug[(size_t)i * g.ld + k] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, i = i0 + threadIdx.x;
+    if (k < g.n_pad && i < g.n_pad) LT[(size_t)k * ldat + i] = t[threadIdx.x][r];
+  }
+}
+cudaError_t kb_launch_fit_extract_factor(cudaStream_t st, const KbAugGeom& g, const double* aug, double* LT, int ldat) {
+  dim3 grid((g.n_pad + 31) / 32, (g.n_pad + 31) / 32), block(32, 8);
+  kb_fit_extract_factor_kernel<<<grid, block, 0, st>>>(g, aug, LT, ldat);
+  return cudaGetLastError();
+}
+
 cudaError_t kb_launch_fit_extract(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
                                   double* AT, int ldat) {
   const int wpb = 8;

@@ -88,6 +88,11 @@ cudaError_t kb_launch_gls(cudaStream_t st, const KbAugGeom& g, int B, const doub
                           const double* sigma2_in, double* Mbuf, double* beta, double* sigma2_out,
                           double* nll, int* info, double* rt_out /*[n_pad] or null (B==1)*/,
                           double* lndet_out);
+// pivot spread of a fitted factor (min / max of diag L over the real rows -> out[0], out[1]) and its k-major copy
+cudaError_t kb_launch_diag_spread(cudaStream_t st, const KbAugGeom& g, const double* aug, double* out2);
+cudaError_t kb_launch_fit_refine_extra(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
+                                       double* AT, const double* LT, int ldat, double* res);
+cudaError_t kb_launch_fit_extract_factor(cudaStream_t st, const KbAugGeom& g, const double* aug, double* LT, int ldat);
 cudaError_t kb_launch_fit_extract(cudaStream_t st, const KbAugGeom& g, const double* aug, const double* rt,
                                   double* AT, int ldat);
 
@@ -95,6 +100,9 @@ cudaError_t kb_launch_loocv(cudaStream_t st, int n, int n_pad, int nind, const d
                             const double* LM, const double* y, double* pred);
 
 // --- kb_predict.cu -----------------------------------------------------------
+// max / min of diag L beyond which a fit's sweeps use the residual-corrected product (calibration: below 250 the
+// explicit-inverse product and a triangular solve agree to rounding; at ~1000, pivots at the nugget, they differ 5-30x)
+#define KB_PRED_REFINE_SPREAD 300.0
 struct KbPredictArgs {
   // model
   int n, d, nind, n_pad, kmask;
@@ -134,6 +142,10 @@ struct KbPredictArgs {
   int resident;            // 1: inverse factor and psi strip stay in shared memory (n_pad <= 128);
                            // 2: warp-autonomous variant (n <= 64, d <= 8, ordinary Kriging)
   KbSweepResult* partials; // [grid]
+  // residual-corrected product for ill-conditioned fits (kb_fit_state sets it from the pivot spread of the factor):
+  //   v0 = W psi,  r = psi - L v0,  v = v0 + W r     (W = L^-1 explicit; three passes of the same tile stream)
+  int refine;
+  const double* LT;        // [n_pad][ldat]  k-major factor: LT[k][i] = L[i][k]  (refine only)
 };
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev);
 // few-sites path: slices of KB_FEW_MAX sites on a model that does not fit the resident variants

@@ -162,7 +162,7 @@ __device__ __forceinline__ void kb_result_merge(KbSweepResult& r, const KbSweepR
 //   memory for the life of the CTA, the psi strip never leaves shared memory, the triangular
 //   product runs without a single barrier and its row blocks are dealt to the warps in
 //   boustrophedon order so every warp carries the same number of DMMAs.
-template <int MASK, bool RESIDENT>
+template <int MASK, bool RESIDENT, bool REFINE = false>
 __global__ void __launch_bounds__(256, 2)
 kb_predict_kernel(KbPredictArgs P) {
   // 256 threads, 64-site strips, 2 CTAs/SM (a single 512-thread CTA with 128-site strips was measured
@@ -191,7 +191,9 @@ kb_predict_kernel(KbPredictArgs P) {
   const int gq = lane >> 2, tq = lane & 3;
   const int wr = warp / WCN, wc = warp % WCN;
   const int n = P.n, d = P.d, n_pad = P.n_pad;
-  double* psi = RESIDENT ? nullptr : P.psi_scratch + (size_t)blockIdx.x * n_pad * MT;
+  constexpr bool refine = !RESIDENT && REFINE;     // (a build of its own: the common path keeps its registers)
+  double* psi = RESIDENT ? nullptr : P.psi_scratch + (size_t)blockIdx.x * n_pad * MT * (refine ? 2 : 1);
+  double* vbuf = psi + (size_t)n_pad * MT;        // refine: v0 = W psi of this strip
   double* ex = P.ex_scratch + (size_t)blockIdx.x * P.qx * MT;
   if (RESIDENT) {
     for (int e = tid; e < n_pad * (n_pad / 2); e += NT) {
@@ -379,7 +381,14 @@ kb_predict_kernel(KbPredictArgs P) {
           sq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], sq[ni][1]);
         }
     } else {
-    const int nblk = qin ? (n_pad + PK_BM - 1) / PK_BM : P.nrows / PK_BM;
+    // refine (ill-conditioned fit): three passes of the same tile stream,
+    //   0: v0 = W psi -> vbuf     1: r = psi - L v0 -> psi (in place)     2: v = v0 + W r, sums of squares
+    // (a pass reads only what earlier passes wrote, row block I of pass 1 its own psi rows)
+    const int npass = refine ? 3 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+    const double* Amat = (pass == 1) ? P.LT : P.AT;
+    const double* Bmat = (pass == 1) ? vbuf : psi;
+    const int nblk = (qin || pass > 0) ? (n_pad + PK_BM - 1) / PK_BM : P.nrows / PK_BM;
       // One continuous chunk stream over all row blocks: the ring keeps prefetching the next
       // block's first chunks while the current block drains and runs its (register-only) epilogue.
       auto nch_of = [&](int I) { return (((I + 1) * PK_BM > n_pad) ? n_pad : (I + 1) * PK_BM) / PK_KC; };
@@ -387,8 +396,8 @@ kb_predict_kernel(KbPredictArgs P) {
       // bookkeeping is kept off the address path so the copies issue in the shadow of the DMMAs)
       int Il = 0, cl = 0, ncl = nch_of(0);
       const size_t a_step = (size_t)PK_KC * P.ldat, a_j = (size_t)4 * P.ldat;
-      const double* gA0 = P.AT + (size_t)(tid >> 6) * P.ldat + (tid & 63) * 2;
-      const double* gB0 = psi + (size_t)(tid >> 5) * MT + (tid & 31) * 2;
+      const double* gA0 = Amat + (size_t)(tid >> 6) * P.ldat + (tid & 63) * 2;
+      const double* gB0 = Bmat + (size_t)(tid >> 5) * MT + (tid & 31) * 2;
       const double* gA = gA0;
       const double* gB = gB0;
       const uint32_t sA0 = kb_smem_u32(&sa[0][tid >> 6][(tid & 63) * 2]);
@@ -455,10 +464,30 @@ kb_predict_kernel(KbPredictArgs P) {
         for (int mi = 0; mi < 4; ++mi) {
           const int row = I * PK_BM + wr * 32 + mi * 8 + gq;
           if (row < n_pad) {
+            if (refine && pass < 2) {
   #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              sq[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], sq[ni][0]);
-              sq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], sq[ni][1]);
+              for (int ni = 0; ni < 4; ++ni) {
+                const size_t o = (size_t)row * MT + wc * 32 + ni * 8 + 2 * tq;
+                if (pass == 0) {
+                  *reinterpret_cast<double2*>(&vbuf[o]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                } else {
+                  const double2 pv = __ldcg(reinterpret_cast<const double2*>(&psi[o]));
+                  *reinterpret_cast<double2*>(&psi[o]) = make_double2(pv.x - acc[mi][ni][0], pv.y - acc[mi][ni][1]);
+                }
+              }
+            } else {
+  #pragma unroll
+              for (int ni = 0; ni < 4; ++ni) {
+                double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
+                if (refine) {
+                  const double2 vv0 = __ldcg(reinterpret_cast<const double2*>(
+                      &vbuf[(size_t)row * MT + wc * 32 + ni * 8 + 2 * tq]));
+                  v0 += vv0.x;
+                  v1 += vv0.y;
+                }
+                sq[ni][0] = fma(v0, v0, sq[ni][0]);
+                sq[ni][1] = fma(v1, v1, sq[ni][1]);
+              }
             }
           } else if (!qin) {
             const int j = row - n_pad;
@@ -475,6 +504,7 @@ kb_predict_kernel(KbPredictArgs P) {
       }
       kb_cp_async_wait<0>();
       __syncthreads();
+    }   // pass
     }
     // column sums of squares: reduce over the 8 row-groups of the warp, then over wr
 #pragma unroll
@@ -613,10 +643,16 @@ int kb_predict_warp_ctas_per_sm(int d, int n, int qx) {
 // D > 0: the design has exactly D columns (compile-time: the per-dimension weights live in registers, no
 // predicated dimension loop); D = 0: any d <= PW_MAXD.  U = correlation chains in flight per lane.
 // The triangular product takes the 8-row blocks in pairs (6 fragment loads per 8 DMMA instead of 10).
-template <int MASK, int D, int U, int NW, int DW>
+// SUBST (ill-conditioned fits, KbPredictArgs::refine): v = L^-1 psi by BLOCKED FORWARD SUBSTITUTION instead of the product
+// with the explicit inverse -- 8-row block rb:  v_rb = W_rb,rb (psi_rb - sum_{kb < rb} L_rb,kb v_kb), the off-diagonal
+// blocks from the factor itself and only the 8x8 diagonal blocks of the inverse (well conditioned each); the same DMMA
+// count, v overwrites psi in the warp's tile block by block.  As accurate as the reference's triangular solve
+// (tools/emulate_predictor.py: blk16 / trsv), where the explicit-inverse product is 5-30x further from an 80-bit evaluation
+// once the pivots reach down to the nugget.
+template <int MASK, int D, int U, int NW, int DW, bool SUBST = false>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
 kb_predict_warp_kernel(KbPredictArgs P) {
-  constexpr bool PACKED = (NW != 8);       // L^-1 as lower 8x8 blocks [rb (rb + 1) / 2 + kb][k % 8][row % 8]
+  constexpr bool PACKED = (NW != 8) || SUBST;   // L^-1 as lower 8x8 blocks [rb (rb + 1) / 2 + kb][k % 8][row % 8]
   constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // DD: the width this build is compiled for.  The runtime-d builds (DW = 8, 16, 24, 32, 40 = kb_pw_rows(d)) see
@@ -625,7 +661,10 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   constexpr int DD = D ? D : DW;
   // single-kernel designs: the weight of a dimension is folded into the coordinates once (x sqrt(gw) for the Gaussian,
   // x / theta otherwise), which leaves a subtract and an FMA (or add) per pair and dimension instead of three
-  constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8);
+  // (not in the SUBST builds: differences of pre-scaled coordinates of two nearby sites carry the rounding of the two
+  // products, up to |x| / |x - t| times the error of the plain form -- harmless except on the ill-conditioned fits
+  // those builds exist for)
+  constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8) && !SUBST;
   const int n = P.n, d = D ? D : P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
   KbSweepResult* red = reinterpret_cast<KbSweepResult*>(smem_raw);
   double* swk = reinterpret_cast<double*>(smem_raw + sizeof(KbSweepResult) * 8);   // [4] (+4 pad)
@@ -662,7 +701,10 @@ kb_predict_warp_kernel(KbPredictArgs P) {
     const int k = e / n8, i = e - k * n8;
     if (PACKED) {
       const int rbk = i >> 3, kbk = k >> 3;
-      if (kbk <= rbk) ATs[(size_t)(rbk * (rbk + 1) / 2 + kbk) * 64 + (k & 7) * 8 + (i & 7)] = P.AT[(size_t)k * P.ldat + i];
+      // (SUBST: the diagonal slots hold the inverse's diagonal blocks, the others the FACTOR's blocks)
+      if (kbk <= rbk)
+        ATs[(size_t)(rbk * (rbk + 1) / 2 + kbk) * 64 + (k & 7) * 8 + (i & 7)] =
+            (SUBST && kbk < rbk) ? P.LT[(size_t)k * P.ldat + i] : P.AT[(size_t)k * P.ldat + i];
     } else {
       ATs[(size_t)k * lda + i] = P.AT[(size_t)k * P.ldat + i];
     }
@@ -790,6 +832,40 @@ kb_predict_warp_kernel(KbPredictArgs P) {
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) sq[cb][0] = sq[cb][1] = 0.0;
     int rb = 0;
+    if (SUBST) {
+      for (; rb < nrb; ++rb) {
+        double acc[4][2];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
+        for (int ks = 0; ks < 2 * rb; ++ks) {             // sum_{kb < rb} L_rb,kb v_kb  (rows < 8 rb of the tile hold v)
+          const double af = a_frag(rb, ks);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {                  // right-hand side of the block, in place
+          double2* pr = reinterpret_cast<double2*>(&psiW[rb * 8 + gq][cb * 8 + 2 * tq]);
+          const double2 pv = *pr;
+          *pr = make_double2(pv.x - acc[cb][0], pv.y - acc[cb][1]);
+          acc[cb][0] = acc[cb][1] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 2 * rb; ks < 2 * rb + 2; ++ks) {    // v_rb = W_rb,rb rhs
+          const double af = a_frag(rb, ks);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          *reinterpret_cast<double2*>(&psiW[rb * 8 + gq][cb * 8 + 2 * tq]) = make_double2(acc[cb][0], acc[cb][1]);
+          sq[cb][0] = fma(acc[cb][0], acc[cb][0], sq[cb][0]);
+          sq[cb][1] = fma(acc[cb][1], acc[cb][1], sq[cb][1]);
+        }
+        __syncwarp();
+      }
+    }
     {
       // two 8-row blocks per pass: the psi fragments of a k-step serve both
       for (; rb + 1 < nrb; rb += 2) {
@@ -894,12 +970,12 @@ __global__ void kb_sweep_final_kernel(const KbSweepResult* __restrict__ partials
   }
 }
 
-template <int MASK, bool RESIDENT>
+template <int MASK, bool RESIDENT, bool REFINE = false>
 static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kb_predict_kernel<MASK, RESIDENT>,
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_kernel<MASK, RESIDENT, REFINE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_kernel<MASK, RESIDENT><<<grid, 256, smem, st>>>(a);
+  kb_predict_kernel<MASK, RESIDENT, REFINE><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -912,35 +988,36 @@ static cudaError_t kb_predict_launch(cudaStream_t st, const KbPredictArgs& a, in
     default: { constexpr int M_ = 15; CALL; } break;                     \
   }
 
-template <int MASK, int D, int U, int NW, int DW>
+template <int MASK, int D, int U, int NW, int DW, bool SUBST = false>
 static cudaError_t kb_predict_warp_launch_w(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U, NW, DW>,
+  cudaError_t e = cudaFuncSetAttribute(kb_predict_warp_kernel<MASK, D, U, NW, DW, SUBST>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kb_predict_warp_kernel<MASK, D, U, NW, DW><<<grid, NW * 32, smem, st>>>(a);
+  kb_predict_warp_kernel<MASK, D, U, NW, DW, SUBST><<<grid, NW * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
-template <int MASK, int D, int U, int DW = 8>
+template <int MASK, int D, int U, int DW = 8, bool SUBST = false>
 static cudaError_t kb_predict_warp_launch_v(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
-  if (((a.n + 7) & ~7) <= 64 && a.d <= PW_MAXD) return kb_predict_warp_launch_w<MASK, D, U, 8, DW>(st, a, grid, smem);
+  if (((a.n + 7) & ~7) <= 64 && a.d <= PW_MAXD) return kb_predict_warp_launch_w<MASK, D, U, 8, DW, SUBST>(st, a, grid, smem);
   // one warp per SM sub-partition: twice the correlation chains per lane (registers are plentiful at 128
   // threads; measured +3 % at d = 2, +17 % at d = 6)
-  return kb_predict_warp_launch_w<MASK, D, 2 * U, 4, DW>(st, a, grid, smem);
+  return kb_predict_warp_launch_w<MASK, D, 2 * U, 4, DW, SUBST>(st, a, grid, smem);
 }
 // The kernel is compiled for every design width it serves exactly (1 .. PW_MAXD; the reliability problems AK-MCS
 // sweeps are 2-D) and, beyond that, for the padded widths 8 / 16 / 24 / 32 / 40 (kb_pw_rows); KB_PW_D=0 forces the
-// padded runtime-d build for narrow designs too (debug aid).
-template <int MASK>
-static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+// padded runtime-d build for narrow designs too (debug aid).  Ill-conditioned fits (a.refine) take the blocked-substitution
+// builds: exact for 1 .. 3 columns (the dense low-dimensional designs where it happens), padded beyond.
+template <int MASK, bool SUBST>
+static cudaError_t kb_predict_warp_launch_s(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
   static const char* env_d = getenv("KB_PW_D");
   const int dsel = (env_d && atoi(env_d) == 0 && a.d > 3) ? 0 : a.d;
   switch (dsel) {
-    case 1: return kb_predict_warp_launch_v<MASK, 1, 4>(st, a, grid, smem);
-    case 2: return kb_predict_warp_launch_v<MASK, 2, 4>(st, a, grid, smem);
-    case 3: return kb_predict_warp_launch_v<MASK, 3, 4>(st, a, grid, smem);
+    case 1: return kb_predict_warp_launch_v<MASK, 1, 4, 8, SUBST>(st, a, grid, smem);
+    case 2: return kb_predict_warp_launch_v<MASK, 2, 4, 8, SUBST>(st, a, grid, smem);
+    case 3: return kb_predict_warp_launch_v<MASK, 3, 4, 8, SUBST>(st, a, grid, smem);
     default: break;
   }
-  if constexpr (MASK != 15) {       // composite kernels carry both weight sets: wider designs would spill
+  if constexpr (MASK != 15 && !SUBST) {       // composite kernels carry both weight sets: wider designs would spill
     switch (dsel) {
       case 4: return kb_predict_warp_launch_v<MASK, 4, 4>(st, a, grid, smem);
       case 5: return kb_predict_warp_launch_v<MASK, 5, 2>(st, a, grid, smem);
@@ -955,12 +1032,17 @@ static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& 
   // while each chain needs DD FMA latencies, so U = 8 for the single-kernel builds (the composite kernel issues four
   // times the work per dimension and keeps U = 2 .. 4 within its registers).
   switch (kb_pw_rows(a.d)) {
-    case 8: return kb_predict_warp_launch_v<MASK, 0, (MASK == 15 ? 2 : 4), 8>(st, a, grid, smem);
-    case 16: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 4 : 8), 4, 16>(st, a, grid, smem);
-    case 24: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, 24>(st, a, grid, smem);
-    case 32: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, 32>(st, a, grid, smem);
-    default: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, PW_MAXD_XWIDE>(st, a, grid, smem);
+    case 8: return kb_predict_warp_launch_v<MASK, 0, (MASK == 15 ? 2 : 4), 8, SUBST>(st, a, grid, smem);
+    case 16: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 4 : 8), 4, 16, SUBST>(st, a, grid, smem);
+    case 24: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, 24, SUBST>(st, a, grid, smem);
+    case 32: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, 32, SUBST>(st, a, grid, smem);
+    default: return kb_predict_warp_launch_w<MASK, 0, (MASK == 15 ? 2 : 8), 4, PW_MAXD_XWIDE, SUBST>(st, a, grid, smem);
   }
+}
+template <int MASK>
+static cudaError_t kb_predict_warp_launch(cudaStream_t st, const KbPredictArgs& a, int grid, size_t smem) {
+  return a.refine ? kb_predict_warp_launch_s<MASK, true>(st, a, grid, smem)
+                  : kb_predict_warp_launch_s<MASK, false>(st, a, grid, smem);
 }
 
 cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid, KbSweepResult* result_dev) {
@@ -971,6 +1053,8 @@ cudaError_t kb_launch_predict(cudaStream_t st, const KbPredictArgs& a, int grid,
     KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_warp_launch<M_>(st, a, grid, smem)));
   } else if (a.resident) {
     KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, true>(st, a, grid, smem)));
+  } else if (a.refine) {
+    KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, false, true>(st, a, grid, smem)));
   } else {
     KB_DISPATCH_MASK_P(a.kmask, (err = kb_predict_launch<M_, false>(st, a, grid, smem)));
   }

@@ -18,6 +18,7 @@ KERNELS = ["gaussian", "exponential", "matern32", "matern52"]
 worst = dict(nll=0.0, pred=0.0, ssqr=0.0)
 fails = narb = 0
 arb = dict(nll=[], pred=[], ssqr=[])
+failq = dict(nll=0, pred=0, ssqr=0, flags=0)
 for case in range(ncases):
     n = int(rng.choice([rng.integers(2, 70), rng.integers(60, 140), rng.integers(120, 420), rng.integers(400, 900)]))
     d = int(rng.integers(1, 9))
@@ -75,6 +76,7 @@ for case in range(ncases):
         status, extra = "ok", ""
         if bad_flags:
             status = "FAIL"
+            failq["flags"] += 1
         if e_nll >= 1e-9 and ok.any():
             rel = np.where(ok, np.abs(nll - ref) / np.abs(ref), 0.0)
             bw = int(np.argmax(rel))
@@ -82,6 +84,7 @@ for case in range(ncases):
             eg, eo = abs(nll[bw] - t) / abs(t), abs(ref[bw] - t) / abs(t)
             extra += f" | nll vs 80-bit: gpu {eg:.1e} lapack {eo:.1e}"
             arb["nll"].append((eg, eo))
+            failq["nll"] += eg > max(1e-9, 3 * eo)
             status = "FAIL" if eg > max(1e-9, 3 * eo) else ("ok(arbitrated)" if status == "ok" else status)
         if (e_pred >= 1e-9 or e_ssqr >= 1e-9) and b is not None:
             tf = lt.nll(xpop[b], X, y, F, kernels=tuple(kern), trainvar=trainvar, fixed_nugget=-6.0, full=True)
@@ -92,6 +95,7 @@ for case in range(ncases):
                 extra += f" | {k} vs 80-bit: gpu {eg:.1e} lapack {eo:.1e}"
                 arb[k].append((eg, eo))
                 if e >= 1e-9:
+                    failq[k] += eg > max(1e-9, 3 * eo)
                     status = "FAIL" if eg > max(1e-9, 3 * eo) else ("ok(arbitrated)" if status == "ok" else status)
         fails += status == "FAIL"
         narb += status == "ok(arbitrated)"
@@ -100,7 +104,8 @@ for case in range(ncases):
         fails += 1
         print(f"EXC {tag}: {type(ex).__name__}: {ex}", flush=True)
 print("worst GPU-vs-LAPACK difference:", {k: f"{v:.1e}" for k, v in worst.items()}, "| cases beyond 1e-9 settled by the 80-bit evaluation:", narb,
-      "| failures:", fails)
+      "| failures:", fails, "| by quantity (further from the 80-bit value than max(1e-9, 3 x LAPACK's distance)):",
+      {k: int(v) for k, v in failq.items()})
 for k, v in arb.items():
     if v:
         a = np.array(v)
