@@ -17,6 +17,7 @@ OUT_IDS = {"pred": 0, "ssqr": 1, "s": 2, "ei": 3, "poi": 4, "pof": 5, "lcb": 6, 
            "fpc": 9}
 OUT_COUNT = 10
 NORM_DEFAULT, NORM_STD, NORM_NONE = 0, 1, 2
+REFINE_AUTO, REFINE_OFF, REFINE_ON = -1, 0, 1
 YMAP_NONE, YMAP_DEFAULT, YMAP_STD = 0, 1, 2
 TYPE_KRIGING, TYPE_KPLS = 0, 1
 ERR_NOT_PD = 4
@@ -73,6 +74,8 @@ _SIGNATURES = [
                                c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("kb_model_set_trend", C.c_int, [C.c_void_p, c_int_p, C.c_int, C.c_int]),
     ("kb_model_set_norm", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    ("kb_model_set_predict_refine", C.c_int, [C.c_void_p, C.c_int]),
+    ("kb_model_predict_refined", C.c_int, [C.c_void_p]),
     ("kb_model_set_ymap", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     ("kb_predict", C.c_int, [C.c_void_p, C.c_longlong, c_double_p, C.POINTER(AcqParams),
                              C.POINTER(c_double_p), C.c_int, C.POINTER(SweepResult)]),
@@ -267,6 +270,18 @@ class DeviceModel:
         self.fitted = True
         return dict(U=U, Psi=Psi, BE=BE.reshape(-1, 1), SigmaSqr=s2.value, NegLnLike=nll.value,
                     nugget=nug.value, wgkf=wg)
+
+    def set_predict_refine(self, mode):
+        """Corrected sweeps on ill-conditioned fits: 'auto' (default: fits whose pivots reach down to the nugget),
+        False / 0 (always the plain explicit-inverse product) or True / 1.  Takes effect at the next fit_state."""
+        code = {"auto": REFINE_AUTO, None: REFINE_AUTO, False: REFINE_OFF, True: REFINE_ON, 0: REFINE_OFF, 1: REFINE_ON,
+                -1: REFINE_AUTO}[mode]
+        check(self._lib.kb_model_set_predict_refine(self._h, code))
+
+    @property
+    def predict_refined(self):
+        """Whether the last fit_state chose the corrected sweeps."""
+        return bool(self._lib.kb_model_predict_refined(self._h))
 
     def set_trend(self, idx):
         """Trend multi-index (nind x d).  The reference-facing layer calls this before every prediction;

@@ -555,7 +555,8 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
   {
     static const char* ref_env = getenv("KB_PRED_REFINE");
     const bool ill = h_spread[0] > 0.0 && h_spread[1] > KB_PRED_REFINE_SPREAD * h_spread[0];
-    const int refine = ref_env ? (atoi(ref_env) > 0 ? 1 : 0) : (ill ? 1 : 0);
+    const int refine = ref_env ? (atoi(ref_env) > 0 ? 1 : 0)
+                               : (m->pred_refine_mode >= 0 ? (m->pred_refine_mode > 0 ? 1 : 0) : (ill ? 1 : 0));
     if (refine) {
       if (!m->LT) CK(kb_dev_malloc(&m->LT, sizeof(double) * (size_t)g.n_pad * m->ldat));
       CK(kb_launch_fit_extract_factor(m->stream, g, m->fit.aug, m->LT, m->ldat));
@@ -601,6 +602,14 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
   m->fitted = true;
   return KB_OK;
 }
+
+kb_status kb_model_set_predict_refine(kb_model* m, int mode) {
+  if (!m || mode < KB_REFINE_AUTO || mode > KB_REFINE_ON) KB_FAIL(KB_ERR_INVALID, "bad argument");
+  m->pred_refine_mode = mode;
+  return KB_OK;
+}
+
+int kb_model_predict_refined(const kb_model* m) { return (m && m->fitted) ? m->pred_refine : 0; }
 
 kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d) {
   if (!m || !idx || nind != m->nind || d != m->d) KB_FAIL(KB_ERR_INVALID, "trend index shape mismatch");

@@ -213,6 +213,7 @@ struct kb_model {
   double* LT = nullptr;            // k-major copy of the factor, kept only for ill-conditioned fits (pred_refine)
   double* spread_dev = nullptr;    // [2] min / max of diag L of the last fit
   int pred_refine = 0;             // the predictor corrects its explicit-inverse product with one residual step
+  int pred_refine_mode = -1;       // KB_REFINE_AUTO / OFF / ON (kb_model_set_predict_refine)
   int pred_refine_scratch = 0;     // ... and the scratch was sized for it
   double* rt = nullptr;
   double* dense_tmp = nullptr;   // n x n staging for U / Psi export

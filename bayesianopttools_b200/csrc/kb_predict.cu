@@ -833,6 +833,55 @@ kb_predict_warp_kernel(KbPredictArgs P) {
     for (int cb = 0; cb < 4; ++cb) sq[cb][0] = sq[cb][1] = 0.0;
     int rb = 0;
     if (SUBST) {
+      // finish one 8-row block: right-hand side psi_rb - acc (in place), v_rb = W_rb,rb rhs, v_rb over psi_rb, squares
+      auto finish = [&](int r8, double (&acc)[4][2]) {
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          double2* pr = reinterpret_cast<double2*>(&psiW[r8 * 8 + gq][cb * 8 + 2 * tq]);
+          const double2 pv = *pr;
+          *pr = make_double2(pv.x - acc[cb][0], pv.y - acc[cb][1]);
+          acc[cb][0] = acc[cb][1] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 2 * r8; ks < 2 * r8 + 2; ++ks) {
+          const double af = a_frag(r8, ks);                 // diagonal slot: the inverse's 8x8 block
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          *reinterpret_cast<double2*>(&psiW[r8 * 8 + gq][cb * 8 + 2 * tq]) = make_double2(acc[cb][0], acc[cb][1]);
+          sq[cb][0] = fma(acc[cb][0], acc[cb][0], sq[cb][0]);
+          sq[cb][1] = fma(acc[cb][1], acc[cb][1], sq[cb][1]);
+        }
+        __syncwarp();
+      };
+      // two row blocks per pass share the v fragments of the columns left of both (as the plain product does); the
+      // second one then takes the first one's fresh v_rb through the factor's block (rb + 1, rb)
+      for (; rb + 1 < nrb; rb += 2) {
+        double acc0[4][2], acc1[4][2];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) acc0[cb][0] = acc0[cb][1] = acc1[cb][0] = acc1[cb][1] = 0.0;
+        for (int ks = 0; ks < 2 * rb; ++ks) {
+          const double a0 = a_frag(rb, ks), a1 = a_frag(rb + 1, ks);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            const double bf = psiW[ks * 4 + tq][cb * 8 + gq];
+            kb_dmma(acc0[cb][0], acc0[cb][1], a0, bf);
+            kb_dmma(acc1[cb][0], acc1[cb][1], a1, bf);
+          }
+        }
+        finish(rb, acc0);
+#pragma unroll
+        for (int ks = 2 * rb; ks < 2 * rb + 2; ++ks) {
+          const double a1 = a_frag(rb + 1, ks);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) kb_dmma(acc1[cb][0], acc1[cb][1], a1, psiW[ks * 4 + tq][cb * 8 + gq]);
+        }
+        finish(rb + 1, acc1);
+      }
       for (; rb < nrb; ++rb) {
         double acc[4][2];
 #pragma unroll
@@ -842,28 +891,7 @@ kb_predict_warp_kernel(KbPredictArgs P) {
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
         }
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {                  // right-hand side of the block, in place
-          double2* pr = reinterpret_cast<double2*>(&psiW[rb * 8 + gq][cb * 8 + 2 * tq]);
-          const double2 pv = *pr;
-          *pr = make_double2(pv.x - acc[cb][0], pv.y - acc[cb][1]);
-          acc[cb][0] = acc[cb][1] = 0.0;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int ks = 2 * rb; ks < 2 * rb + 2; ++ks) {    // v_rb = W_rb,rb rhs
-          const double af = a_frag(rb, ks);
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb) kb_dmma(acc[cb][0], acc[cb][1], af, psiW[ks * 4 + tq][cb * 8 + gq]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          *reinterpret_cast<double2*>(&psiW[rb * 8 + gq][cb * 8 + 2 * tq]) = make_double2(acc[cb][0], acc[cb][1]);
-          sq[cb][0] = fma(acc[cb][0], acc[cb][0], sq[cb][0]);
-          sq[cb][1] = fma(acc[cb][1], acc[cb][1], sq[cb][1]);
-        }
-        __syncwarp();
+        finish(rb, acc);
       }
     }
     {

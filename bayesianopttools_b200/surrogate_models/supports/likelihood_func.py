@@ -58,6 +58,7 @@ def likelihood(x, KrigInfo, mode="default", trainvar=True):
             raise np.linalg.LinAlgError("Matrix is not positive definite")      # likelihood_func.py:175
         return float(nll[0])
     try:
+        holder.model.set_predict_refine(KrigInfo.get("predict_refine", "auto"))
         st = holder.model.fit_state(x, trainvar, fixed_nugget_of(KrigInfo))
     except _lib.KrigB200Error as e:
         if e.status == _lib.ERR_NOT_PD:

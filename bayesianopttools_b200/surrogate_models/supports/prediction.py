@@ -21,6 +21,8 @@ def _ensure_fitted(KrigInfo, holder):
     x = np.concatenate([theta, [np.log10(s2)], [nug]])
     if int(KrigInfo["nkernel"]) > 1:
         x = np.concatenate([x, np.asarray(KrigInfo["wgkf"], dtype=float).ravel()])
+    # KrigInfo["predict_refine"]: 'auto' (default) / False / True -- corrected sweeps on ill-conditioned fits
+    holder.model.set_predict_refine(KrigInfo.get("predict_refine", "auto"))
     holder.model.fit_state(x, True, nug, want_U=False, want_Psi=False)
     holder.fit_sig = sig
 

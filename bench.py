@@ -641,6 +641,15 @@ def cfg_sweep(cx, peak, hbm, fp64_peak, name, n, d, m, acq, cpu_m=20000, reps=3,
         res["r"] = mdl.predict_points(pts, (), acq=acq, ybest=float(y.min()))[1]
     ms = timed(torch, go, reps, warm=1)
     r = res["r"]
+    # an ill-conditioned fit (pivots at the nugget) sweeps through the corrected paths by default: time the plain
+    # explicit-inverse product too, so that the cost of the correction is on the record
+    refined, ms_plain = bool(mdl.predict_refined), None
+    if refined:
+        mdl.set_predict_refine(False)
+        mdl.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
+        ms_plain = timed(torch, go, reps, warm=1)
+        mdl.set_predict_refine("auto")
+        mdl.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
     # sampled check + CPU baseline: the first cpu_m sites of the same Philox stream
     xs = pts.rows(0, cpu_m)
     fit = ko.nll(th, X, y, F, full=True)
@@ -676,7 +685,13 @@ def cfg_sweep(cx, peak, hbm, fp64_peak, name, n, d, m, acq, cpu_m=20000, reps=3,
            "hbm": {"input_GBps": inb, "frac_of_measured_hbm": inb / hbm},
            "cpu_baseline": {"value": cpu_m / cpu_s, "unit": "points/s", "cores": blas_threads(), "kind": "port",
                             "sample": "%d sites" % cpu_m},
-           "check_on_sample": chk, "n_fail": int(r["n_fail"]), "min_idx": int(r["min_u_idx"] if acq == "u" else r["best_idx"])}
+           "check_on_sample": chk, "n_fail": int(r["n_fail"]), "min_idx": int(r["min_u_idx"] if acq == "u" else r["best_idx"]),
+           "ill_conditioned_fit": refined,
+           "explicit_inverse_product": ({"ms": ms_plain, "sites_per_s": m / ms_plain * 1e3,
+                                         "what": "the same sweep with the corrected paths switched off "
+                                                 "(KrigInfo['predict_refine'] = False): faster, 5-30x further from an "
+                                                 "exact evaluation of the variance on such fits (DESIGN section 2)"}
+                                        if refined else None)}
     return out
 
 

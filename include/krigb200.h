@@ -115,6 +115,20 @@ kb_status kb_model_set_trend(kb_model* m, const int* idx, int nind, int d);
  * (samplingplan.py:84-88); KB_NORM_STD p0=X_mean,p1=X_std (prediction.py:160). */
 kb_status kb_model_set_norm(kb_model* m, int norm_type, const double* p0, const double* p1);
 
+/* Accuracy of the sweeps on ILL-CONDITIONED fits.  prediction.py:222-224 obtains v = L^-1 psi by a triangular solve; the
+ * sweeps here multiply by the explicit inverse, which is one GEMM but, once the pivots of the factor reach down to the
+ * nugget (dense low-dimensional designs, smooth kernels), 5-30x further from an exact evaluation than the solve.
+ * kb_fit_state measures max / min of diag L and flags such fits (spread > 300); their sweeps then use the corrected
+ * paths (blocked forward substitution in the small-model kernel, one residual step per strip otherwise: 3x the tensor
+ * work of the strip kernel, 0-20 % on the small-model kernel).
+ *   KB_REFINE_AUTO (default)  corrected paths for flagged fits
+ *   KB_REFINE_OFF             always the plain product
+ *   KB_REFINE_ON              always the corrected paths
+ * Takes effect at the next kb_fit_state.  kb_model_predict_refined reports what the last fit chose (0 / 1). */
+enum { KB_REFINE_AUTO = -1, KB_REFINE_OFF = 0, KB_REFINE_ON = 1 };
+kb_status kb_model_set_predict_refine(kb_model* m, int mode);
+int kb_model_predict_refined(const kb_model* m);
+
 /* Output map of the predicted mean when the model was trained on normalised responses (KrigInfo["norm_y"],
  * prediction.py:213-217 -> stdtoreal :300-313): applied to f BEFORE every acquisition function, U and the AK-MCS
  * counters, exactly where the reference applies it; variance and s stay in the model's units, as in the reference.

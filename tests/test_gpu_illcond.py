@@ -62,3 +62,37 @@ def test_flagged_fit_predicts_as_accurately_as_a_triangular_solve(lib, n, d, ker
                               tol=1e-9, arbiter_tol=2e-9)
     assert res["best_idx"] == int(np.argmin(outs["pred"]))
     mdl.close()
+
+
+def test_predict_refine_switch(lib):
+    """kb_model_set_predict_refine / KrigInfo['predict_refine']: 'auto' flags an ill-conditioned fit and leaves a
+    well-conditioned one alone; False and True force the plain product / the corrected paths; the corrected variance is
+    the one closer to the 80-bit evaluation."""
+    rng = np.random.default_rng(77)
+    n, d = 150, 1
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(3 * X[:, 0]) + 0.05 * rng.standard_normal(n)
+    F = np.ones((n, 1))
+    x = np.array([0.3])
+    mdl = lib.DeviceModel(X, y, F, ["gaussian"])
+    mdl.set_norm(lib.NORM_NONE)
+    xq = rng.uniform(-1, 1, (2000, d))
+    idx = np.zeros((1, d), int)
+    tf = lt.nll(x, X, y, F, full=True, kernels=("gaussian",))
+    truth = lt.predict(xq, X, y, F, idx, tf, kernels=("gaussian",))["ssqr"]
+    err = {}
+    for mode, want in (("auto", True), (False, False), (True, True)):
+        mdl.set_predict_refine(mode)
+        mdl.fit_state(x, False, -6.0, want_U=False, want_Psi=False)
+        assert mdl.predict_refined is want, mode
+        outs, _ = mdl.predict(xq, ("ssqr",), acq="pred")
+        err[mode] = float(np.max(np.abs(outs["ssqr"] - truth)) / np.max(np.abs(truth)))
+    print(f"[achieved] ssqr from the 80-bit value: plain {err[False]:.1e}, corrected {err[True]:.1e}")
+    assert err["auto"] == err[True] and err[True] < err[False]
+    mdl.close()
+    # a well-conditioned design (d = 6) is not flagged
+    X6 = rng.uniform(-1, 1, (200, 6))
+    m6 = lib.DeviceModel(X6, np.sum(X6 ** 2, axis=1), np.ones((200, 1)), ["gaussian"])
+    m6.fit_state(np.full(6, 0.2), False, -6.0, want_U=False, want_Psi=False)
+    assert m6.predict_refined is False
+    m6.close()
