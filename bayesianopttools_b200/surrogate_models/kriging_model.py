@@ -97,24 +97,24 @@ def lbfgsb_lockstep(batch_nll, x0s, lbv, ubv, eps=1e-3, maxcor=10, ftol=2.220446
     idt = np.int32
     factr = ftol / np.finfo(float).eps
 
+    diag_i = np.arange(n)
+
     def stencils(xs):
         """(f, g) at every x of xs from one population: scipy's '2-point' rule with bounds (the step flips where
-        x + eps leaves the box), PENALTY for failed evaluations -- the arithmetic of Kriging._fun_and_grad."""
-        blocks, hs = [], []
-        for x in xs:
-            h = np.full(n, eps)
-            flip = (x + h > ubv) & (x - h >= lbv)
-            h[flip] = -eps
-            blocks.append(np.vstack([x[None, :], x[None, :] + np.diag(h)]))
-            hs.append(h)
-        f = np.asarray(batch_nll(np.vstack(blocks)))
-        f = np.where(np.isfinite(f), f, PENALTY)
-        out = []
-        for i, (pts, x) in enumerate(zip(blocks, xs)):
-            fi = f[i * (n + 1):(i + 1) * (n + 1)]
-            dx = (pts[1:, :] - x[None, :])[np.arange(n), np.arange(n)]
-            out.append((float(fi[0]), (fi[1:] - fi[0]) / dx))
-        return out
+        x + eps leaves the box), PENALTY for failed evaluations -- the arithmetic of Kriging._fun_and_grad.
+        Vectorised over the start points (the per-point numpy calls of a Python loop here were most of the host time of
+        a round on small designs: 120 us against 55 us of device call); the evaluation points and the differences are
+        formed by the same floating-point operations as before (x + 0.0 is x)."""
+        X = np.asarray(xs, dtype=np.float64).reshape(len(xs), n)
+        H = np.full(X.shape, eps)
+        H[(X + H > ubv) & (X - H >= lbv)] = -eps
+        pts = np.repeat(X[:, None, :], n + 1, axis=1)            # (P, n + 1, n): row 0 is x itself
+        stepped = X + H
+        pts[:, diag_i + 1, diag_i] = stepped
+        f = np.asarray(batch_nll(pts.reshape(-1, n)), dtype=np.float64)
+        f = np.where(np.isfinite(f), f, PENALTY).reshape(len(xs), n + 1)
+        G = (f[:, 1:] - f[:, :1]) / (stepped - X)
+        return [(float(f[i, 0]), G[i]) for i in range(len(xs))]
 
     st = []
     for r in range(R):
