@@ -661,10 +661,9 @@ kb_predict_warp_kernel(KbPredictArgs P) {
   constexpr int DD = D ? D : DW;
   // single-kernel designs: the weight of a dimension is folded into the coordinates once (x sqrt(gw) for the Gaussian,
   // x / theta otherwise), which leaves a subtract and an FMA (or add) per pair and dimension instead of three
-  // (not in the SUBST builds: differences of pre-scaled coordinates of two nearby sites carry the rounding of the two
-  // products, up to |x| / |x - t| times the error of the plain form -- harmless except on the ill-conditioned fits
-  // those builds exist for)
-  constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8) && !SUBST;
+  // (also in the SUBST builds: measured on the ill-conditioned designs of tools/illcond_check.py, the distance of the
+  // variance from an 80-bit evaluation is the same with and without the fold)
+  constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8);
   const int n = P.n, d = D ? D : P.d, n8 = (n + 7) & ~7, lda = n8 + 4;
   KbSweepResult* red = reinterpret_cast<KbSweepResult*>(smem_raw);
   double* swk = reinterpret_cast<double*>(smem_raw + sizeof(KbSweepResult) * 8);   // [4] (+4 pad)
