@@ -558,7 +558,11 @@ kb_status kb_fit_state(kb_model* m, const double* x, int nbhyp, int trainvar, do
     const int refine = ref_env ? (atoi(ref_env) > 0 ? 1 : 0)
                                : (m->pred_refine_mode >= 0 ? (m->pred_refine_mode > 0 ? 1 : 0) : (ill ? 1 : 0));
     if (refine) {
-      if (!m->LT) CK(kb_dev_malloc(&m->LT, sizeof(double) * (size_t)g.n_pad * m->ldat));
+      if (!m->LT) {
+        CK(kb_dev_malloc(&m->LT, sizeof(double) * (size_t)g.n_pad * m->ldat));
+        // (the strip kernel reads 128-column blocks: the columns past n_pad must hold zeros, not whatever was there)
+        CK(cudaMemsetAsync(m->LT, 0, sizeof(double) * (size_t)g.n_pad * m->ldat, m->stream));
+      }
       CK(kb_launch_fit_extract_factor(m->stream, g, m->fit.aug, m->LT, m->ldat));
       // ... and alpha, R^-1 F (formed with the explicit inverse) get one residual step against the factor
       double* res = nullptr;

@@ -489,7 +489,7 @@ kb_predict_kernel(KbPredictArgs P) {
                 sq[ni][1] = fma(v1, v1, sq[ni][1]);
               }
             }
-          } else if (!qin) {
+          } else if (!qin && pass == 0) {        // (the extra rows belong to the first pass: A = the fit state, B = psi)
             const int j = row - n_pad;
             if (j < P.qx) {
   #pragma unroll

@@ -28,7 +28,10 @@ def lib():
 # strip kernel proper; a handful of sites on a large model (the few-sites kernels stand aside for flagged fits)
 CASES = [(45, 1, "gaussian", 0, 5000), (60, 2, "matern52", 0, 3000), (110, 1, "matern32", 0, 4000),
          (126, 2, "gaussian", 0, 2500), (100, 2, "gaussian", 1, 2000), (378, 1, "gaussian", 0, 3000),
-         (617, 1, "matern52", 0, 300), (557, 2, "gaussian", 0, 40), (870, 1, "gaussian", 0, 2000)]
+         (617, 1, "matern52", 0, 300), (557, 2, "gaussian", 0, 40), (870, 1, "gaussian", 0, 2000),
+         # more than 8 regressors: the strip kernel forms psi' alpha and F' R^-1 psi as extra row blocks of its first pass
+         # (n_pad not a multiple of 128: the last row block of the corrected passes runs past the factor)
+         (162, 3, "gaussian", 2, 700), (300, 2, "gaussian", 3, 100), (500, 3, "gaussian", 2, 2500)]
 
 
 @pytest.mark.parametrize("n,d,kernel,order,m", CASES)
