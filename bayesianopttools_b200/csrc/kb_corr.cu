@@ -167,6 +167,9 @@ __device__ __forceinline__ void kb_stage_x_tiles(const double* __restrict__ XTi,
 // ---------------------------------------------------------------------------
 // Population build of the augmented matrices (one 64x64 tile per CTA).
 // ---------------------------------------------------------------------------
+#ifndef KB_BUILD_PRESCALE
+#define KB_BUILD_PRESCALE 1          // A/B build aid: 0 keeps the three-operation form in the population build
+#endif
 template <int MASK>
 __global__ void __launch_bounds__(KB_THREADS)
 kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ aug, int t_begin) {
@@ -191,7 +194,7 @@ kb_build_aug_kernel(KbModelDev m, KbAugGeom g, KbHyper hp, double* __restrict__ 
     const int tj = t - ti * (ti + 1) / 2;
     // single-kernel designs: the staged coordinates are multiplied by the candidate's per-dimension weight once
     // (128 d products per tile), which takes one of the three FP64 operations out of the 4096 d pair-dimension steps
-    constexpr bool PRE = (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8);
+    constexpr bool PRE = KB_BUILD_PRESCALE && (MASK == 1 || MASK == 2 || MASK == 4 || MASK == 8);
     for (int i = threadIdx.x; i < m.d; i += blockDim.x) {
       const double gwv = hp.gw[(size_t)b * m.d + i], ithv = hp.ith[(size_t)b * m.d + i];
       sgw[i] = PRE ? ((MASK == 1) ? sqrt(gwv) : ithv) : gwv;
