@@ -591,7 +591,7 @@ kb_predict_kernel(KbPredictArgs P) {
 }
 
 // ---------------------------------------------------------------------------
-// Warp-autonomous variant for very small models (n <= 64, d <= 8, ordinary Kriging): the AK-MCS
+// Warp-autonomous variant for small models (n <= 128, d <= 40, ordinary Kriging): the AK-MCS
 // population sweep (akmcs.py:77-89 over 1e8 points with tens of training points) is bound by the
 // exp() of the correlations, not by memory or the tensor pipe, so the goal is to keep every
 // issue slot busy: no CTA barrier in the loop, a warp owns 32 sites (one per lane), builds its
@@ -601,8 +601,8 @@ kb_predict_kernel(KbPredictArgs P) {
 #define PW_LDP 36          // padded psi row: 32 sites + 4 (== 4 mod 16 -> conflict-free B fragments)
 #define PW_MAXD 8           // widest design of the 8-warp kernel (128 registers per thread)
 #define PW_MAXD_WIDE 16     // ... of the 4-warp kernel (255 registers per thread): runtime-d loop
-#define PW_MAXD_XWIDE 40    // ... of its extra-wide build (hidimenRA, testcase/RA/testcase.py:81-88: 40 inputs): the lane's
-                            // 40 coordinates still live in registers, two correlation chains per lane
+#define PW_MAXD_XWIDE 40    // ... of its extra-wide builds (hidimenRA, testcase/RA/testcase.py:81-88: 40 inputs): the lane's
+                            // 40 coordinates still live in registers; widths padded to 24 / 32 / 40 (kb_pw_rows)
 
 // Up to 64 training sites: 8 warps per CTA, L^-1 as a full k-major matrix, two CTAs per SM.  65 .. 128 sites:
 // 4 warps per CTA (one per SM sub-partition), L^-1 packed as its lower 8x8 blocks, one CTA per SM -- the psi
