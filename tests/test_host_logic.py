@@ -22,6 +22,18 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert isinstance(lib.kb_device_count(), int)
 
 
+def test_header_enums_match_the_binding():
+    """The enum values of include/krigb200.h the Python binding restates (normalisation, y map, refine mode)."""
+    from bayesianopttools_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "krigb200.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(KB_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    assert (enums["KB_REFINE_AUTO"], enums["KB_REFINE_OFF"], enums["KB_REFINE_ON"]) == \
+        (_lib.REFINE_AUTO, _lib.REFINE_OFF, _lib.REFINE_ON)
+    for name, val in (("KB_NORM_DEFAULT", _lib.NORM_DEFAULT), ("KB_NORM_STD", _lib.NORM_STD), ("KB_NORM_NONE", _lib.NORM_NONE)):
+        if name in enums:
+            assert enums[name] == val, name
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "bayesianopttools_b200")
     for dp, _, files in os.walk(pkg):
